@@ -1,0 +1,10 @@
+"""dysgu_b200 - B200-native batched alignment engine for dysgu's SSW / edlib hot path.
+
+  dysgu_b200.scikitbio.StripedSmithWaterman   drop-in for dysgu.scikitbio._ssw_wrapper.StripedSmithWaterman
+  dysgu_b200.edlib.align                      drop-in for dysgu.edlib.align
+  dysgu_b200.batch.sw_align_batch / ed_align_batch   batched API (numpy CSR in, numpy out)
+  dysgu_b200.shard                            pair sharding over the GPUs of one box
+
+All compute happens in libdysgu_b200_align.so (CUDA, sm_100a).  There is no CPU fallback.
+"""
+__version__ = "0.1.0"

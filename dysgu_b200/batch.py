@@ -1,0 +1,149 @@
+"""Batched alignment API over the C ABI: numpy CSR batches in, numpy results out.
+
+This is the call a throughput-minded caller makes (SURVEY.md 8b "new batched ABI"); the drop-in
+classes in dysgu_b200.scikitbio / dysgu_b200.edlib are thin single-pair views over it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .workloads import SeqBatch
+
+SW_FIELDS = ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len")
+ED_MODES = {"NW": 0, "SHW": 1, "HW": 2}
+ED_TASKS = {"distance": 0, "locations": 1, "path": 2}
+ED_NO_START = -(2 ** 31)
+
+PAIR_STATUS = {0: "ok", 1: "empty sequence", 2: "8-bit score overflow with score_size=0", 3: "score does not fit int16",
+               4: "unsupported", 5: "device scratch exhausted"}
+
+
+def default_device() -> int:
+    return int(os.environ.get("DB200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def _as_batch(x) -> SeqBatch:
+    return x if isinstance(x, SeqBatch) else SeqBatch.from_list(x)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class SwResults:
+    """Results of a Smith-Waterman batch (fields follow s_align, ssw.h:38-48)."""
+
+    def __init__(self, fixed, cigar, cigar_off, status):
+        self.fixed = fixed          # int32 [n, 8]
+        self.cigar = cigar          # uint32 [total], BAM encoding
+        self.cigar_off = cigar_off  # int64 [n+1]
+        self.status = status        # int32 [n]
+
+    def __len__(self):
+        return self.fixed.shape[0]
+
+    def __getattr__(self, name):
+        if name in SW_FIELDS:
+            return self.fixed[:, SW_FIELDS.index(name)]
+        raise AttributeError(name)
+
+    def cigar_of(self, i):
+        return self.cigar[self.cigar_off[i]:self.cigar_off[i + 1]]
+
+    def cigar_str(self, i):
+        return "".join("%d%s" % (c >> 4, "MID"[c & 0xF]) for c in self.cigar_of(i))
+
+    def as_tuple(self, i):
+        return tuple(int(x) for x in self.fixed[i, :7]) + (self.cigar_str(i),)
+
+
+def sw_align_batch(queries, targets, match=2, mismatch=-3, gap_open=5, gap_extend=2, score_size=2, flag=1, filters=0,
+                   filterd=0, mask_len=None, matrix=None, device=None, want_cigar=True) -> SwResults:
+    """Align queries[i] (profiled sequence) against targets[i]; semantics of ssw_init + ssw_align per pair."""
+    q, t = _as_batch(queries), _as_batch(targets)
+    n = len(q)
+    if len(t) != n:
+        raise ValueError("queries and targets differ in length")
+    L = _lib.lib()
+    prm = _lib.SwParams()
+    prm.match, prm.mismatch, prm.gap_open, prm.gap_extend = match, mismatch, gap_open, gap_extend
+    prm.score_size, prm.flag, prm.filters, prm.filterd = score_size, flag, filters, filterd
+    mat_arr = None
+    if matrix is not None:
+        mat_arr = np.ascontiguousarray(matrix, dtype=np.int8).reshape(25)
+        prm.mat = mat_arr.ctypes.data_as(C.POINTER(C.c_int8))
+        prm.n = 5
+    ml = None if mask_len is None else np.ascontiguousarray(np.broadcast_to(np.asarray(mask_len, dtype=np.int32), (n,)))
+    fixed = np.zeros((n, 8), dtype=np.int32)
+    status = np.zeros(n, dtype=np.int32)
+    coff = np.zeros(n + 1, dtype=np.int64)
+    cap = int(q.off[-1] + t.off[-1] + 2 * n + 16) if want_cigar else 0
+    cigar = np.zeros(max(cap, 1), dtype=np.uint32)
+    qbuf = q.buf if q.buf.size else np.zeros(1, np.uint8)
+    tbuf = t.buf if t.buf.size else np.zeros(1, np.uint8)
+    rc = L.db200_sw_batch_host(default_device() if device is None else device, C.byref(prm), _ptr(qbuf), _ptr(q.off), _ptr(tbuf),
+                               _ptr(t.off), n, _ptr(ml), _ptr(fixed), _ptr(cigar) if want_cigar else None, cap, _ptr(coff),
+                               _ptr(status))
+    _lib.check(rc, "db200_sw_batch_host")
+    return SwResults(fixed, cigar[:coff[n]] if want_cigar else cigar[:0], coff, status)
+
+
+class EdResults:
+    """Results of an edit-distance batch (fields follow EdlibAlignResult, edlib.h:162-218)."""
+
+    def __init__(self, fixed, loc, loc_off):
+        self.fixed = fixed      # int32 [n,4]: status, editDistance, alphabetLength, numLocations
+        self.loc = loc          # int32 [total,2]: (start, end); start == ED_NO_START -> None
+        self.loc_off = loc_off
+
+    def __len__(self):
+        return self.fixed.shape[0]
+
+    @property
+    def edit_distance(self):
+        return self.fixed[:, 1]
+
+    def as_dict(self, i):
+        st, ed, al, nl = (int(x) for x in self.fixed[i])
+        locs = [(None if int(s) == ED_NO_START else int(s), int(e)) for s, e in self.loc[self.loc_off[i]:self.loc_off[i + 1]]]
+        return {"status": st, "editDistance": ed, "alphabetLength": al, "locations": locs}
+
+
+def ed_align_batch(queries, targets, mode="NW", task="distance", k=-1, additional_equalities=None, device=None) -> EdResults:
+    """edlib.align semantics per pair (edlib.pyx:57-156) for tasks 'distance' and 'locations'."""
+    q, t = _as_batch(queries), _as_batch(targets)
+    n = len(q)
+    if len(t) != n:
+        raise ValueError("queries and targets differ in length")
+    L = _lib.lib()
+    if not hasattr(L, "db200_ed_batch_host"):
+        raise _lib.AlignEngineError("this build of libdysgu_b200_align.so has no edit-distance entry points")
+    prm = _lib.EdParams()
+    prm.mode = ED_MODES[mode] if isinstance(mode, str) else int(mode)
+    prm.task = ED_TASKS[task] if isinstance(task, str) else int(task)
+    karr = None
+    if np.ndim(k) == 0:
+        prm.k = int(k)
+    else:
+        prm.k = -1
+        karr = np.ascontiguousarray(k, dtype=np.int32)
+    eq = None
+    if additional_equalities:
+        eq = b"".join(bytes([a if isinstance(a, int) else ord(a), b if isinstance(b, int) else ord(b)]) for a, b in additional_equalities)
+        prm.eq_pairs = eq
+        prm.n_eq_pairs = len(eq) // 2
+    fixed = np.zeros((n, 4), dtype=np.int32)
+    loff = np.zeros(n + 1, dtype=np.int64)
+    cap = int(t.off[-1] + 2 * n + 16)
+    loc = np.zeros((cap, 2), dtype=np.int32)
+    qbuf = q.buf if q.buf.size else np.zeros(1, np.uint8)
+    tbuf = t.buf if t.buf.size else np.zeros(1, np.uint8)
+    rc = L.db200_ed_batch_host(default_device() if device is None else device, C.byref(prm), _ptr(qbuf), _ptr(q.off), _ptr(tbuf),
+                               _ptr(t.off), n, _ptr(karr), _ptr(fixed), _ptr(loc), cap, _ptr(loff))
+    _lib.check(rc, "db200_ed_batch_host")
+    return EdResults(fixed, loc[:loff[n]], loff)

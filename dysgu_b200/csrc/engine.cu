@@ -1,0 +1,394 @@
+// Engine plumbing and the C ABI of libdysgu_b200_align.so (include/dysgu_b200_align.h).
+#include "engine.cuh"
+
+#include <stdarg.h>
+#include <stdlib.h>
+#include <unistd.h>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+namespace db200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- arena --------------------------------------------------------------------------------------
+void *Arena::alloc_bytes(size_t bytes)
+{
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes == 0) bytes = 256;
+    while (cur < nblocks) {
+        if (used + bytes <= blocks[cur].cap) {
+            void *p = blocks[cur].ptr + used;
+            used += bytes;
+            return p;
+        }
+        ++cur;
+        used = 0;
+    }
+    if (nblocks >= 64) return nullptr;
+    size_t cap = std::max(bytes, min_block);
+    char *p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) {
+        cudaGetLastError();
+        if (cap == bytes || cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cap = bytes;
+    }
+    blocks[nblocks].ptr = p;
+    blocks[nblocks].cap = cap;
+    cur = nblocks++;
+    used = bytes;
+    return p;
+}
+
+void Arena::release()
+{
+    for (int i = 0; i < nblocks; ++i) cudaFree(blocks[i].ptr);
+    nblocks = 0;
+    cur = 0;
+    used = 0;
+}
+
+// ---- engines (per process; re-created after fork because the pid changes) --------------------------
+static std::mutex g_mu;
+static Engine *g_engines[64] = {nullptr};
+static pid_t g_pid = 0;
+
+Engine *get_engine(int device)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_pid != getpid()) { // first use, or a fork()ed child: CUDA state of the parent is unusable here
+        for (auto &e : g_engines) e = nullptr;
+        g_pid = getpid();
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libdysgu_b200_align has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= count || device >= 64) { set_error("invalid device %d (have %d)", device, count); return nullptr; }
+    if (g_engines[device]) {
+        cudaSetDevice(device);
+        return g_engines[device];
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return nullptr; }
+    Engine *e = new Engine();
+    e->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); delete e; return nullptr; }
+    e->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        delete e;
+        return nullptr;
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
+    }
+    const char *mb = getenv("DB200_TRACE_POOL_MB");
+    e->trace_pool_bytes = (size_t)(mb ? atol(mb) : 1024) << 20;
+    if (e->trace_pool_bytes < ((size_t)16 << 20)) e->trace_pool_bytes = (size_t)16 << 20;
+    e->ready = true;
+    g_engines[device] = e;
+    return e;
+}
+
+// ---- exclusive scan (int32 -> int64), three small kernels ---------------------------------------------
+__global__ void scan_block_sums(const int32_t *in, int64_t n, int64_t *sums)
+{
+    __shared__ long long sh[32];
+    const int64_t base = (int64_t)blockIdx.x * 1024;
+    long long v = 0;
+    const int64_t i = base + threadIdx.x;
+    if (i < n) v = in[i];
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        long long w = sh[threadIdx.x];
+        for (int o = 16; o >= 1; o >>= 1) w += __shfl_xor_sync(0xFFFFFFFFu, w, o);
+        if (threadIdx.x == 0) sums[blockIdx.x] = w;
+    }
+}
+
+__global__ void scan_sums(int64_t *sums, int64_t nblocks)
+{
+    // single thread block, sequential over chunks of 1024 block sums
+    __shared__ long long sh[1024];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nblocks; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        long long v = i < nblocks ? sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            long long add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < nblocks) sums[i] = carry + sh[threadIdx.x] - v; // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[nblocks] = carry; // grand total
+}
+
+__global__ void scan_apply(const int32_t *in, int64_t n, const int64_t *sums, int64_t nblocks, int64_t *out)
+{
+    __shared__ long long sh[1024];
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    long long v = i < n ? in[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        long long add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    if (i < n) out[i] = sums[blockIdx.x] + sh[threadIdx.x] - v;
+    if (i == n - 1) out[n] = sums[nblocks];
+}
+
+void exclusive_scan_i32_i64(Engine *e, const int32_t *in, int64_t *out, int64_t n, int64_t *tmp, cudaStream_t st)
+{
+    if (n <= 0) return;
+    const int64_t nblocks = (n + 1023) / 1024;
+    scan_block_sums<<<(unsigned)nblocks, 1024, 0, st>>>(in, n, tmp);
+    scan_sums<<<1, 1024, 0, st>>>(tmp, nblocks);
+    scan_apply<<<(unsigned)nblocks, 1024, 0, st>>>(in, n, tmp, nblocks, out);
+    count_launch(e, 3);
+}
+
+}  // namespace db200
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+using namespace db200;
+
+extern "C" {
+
+int db200_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+int db200_init(int device) { return get_engine(device) ? DB200_OK : DB200_ERR_CUDA; }
+
+void db200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_pid != getpid()) return;
+    for (auto &e : g_engines) {
+        if (!e) continue;
+        cudaSetDevice(e->device);
+        cudaDeviceSynchronize();
+        for (int i = 0; i < 2; ++i) { e->arena[i].release(); e->io[i].release(); }
+        for (int i = 0; i < 2; ++i) if (e->pinned_out[i]) cudaFreeHost(e->pinned_out[i]);
+        if (e->pinned) cudaFreeHost(e->pinned);
+        cudaStreamDestroy(e->stream);
+        cudaStreamDestroy(e->copy_stream);
+        delete e;
+        e = nullptr;
+    }
+}
+
+const char *db200_last_error(void) { return g_err; }
+const char *db200_version(void) { return "dysgu_b200_align 0.1.0 (sm_100a)"; }
+
+int64_t db200_workspace_bytes(int device)
+{
+    Engine *e = get_engine(device);
+    if (!e) return -1;
+    return (int64_t)(e->arena[0].total() + e->arena[1].total() + e->io[0].total() + e->io[1].total());
+}
+
+int64_t db200_kernel_launches(int device, int reset)
+{
+    Engine *e = get_engine(device);
+    if (!e) return -1;
+    const int64_t n = e->launches;
+    if (reset) e->launches = 0;
+    return n;
+}
+
+void *db200_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostAlloc(%lld) failed", (long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void db200_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ---- Smith-Waterman -------------------------------------------------------------------------------
+int db200_sw_batch_device(int device, const db200_sw_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
+                          const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs, int32_t max_query_len,
+                          const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
+                          int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, void *stream)
+{
+    Engine *e = get_engine(device);
+    if (!e) return DB200_ERR_CUDA;
+    e->arena[0].reset();
+    return sw_batch_device_impl(e, e->arena[0], params, d_qbuf, d_qoff, q_bytes, d_tbuf, d_toff, t_bytes, npairs, max_query_len,
+                                d_mask_len, d_results, d_cigar_buf, cigar_cap, d_cigar_off, d_status, cigar_total,
+                                (cudaStream_t)stream);
+}
+
+// Host entry point: chunks of pairs are copied to the device, aligned and copied back.
+int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
+                        const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
+                        int64_t cigar_cap, int64_t *cigar_off, int32_t *status)
+{
+    Engine *e = get_engine(device);
+    if (!e) return DB200_ERR_CUDA;
+    if (npairs < 0 || !params || !qoff || !toff || !results) { set_error("sw_batch_host: bad arguments"); return DB200_ERR_ARG; }
+    if (cigar_off) cigar_off[0] = 0;
+    cudaStream_t st = e->stream;
+    const int64_t MAX_CHUNK_PAIRS = (int64_t)1 << 20;
+    const int64_t MAX_CHUNK_BYTES = (int64_t)3 << 30;
+    int64_t cig_written = 0;
+    std::vector<int64_t> offs;
+    for (int64_t c0 = 0; c0 < npairs;) {
+        int64_t c1 = c0;
+        int64_t bytes = 0;
+        int32_t maxq = 0;
+        while (c1 < npairs && c1 - c0 < MAX_CHUNK_PAIRS) {
+            const int64_t ql = qoff[c1 + 1] - qoff[c1], tl = toff[c1 + 1] - toff[c1];
+            if (ql < 0 || tl < 0 || ql > 0x7FFFFFF0 || tl > 0x7FFFFFF0) { set_error("sw_batch_host: bad offsets at pair %lld", (long long)c1); return DB200_ERR_ARG; }
+            if (c1 > c0 && bytes + ql + tl > MAX_CHUNK_BYTES) break;
+            bytes += ql + tl;
+            maxq = std::max<int32_t>(maxq, (int32_t)ql);
+            ++c1;
+        }
+        const int64_t n = c1 - c0;
+        const int64_t qb = qoff[c1] - qoff[c0], tb = toff[c1] - toff[c0];
+        offs.resize((size_t)(2 * (n + 1)));
+        for (int64_t i = 0; i <= n; ++i) { offs[(size_t)i] = qoff[c0 + i] - qoff[c0]; offs[(size_t)(n + 1 + i)] = toff[c0 + i] - toff[c0]; }
+        Arena &io = e->io[0];
+        io.reset();
+        e->arena[0].reset();
+        const int64_t cig_bound = std::min<int64_t>(cigar_buf ? std::max<int64_t>(cigar_cap - cig_written, 0) : 0, qb + tb + 2 * n);
+        uint8_t *d_q = io.alloc<uint8_t>((size_t)qb + 16), *d_t = io.alloc<uint8_t>((size_t)tb + 16);
+        int64_t *d_off = io.alloc<int64_t>((size_t)(2 * (n + 1)));
+        int32_t *d_mask = mask_len ? io.alloc<int32_t>((size_t)n) : nullptr;
+        db200_sw_result *d_res = io.alloc<db200_sw_result>((size_t)n);
+        int32_t *d_status = io.alloc<int32_t>((size_t)n);
+        int64_t *d_coff = io.alloc<int64_t>((size_t)n + 1);
+        uint32_t *d_cig = cigar_buf ? io.alloc<uint32_t>((size_t)cig_bound + 16) : nullptr;
+        if (!d_q || !d_t || !d_off || (mask_len && !d_mask) || !d_res || !d_status || !d_coff || (cigar_buf && !d_cig)) {
+            set_error("sw_batch_host: device allocation failed");
+            return DB200_ERR_NOMEM;
+        }
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_q, qbuf + qoff[c0], (size_t)qb, cudaMemcpyHostToDevice, st));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_t, tbuf + toff[c0], (size_t)tb, cudaMemcpyHostToDevice, st));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_off, offs.data(), sizeof(int64_t) * (size_t)(2 * (n + 1)), cudaMemcpyHostToDevice, st));
+        if (mask_len) DB200_CUDA_CHECK(cudaMemcpyAsync(d_mask, mask_len + c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        int64_t total = 0;
+        int rc = sw_batch_device_impl(e, e->arena[0], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, d_mask, d_res, d_cig,
+                                      cig_bound, d_coff, d_status, &total, st);
+        if (rc) return rc;
+        DB200_CUDA_CHECK(cudaMemcpyAsync(results + c0, d_res, sizeof(db200_sw_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (status) DB200_CUDA_CHECK(cudaMemcpyAsync(status + c0, d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (cigar_off) DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_off + c0, d_coff, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+        if (cigar_buf) {
+            if (total > cig_bound) { cudaStreamSynchronize(st); set_error("sw_batch_host: cigar buffer too small"); return DB200_ERR_CAPACITY; }
+            if (total > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_buf + cig_written, d_cig, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+        }
+        DB200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (cigar_off && cig_written) for (int64_t i = 0; i <= n; ++i) cigar_off[c0 + i] += cig_written;
+        cig_written += total;
+        c0 = c1;
+    }
+    if (cigar_off) cigar_off[npairs] = cig_written;
+    return DB200_OK;
+}
+
+// ---- legacy single-pair SW entry points (ssw.h:72-125) --------------------------------------------------
+struct db200_s_profile {
+    std::vector<uint8_t> read_ascii;
+    int8_t mat[25];
+    int32_t n;
+    int8_t score_size;
+};
+
+static const char CODE2ASCII[6] = {'A', 'C', 'G', 'T', 'N', 'N'};
+
+db200_s_profile *db200_ssw_init(const int8_t *read, int32_t readLen, const int8_t *mat, int32_t n, int8_t score_size)
+{
+    if (!read || !mat || n != 5 || readLen < 0) { set_error("ssw_init: only 5x5 nucleotide matrices are supported"); return nullptr; }
+    db200_s_profile *p = new db200_s_profile();
+    p->read_ascii.resize((size_t)readLen);
+    for (int32_t i = 0; i < readLen; ++i) p->read_ascii[(size_t)i] = (uint8_t)CODE2ASCII[read[i] >= 0 && read[i] < 5 ? read[i] : 4];
+    memcpy(p->mat, mat, 25);
+    p->n = n;
+    p->score_size = score_size;
+    return p;
+}
+
+void db200_init_destroy(db200_s_profile *p) { delete p; }
+
+db200_s_align *db200_ssw_align(const db200_s_profile *prof, const int8_t *ref, int32_t refLen, uint8_t weight_gapO, uint8_t weight_gapE,
+                               uint8_t flag, uint16_t filters, int32_t filterd, int32_t maskLen)
+{
+    if (!prof || !ref || refLen < 0) { set_error("ssw_align: bad arguments"); return nullptr; }
+    std::vector<uint8_t> t((size_t)refLen);
+    for (int32_t i = 0; i < refLen; ++i) t[(size_t)i] = (uint8_t)CODE2ASCII[ref[i] >= 0 && ref[i] < 5 ? ref[i] : 4];
+    db200_sw_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.mat = prof->mat; prm.n = 5;
+    prm.gap_open = weight_gapO; prm.gap_extend = weight_gapE; prm.score_size = prof->score_size;
+    prm.flag = flag; prm.filters = filters; prm.filterd = filterd;
+    int64_t qoff[2] = {0, (int64_t)prof->read_ascii.size()}, toff[2] = {0, refLen};
+    db200_sw_result r;
+    int32_t status = 0;
+    int64_t coff[2] = {0, 0};
+    std::vector<uint32_t> cig((size_t)(qoff[1] + toff[1] + 4));
+    int rc = db200_sw_batch_host(0, &prm, prof->read_ascii.data(), qoff, t.data(), toff, 1, &maskLen, &r, cig.data(), (int64_t)cig.size(),
+                                 coff, &status);
+    if (rc != DB200_OK || status != DB200_PAIR_OK) return nullptr; // as ssw_align does on error (ssw.c:803-812)
+    db200_s_align *a = (db200_s_align *)calloc(1, sizeof(db200_s_align));
+    a->score1 = (uint16_t)r.score1; a->score2 = (uint16_t)r.score2;
+    a->ref_begin1 = r.ref_begin1; a->ref_end1 = r.ref_end1; a->read_begin1 = r.read_begin1; a->read_end1 = r.read_end1;
+    a->ref_end2 = r.ref_end2;
+    a->cigarLen = r.cigar_len;
+    if (r.cigar_len > 0) {
+        a->cigar = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)r.cigar_len);
+        memcpy(a->cigar, cig.data(), sizeof(uint32_t) * (size_t)r.cigar_len);
+    }
+    return a;
+}
+
+void db200_align_destroy(db200_s_align *a)
+{
+    if (!a) return;
+    free(a->cigar);
+    free(a);
+}
+
+}  // extern "C"

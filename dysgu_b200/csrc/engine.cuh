@@ -1,0 +1,82 @@
+// Shared engine plumbing for libdysgu_b200_align.so: per-device state, grow-only workspace arena,
+// error reporting, launch counting and a small device-side exclusive scan.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <algorithm>
+
+#include "../../include/dysgu_b200_align.h"
+
+namespace db200 {
+
+void set_error(const char *fmt, ...);
+
+#define DB200_CUDA_CHECK(expr)                                                                       \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            db200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return DB200_ERR_CUDA;                                                                   \
+        }                                                                                            \
+    } while (0)
+
+// Grow-only device arena made of cudaMalloc'd blocks that never move.  A batch call resets the
+// cursor and carves regions; a request that does not fit the remaining blocks adds a block
+// (device-synchronising cudaMalloc), which only happens while batch sizes are still increasing.
+struct Arena {
+    struct Block { char *ptr; size_t cap; };
+    Block blocks[64];
+    int nblocks = 0;
+    int cur = 0;
+    size_t used = 0;
+    size_t min_block = (size_t)64 << 20;
+
+    void reset() { cur = 0; used = 0; }
+    size_t total() const { size_t t = 0; for (int i = 0; i < nblocks; ++i) t += blocks[i].cap; return t; }
+    void *alloc_bytes(size_t bytes);
+    void release();
+    template <typename T>
+    T *alloc(size_t count) { return reinterpret_cast<T *>(alloc_bytes(count * sizeof(T))); }
+};
+
+struct Engine {
+    int device = -1;
+    bool ready = false;
+    cudaStream_t stream = nullptr;       // used by the *_host entry points
+    cudaStream_t copy_stream = nullptr;  // H2D prefetch of the next chunk
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    Arena arena[2];                      // compute workspace (one per in-flight chunk)
+    Arena io[2];                         // device copies of host inputs / outputs (one per in-flight chunk)
+    int64_t launches = 0;
+    int sm_count = 0;
+    void *pinned = nullptr;              // small pinned scratch (counters read back from the device)
+    size_t pinned_cap = 0;
+    void *pinned_out[2] = {nullptr, nullptr};
+    size_t pinned_out_cap[2] = {0, 0};
+    size_t trace_pool_bytes = (size_t)1 << 30;  // scratch of the banded traceback (DB200_TRACE_POOL_MB)
+};
+
+Engine *get_engine(int device);  // nullptr + error set on failure
+
+inline void count_launch(Engine *e, int n = 1) { e->launches += n; }
+
+// Exclusive scan of int32 counts into int64 offsets (offsets[n] = total).  n up to 2^31.
+// tmp must hold ceil(n / 1024) + 1 int64 values.
+void exclusive_scan_i32_i64(Engine *e, const int32_t *in, int64_t *out, int64_t n, int64_t *tmp, cudaStream_t st);
+inline size_t scan_tmp_count(int64_t n) { return (size_t)((n + 1023) / 1024 + 2); }
+
+int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff,
+                         int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
+                         int32_t max_query_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
+                         int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st);
+
+int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff,
+                         int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
+                         int32_t max_query_len, int32_t max_target_len, const int32_t *d_k, db200_ed_result *d_results, int32_t *d_loc_buf, int64_t loc_cap,
+                         int64_t *d_loc_off, int64_t *loc_total, cudaStream_t st);
+
+}  // namespace db200

@@ -1,0 +1,758 @@
+// Batched Smith-Waterman pipeline on the device: encode/pack -> bucket -> scoring pass ->
+// (re-run of ambiguous pairs) -> reversed extraction -> reverse scoring pass -> second-best /
+// finalize -> banded traceback -> cigar compaction.  Host side only enqueues kernels.
+//
+// Reference behaviour being reproduced (dysgu v1.9.0):
+//   _ssw_wrapper.pyx:60-68 (encoding), 583-588 (mask length), ssw.c:772-857 (driver),
+//   ssw.c:124-346 / 372-548 (scoring passes), ssw.c:550-728 (banded traceback).
+#include "sw_kernels.cuh"
+
+namespace db200 {
+
+// ------------------------------------------------------------------------------------------------
+// kernel configurations: index -> (K columns per virtual lane, G threads per pair)
+// ------------------------------------------------------------------------------------------------
+static const int CFG_K[SW_NCFG] = {16, 16, 16, 16, 16, 16, 32};
+static const int CFG_G[SW_NCFG] = {1, 2, 4, 8, 16, 32, 32};
+__device__ __constant__ int d_cfg_cap[SW_NCFG] = {32, 64, 128, 256, 512, 1024, 2048};
+
+struct PairState {          // per-pair bookkeeping of the pipeline
+    int32_t mask_len;
+    int32_t need_colmax;
+    int32_t use_word;
+    int32_t status;
+    int32_t want_rev;       // reverse pass required
+    int32_t want_cigar;     // traceback required
+    int32_t cigar_len;
+    int32_t pad_;
+    int64_t cigar_pos;      // position in the cigar pool
+};
+
+// ------------------------------------------------------------------------------------------------
+// 1. sequence units + packing (ASCII -> 4-bit codes, _ssw_wrapper.pyx:60-68)
+// ------------------------------------------------------------------------------------------------
+__global__ void sw_units_kernel(const int64_t *qoff, const int64_t *toff, int64_t npairs, int32_t *units)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= 2 * npairs) return;
+    const int64_t *off = i < npairs ? qoff : toff;
+    int64_t p = i < npairs ? i : i - npairs;
+    int64_t len = off[p + 1] - off[p];
+    units[i] = (int32_t)((len + 31) >> 5);
+}
+
+__device__ __forceinline__ uint32_t nt_code(uint8_t ch)
+{
+    switch (ch) {
+        case 'A': case 'a': case 'U': case 'u': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
+
+// one warp per sequence; each lane packs 8 bases into one 32-bit word per iteration
+__global__ void sw_pack_kernel(const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf, const int64_t *toff,
+                               int64_t npairs, const int64_t *unit_off, uint32_t *pool, PairMeta *meta)
+{
+    const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= 2 * npairs) return;
+    const bool isq = wid < npairs;
+    const int64_t p = isq ? wid : wid - npairs;
+    const int64_t *off = isq ? qoff : toff;
+    const uint8_t *src = (isq ? qbuf : tbuf) + off[p];
+    const int64_t len = off[p + 1] - off[p];
+    const int64_t u0 = unit_off[wid];
+    const int64_t nwords = ((len + 31) >> 5) << 2;
+    uint32_t *dst = pool + u0 * 4;
+    for (int64_t w = lane; w < nwords; w += 32) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int64_t i = w * 8 + e;
+            const uint32_t c = i < len ? nt_code(src[i]) : (uint32_t)SW_PAD_CODE;
+            x |= c << (4 * e);
+        }
+        dst[w] = x;
+    }
+    if (lane == 0) {
+        if (isq) { meta[p].q_unit = (uint32_t)u0; meta[p].m = (int32_t)len; }
+        else { meta[p].t_unit = (uint32_t)u0; meta[p].n = (int32_t)len; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. bucketing: counting sort of pairs by (config, needs column maxima, descending length bin)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sw_cfg_for(int n)
+{
+    int c = 0;
+    while (c < SW_NCFG - 1 && d_cfg_cap[c] < n) ++c;
+    return c;
+}
+
+__device__ __forceinline__ int sw_bin_key(int m, int n, int need_colmax)
+{
+    const int c = sw_cfg_for(n);
+    const int lb = min(m >> 5, SW_LBINS - 1);
+    return ((c * 2 + need_colmax) * SW_LBINS) + (SW_LBINS - 1 - lb);
+}
+
+struct InitArgs {
+    const PairMeta *meta;
+    const int32_t *mask_len;   // may be null -> auto
+    PairState *state;
+    int64_t npairs;
+    int32_t max_match;         // largest matrix entry
+    int32_t flag;
+};
+
+// per pair: status, mask length, colmax need, histogram of forward bins
+__global__ void sw_init_kernel(InitArgs a, int32_t *hist)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= a.npairs) return;
+    const PairMeta pm = a.meta[p];
+    PairState s;
+    memset(&s, 0, sizeof(s));
+    s.mask_len = a.mask_len ? a.mask_len[p] : max(pm.m / 2, 15);
+    s.status = DB200_PAIR_OK;
+    if (pm.m <= 0 || pm.n <= 0) s.status = DB200_PAIR_EMPTY;
+    else if ((int64_t)a.max_match * min(pm.m, pm.n) > 30000) s.status = DB200_PAIR_SCORE_RANGE;
+    // column maxima are only needed when a column can fall outside the mask window (ssw.c:326-341)
+    s.need_colmax = (s.mask_len >= 15 && pm.n > s.mask_len - 1) ? 1 : 0;
+    a.state[p] = s;
+    if (s.status == DB200_PAIR_OK) atomicAdd(&hist[sw_bin_key(pm.m, pm.n, s.need_colmax)], 1);
+}
+
+// single block: exclusive scan of the bin histogram, segment ranges
+__global__ void sw_binscan_kernel(const int32_t *hist, int32_t *bin_start, int32_t *seg_begin, int32_t *seg_count)
+{
+    __shared__ int32_t seg_tot[SW_NSEG];
+    __shared__ int32_t seg_off[SW_NSEG + 1];
+    const int tid = threadIdx.x;
+    if (tid < SW_NSEG) {
+        int s = 0;
+        for (int b = 0; b < SW_LBINS; ++b) s += hist[tid * SW_LBINS + b];
+        seg_tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int s = 0; s < SW_NSEG; ++s) { seg_off[s] = acc; acc += seg_tot[s]; }
+        seg_off[SW_NSEG] = acc;
+    }
+    __syncthreads();
+    if (tid < SW_NSEG) {
+        seg_begin[tid] = seg_off[tid];
+        seg_count[tid] = seg_tot[tid];
+        int acc = seg_off[tid];
+        for (int b = 0; b < SW_LBINS; ++b) {
+            bin_start[tid * SW_LBINS + b] = acc;
+            acc += hist[tid * SW_LBINS + b];
+        }
+    }
+}
+
+__global__ void sw_scatter_kernel(const PairMeta *meta, const PairState *state, int64_t npairs, int which,
+                                  const int32_t *bin_start, int32_t *bin_fill, int32_t *tasks)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const PairState &s = state[p];
+    if (s.status != DB200_PAIR_OK) return;
+    if (which == 1 && !s.want_rev) return;
+    const PairMeta pm = meta[p];
+    const int key = sw_bin_key(pm.m, pm.n, which == 0 ? s.need_colmax : 0);
+    const int pos = bin_start[key] + atomicAdd(&bin_fill[key], 1);
+    tasks[pos] = (int32_t)p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. after the forward pass: decide what else a pair needs, build the reversed problem
+//    (ssw.c:825-841: flag handling; ssw.c:827-835: reversed read prefix, columns ref_end1..0)
+// ------------------------------------------------------------------------------------------------
+struct MidArgs {
+    const PassOut *fwd;
+    const PairMeta *meta;
+    PairMeta *rmeta;
+    PairState *state;
+    int64_t npairs;
+    int32_t bias, score_size, flag, filters;
+    int32_t max_match, gap_open, gap_extend;
+    uint32_t *unit_cursor;   // bump allocator for reversed sequences (units)
+    uint32_t unit_base;
+};
+
+__global__ void sw_mid_kernel(MidArgs a, int32_t *hist)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= a.npairs) return;
+    PairState &s = a.state[p];
+    if (s.status != DB200_PAIR_OK) return;
+    const PairMeta pm = a.meta[p];
+    const PassOut fw = a.fwd[p];
+    const int score = fw.score;
+    const bool overflow8 = score + a.bias >= 255;
+    s.use_word = (a.score_size == 1) || (a.score_size == 2 && overflow8);
+    if (a.score_size == 0 && overflow8) { s.status = DB200_PAIR_OVERFLOW; return; }
+    const bool want_begin = !(a.flag == 0 || (a.flag == 2 && score < a.filters));
+    s.want_rev = 0;
+    s.want_cigar = 0;
+    if (!want_begin) return;
+    if (score == 0) return; // degenerate: handled in finalize (no cells to walk)
+    s.want_rev = 1;
+    // rows the reverse pass can possibly need: the alignment spans at most tspan columns and
+    // g query-only gap bases with  score <= max_match*tspan - (gap_open + (g-1)*gap_extend)
+    const int tspan = fw.end_t + 1;
+    int g = (a.max_match * tspan - score - a.gap_open) / a.gap_extend + 1;
+    if (a.max_match * tspan - score - a.gap_open < 0) g = 0;
+    const int rows = min(fw.end_q + 1, tspan + max(g, 0));
+    const uint32_t uq = (uint32_t)((rows + 31) >> 5), ut = (uint32_t)((tspan + 31) >> 5);
+    const uint32_t u0 = a.unit_base + atomicAdd(a.unit_cursor, uq + ut);
+    PairMeta r;
+    r.q_unit = u0; r.t_unit = u0 + uq; r.m = rows; r.n = tspan;
+    a.rmeta[p] = r;
+    atomicAdd(&hist[sw_bin_key(r.m, r.n, 0)], 1);
+}
+
+// one warp per pair: write reversed prefixes as packed codes
+__global__ void sw_reverse_extract_kernel(const PairMeta *meta, const PairMeta *rmeta, const PairState *state,
+                                          const PassOut *fwd, int64_t npairs, uint32_t *pool)
+{
+    const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= npairs) return;
+    const PairState &s = state[p];
+    if (s.status != DB200_PAIR_OK || !s.want_rev) return;
+    const PairMeta pm = meta[p], r = rmeta[p];
+    const PassOut fw = fwd[p];
+    const uint4 *pool4 = reinterpret_cast<const uint4 *>(pool);
+    {   // reversed query prefix: R[i] = Q[end_q - i], i < r.m
+        uint32_t *dst = pool + (size_t)r.q_unit * 4;
+        const int nwords = ((r.m + 31) >> 5) << 2;
+        for (int w = lane; w < nwords; w += 32) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int i = w * 8 + e;
+                const uint32_t c = i < r.m ? (uint32_t)pool_code(pool4, pm.q_unit, fw.end_q - i) : (uint32_t)SW_PAD_CODE;
+                x |= c << (4 * e);
+            }
+            dst[w] = x;
+        }
+    }
+    {   // reversed target prefix: R[j] = T[end_t - j], j < r.n
+        uint32_t *dst = pool + (size_t)r.t_unit * 4;
+        const int nwords = ((r.n + 31) >> 5) << 2;
+        for (int w = lane; w < nwords; w += 32) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int j = w * 8 + e;
+                const uint32_t c = j < r.n ? (uint32_t)pool_code(pool4, pm.t_unit, fw.end_t - j) : (uint32_t)SW_PAD_CODE;
+                x |= c << (4 * e);
+            }
+            dst[w] = x;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. finalize: coordinates, second best (ssw.c:326-341 / 530-543 incl. the padded profile rows,
+//    ssw.c:109 / 364), flags -> traceback request
+// ------------------------------------------------------------------------------------------------
+struct FinalArgs {
+    const PassOut *fwd;
+    const PassOut *rev;
+    const PairMeta *meta;
+    PairState *state;
+    const int16_t *colmax;
+    const int64_t *colmax_off;
+    db200_sw_result *results;
+    int32_t *status_out;
+    int64_t npairs;
+    int32_t flag, filters, filterd;
+};
+
+__global__ void sw_finalize_kernel(FinalArgs a)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= a.npairs) return;
+    PairState &s = a.state[p];
+    db200_sw_result r;
+    r.score1 = 0; r.score2 = 0; r.ref_begin1 = -1; r.ref_end1 = -1; r.read_begin1 = -1; r.read_end1 = -1;
+    r.ref_end2 = 0; r.cigar_len = 0;
+    if (s.status != DB200_PAIR_OK) {
+        a.results[p] = r;
+        if (a.status_out) a.status_out[p] = s.status;
+        return;
+    }
+    const PairMeta pm = a.meta[p];
+    const PassOut fw = a.fwd[p], rv = a.rev[p];
+    const int score = fw.score;
+    r.score1 = score;
+    if (score == 0) {
+        // no positive cell: ssw.c:146 (8-bit: end_ref stays -1) vs ssw.c:389 (16-bit: 0); read end collapses to 0
+        r.ref_end1 = s.use_word ? 0 : -1;
+        r.read_end1 = 0;
+    } else {
+        r.ref_end1 = fw.end_t;
+        r.read_end1 = fw.end_q;
+    }
+    // ---- second best ----------------------------------------------------------------------------
+    if (s.mask_len < 15) { r.score2 = 0; r.ref_end2 = -1; }
+    else if (s.need_colmax && score > 0) {
+        const int16_t *cm = a.colmax + a.colmax_off[p];
+        const int16_t *lr = cm + pm.n;
+        const int L = s.use_word ? 8 : 16;
+        const int P = ((pm.m + L - 1) / L) * L - pm.m; // padded profile rows
+        int best = 0, bref = 0;
+        int edge = max(r.ref_end1 - s.mask_len, 0);
+        for (int j = 0; j < edge; ++j) {
+            int x = cm[j];
+            for (int k = 0; k < P && j - 1 - k >= 0; ++k) x = max(x, (int)lr[j - 1 - k]);
+            if (x > best) { best = x; bref = j; }
+        }
+        edge = min(r.ref_end1 + s.mask_len, pm.n);
+        for (int j = edge + (s.use_word ? 0 : 1); j < pm.n; ++j) {
+            int x = cm[j];
+            for (int k = 0; k < P && j - 1 - k >= 0; ++k) x = max(x, (int)lr[j - 1 - k]);
+            if (x > best) { best = x; bref = j; }
+        }
+        r.score2 = best;
+        r.ref_end2 = bref;
+    }
+    // ---- begin coordinates ------------------------------------------------------------------------
+    const bool want_begin = !(a.flag == 0 || (a.flag == 2 && score < a.filters));
+    s.want_cigar = 0;
+    if (want_begin) {
+        if (score == 0) {
+            // reverse pass over zero (8-bit) or one (16-bit) column: ssw.c:828-839
+            r.ref_begin1 = s.use_word ? 0 : -1;
+            r.read_begin1 = 0;
+        } else {
+            r.ref_begin1 = fw.end_t - rv.end_t;
+            r.read_begin1 = fw.end_q - rv.end_q;
+        }
+        const bool stop = ((7 & a.flag) == 0) || ((2 & a.flag) != 0 && score < a.filters) ||
+                          ((4 & a.flag) != 0 && (r.ref_end1 - r.ref_begin1 > a.filterd || r.read_end1 - r.read_begin1 > a.filterd));
+        if (!stop) s.want_cigar = 1;
+    }
+    a.results[p] = r;
+    if (a.status_out) a.status_out[p] = s.status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 5. banded traceback, one thread per pair (behaviour of banded_sw, ssw.c:550-728)
+// ------------------------------------------------------------------------------------------------
+struct TraceArgs {
+    const uint4 *pool;
+    const PairMeta *meta;
+    PairState *state;
+    db200_sw_result *results;
+    int64_t npairs;
+    SwScoring sc;
+    uint8_t *scratch;              // bump-allocated per attempt: direction nibbles + rolling rows
+    unsigned long long *scratch_cursor;
+    unsigned long long scratch_cap;
+    uint32_t *cigar_pool;
+    unsigned long long *cigar_cursor;
+    unsigned long long cigar_cap;
+    int32_t *overflow_flag;
+};
+
+// direction nibble: bits 0-1 = H source (0 diagonal, 1 vertical state E, 2 horizontal state F),
+// bit 2 = E opened from H (code 3) else extended (2), bit 3 = F opened from H (code 5) else extended (4)
+__global__ void __launch_bounds__(128) sw_traceback_kernel(TraceArgs a)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= a.npairs) return;
+    PairState &s = a.state[p];
+    if (s.status != DB200_PAIR_OK || !s.want_cigar) return;
+    db200_sw_result &res = a.results[p];
+    const PairMeta pm = a.meta[p];
+    if (res.score1 == 0) {
+        // 1x1 rectangle with score 0: the reference's only observable output is 1M (ssw.c:844-847, 690-698)
+        const unsigned long long pos = atomicAdd(a.cigar_cursor, 1ull);
+        if (pos + 1 > a.cigar_cap) { atomicExch(a.overflow_flag, 1); s.status = DB200_PAIR_NOSCRATCH; return; }
+        a.cigar_pool[pos] = 16u;
+        s.cigar_pos = (int64_t)pos;
+        s.cigar_len = 1;
+        res.cigar_len = 1;
+        return;
+    }
+    const int refLen = res.ref_end1 - res.ref_begin1 + 1;    // columns j
+    const int readLen = res.read_end1 - res.read_begin1 + 1; // rows i
+    const int score = res.score1;
+    const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
+    int bw = abs(refLen - readLen) + 1;
+    uint8_t *dir = nullptr;
+    int width = 0;
+    while (true) {
+        width = min(2 * bw + 1, refLen);
+        // scratch per attempt: direction nibbles + two rolling rows of (H, E), band-relative
+        const unsigned long long dir_bytes = ((((unsigned long long)readLen * (unsigned long long)width + 1) / 2) + 15) & ~15ull;
+        const unsigned long long row_bytes = (unsigned long long)(width + 2) * 4ull * sizeof(int32_t);
+        const unsigned long long need = dir_bytes + row_bytes;
+        const unsigned long long off = atomicAdd(a.scratch_cursor, need);
+        if (off + need > a.scratch_cap) { atomicExch(a.overflow_flag, 2); s.status = DB200_PAIR_NOSCRATCH; return; }
+        dir = a.scratch + off;
+        int32_t *Hp = reinterpret_cast<int32_t *>(a.scratch + off + dir_bytes);
+        int32_t *Ep = Hp + (width + 2), *Hc = Ep + (width + 2), *Ec = Hc + (width + 2);
+        int best = 0;
+        int pbeg = 0, pend = -1;
+        for (int i = 0; i < readLen; ++i) {
+            const int beg = max(0, i - bw), end = min(refLen - 1, i + bw);
+            const int qc = pool_code(a.pool, pm.q_unit, res.read_begin1 + i);
+            int f = 0, hleft = 0;
+            const unsigned long long rowbase = (unsigned long long)i * (unsigned long long)width;
+            for (int j = beg; j <= end; ++j) {
+                const bool up_in = (i > 0 && j >= pbeg && j <= pend);
+                const bool dg_in = (i > 0 && j - 1 >= pbeg && j - 1 <= pend);
+                const int hup = up_in ? Hp[j - pbeg] : 0, eup = up_in ? Ep[j - pbeg] : 0;
+                const int hdg = dg_in ? Hp[j - 1 - pbeg] : 0;
+                int t1 = (i == 0) ? -gapO : hup - gapO;
+                int t2 = (i == 0) ? -gapE : eup - gapE;
+                const int e = t1 > t2 ? t1 : t2;
+                const int e_open = t1 > t2;
+                t1 = hleft - gapO;
+                t2 = f - gapE;
+                f = t1 > t2 ? t1 : t2;
+                const int f_open = t1 > t2;
+                const int e1 = e > 0 ? e : 0, f1 = f > 0 ? f : 0;
+                const int g = e1 > f1 ? e1 : f1;
+                const int tc = pool_code(a.pool, pm.t_unit, res.ref_begin1 + j);
+                const int d = hdg + a.sc.mat[tc * 6 + qc];
+                const int h = g > d ? g : d;
+                if (h > best) best = h;
+                const int src = (g <= d) ? 0 : (e1 > f1 ? 1 : 2);
+                const uint8_t nib = (uint8_t)(src | (e_open << 2) | (f_open << 3));
+                const unsigned long long cell = rowbase + (unsigned long long)(j - beg);
+                uint8_t &byte = dir[cell >> 1];
+                byte = (cell & 1) ? (uint8_t)((byte & 0x0F) | (nib << 4)) : (uint8_t)((byte & 0xF0) | nib);
+                Hc[j - beg] = h; Ec[j - beg] = e;
+                hleft = h;
+            }
+            int32_t *t = Hp; Hp = Hc; Hc = t;
+            t = Ep; Ep = Ec; Ec = t;
+            pbeg = beg; pend = end;
+        }
+        if (best >= score) break;
+        bw *= 2;
+    }
+    // ---- walk twice: first count the runs, then write them in final (reversed) order ------------------
+    int ncig = 0;
+    unsigned long long cpos = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        int i = readLen - 1, j = refLen - 1;
+        int run = 0, prev = 0, op = 0, state = 2; // state: 0 = in E, 1 = in F, 2 = in H
+        int l = 0;
+        bool bad = false;
+        while (i > 0) {
+            const int beg = max(0, i - bw);
+            const int x = j - beg;
+            if (x < 0 || x >= width || j < 0) { bad = true; break; } // the reference would read out of bounds here
+            const unsigned long long cell = (unsigned long long)i * (unsigned long long)width + (unsigned long long)x;
+            const int nib = (dir[cell >> 1] >> ((cell & 1) * 4)) & 15;
+            int code;
+            if (state == 2) { const int src = nib & 3; code = src == 0 ? 1 : (src == 1 ? ((nib & 4) ? 3 : 2) : ((nib & 8) ? 5 : 4)); }
+            else if (state == 0) code = (nib & 4) ? 3 : 2;
+            else code = (nib & 8) ? 5 : 4;
+            switch (code) {
+                case 1: --i; --j; state = 2; op = 0; break;
+                case 2: --i; state = 0; op = 1; break;
+                case 3: --i; state = 2; op = 1; break;
+                case 4: --j; state = 1; op = 2; break;
+                default: --j; state = 2; op = 2; break;
+            }
+            if (op == prev) ++run;
+            else {
+                if (phase == 1) a.cigar_pool[cpos + (unsigned long long)(ncig - 1 - l)] = ((uint32_t)run << 4) | (uint32_t)prev;
+                ++l;
+                prev = op;
+                run = 1;
+            }
+        }
+        if (bad) { s.status = DB200_PAIR_UNSUPPORTED; res.cigar_len = 0; return; }
+        if (op == 0) {
+            if (phase == 1) a.cigar_pool[cpos + (unsigned long long)(ncig - 1 - l)] = ((uint32_t)(run + 1)) << 4;
+            ++l;
+        } else {
+            if (phase == 1) {
+                a.cigar_pool[cpos + (unsigned long long)(ncig - 1 - l)] = ((uint32_t)run << 4) | (uint32_t)op;
+                a.cigar_pool[cpos + (unsigned long long)(ncig - 2 - l)] = 16u;
+            }
+            l += 2;
+        }
+        if (phase == 0) {
+            ncig = l;
+            cpos = atomicAdd(a.cigar_cursor, (unsigned long long)ncig);
+            if (cpos + (unsigned long long)ncig > a.cigar_cap) { atomicExch(a.overflow_flag, 1); s.status = DB200_PAIR_NOSCRATCH; return; }
+        }
+    }
+    s.cigar_pos = (int64_t)cpos;
+    s.cigar_len = ncig;
+    res.cigar_len = ncig;
+}
+
+__global__ void sw_colmax_len_kernel(const PairMeta *meta, const PairState *state, int64_t npairs, int32_t *lens)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    lens[p] = (state[p].status == DB200_PAIR_OK && state[p].need_colmax) ? 2 * meta[p].n : 0;
+}
+
+__global__ void sw_cigar_len_kernel(const PairState *state, int64_t npairs, int32_t *lens)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    lens[p] = state[p].cigar_len;
+}
+
+__global__ void sw_cigar_gather_kernel(const PairState *state, int64_t npairs, const int64_t *off, const uint32_t *pool,
+                                       uint32_t *out, int64_t out_cap, int32_t *status_out, int32_t *overflow_flag)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    if (status_out) status_out[p] = state[p].status;
+    const int len = state[p].cigar_len;
+    if (len <= 0 || !out) return;
+    if (off[p] + len > out_cap) { atomicExch(overflow_flag, 3); return; }
+    const uint32_t *src = pool + state[p].cigar_pos;
+    uint32_t *dst = out + off[p];
+    for (int i = 0; i < len; ++i) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+template <int K, int G, bool COLMAX, bool MULTI, bool WATCH>
+static int launch_pass(Engine *e, const PassArgs &a, cudaStream_t st)
+{
+    constexpr int NCH = K / 8, ROW = 2 * NCH * 32;
+    const size_t smem = (size_t)4 * 6 * ROW * sizeof(uint4);
+    static int blocks_cached[16] = {0};
+    int &blocks = blocks_cached[e->device & 15];
+    if (blocks == 0) {
+        DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_pass_kernel<K, G, COLMAX, MULTI, WATCH>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_pass_kernel<K, G, COLMAX, MULTI, WATCH>, 128, smem));
+        if (per_sm < 1) per_sm = 1;
+        if (MULTI && per_sm * 4 > SW_MULTI_MAX_WARPS_PER_SM) per_sm = SW_MULTI_MAX_WARPS_PER_SM / 4;
+        blocks = e->sm_count * per_sm;
+    }
+    sw_pass_kernel<K, G, COLMAX, MULTI, WATCH><<<blocks, 128, smem, st>>>(a);
+    count_launch(e);
+    DB200_CUDA_CHECK(cudaGetLastError());
+    return DB200_OK;
+}
+
+template <bool COLMAX, bool WATCH>
+static int launch_cfg(Engine *e, int cfg, const PassArgs &a, cudaStream_t st)
+{
+    switch (cfg) {
+        case 0: return launch_pass<16, 1, COLMAX, false, WATCH>(e, a, st);
+        case 1: return launch_pass<16, 2, COLMAX, false, WATCH>(e, a, st);
+        case 2: return launch_pass<16, 4, COLMAX, false, WATCH>(e, a, st);
+        case 3: return launch_pass<16, 8, COLMAX, false, WATCH>(e, a, st);
+        case 4: return launch_pass<16, 16, COLMAX, false, WATCH>(e, a, st);
+        case 5: return launch_pass<16, 32, COLMAX, false, WATCH>(e, a, st);
+        default: return launch_pass<32, 32, COLMAX, true, WATCH>(e, a, st);
+    }
+}
+
+int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const uint8_t *d_qbuf, const int64_t *d_qoff,
+                         int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
+                         int32_t max_query_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf,
+                         int64_t cigar_cap, int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st)
+{
+    if (npairs < 0 || !prm || !d_results) { set_error("sw_batch: bad arguments"); return DB200_ERR_ARG; }
+    if (prm->gap_open <= 0 || prm->gap_extend <= 0 || prm->gap_open > 255 || prm->gap_extend > 255) {
+        set_error("sw_batch: gap penalties must be in 1..255"); return DB200_ERR_ARG;
+    }
+    if (prm->mat && prm->n != 5) { set_error("sw_batch: only 5x5 nucleotide matrices are supported"); return DB200_ERR_ARG; }
+    if (prm->score_size < 0 || prm->score_size > 2) { set_error("sw_batch: score_size must be 0, 1 or 2"); return DB200_ERR_ARG; }
+    if (npairs == 0) {
+        if (d_cigar_off) DB200_CUDA_CHECK(cudaMemsetAsync(d_cigar_off, 0, sizeof(int64_t), st));
+        if (cigar_total) *cigar_total = 0;
+        return DB200_OK;
+    }
+    if (npairs > (int64_t)1 << 30) { set_error("sw_batch: at most 2^30 pairs per call"); return DB200_ERR_ARG; }
+    // ---- scoring ---------------------------------------------------------------------------------
+    SwScoring sc;
+    int8_t m5[25];
+    for (int a = 0; a < 5; ++a)
+        for (int b = 0; b < 5; ++b)
+            m5[a * 5 + b] = prm->mat ? prm->mat[a * 5 + b] : (int8_t)((a == 4 || b == 4) ? 0 : (a == b ? prm->match : prm->mismatch));
+    int bias = 0, max_match = 0;
+    for (int i = 0; i < 25; ++i) { if (m5[i] < bias) bias = m5[i]; if (m5[i] > max_match) max_match = m5[i]; }
+    bias = -bias;
+    for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b)
+            sc.mat[a * 6 + b] = (a < 5 && b < 5) ? (int16_t)m5[a * 5 + b] : (int16_t)SW_NEG;
+    sc.gap_open = prm->gap_open;
+    sc.gap_extend = prm->gap_extend;
+
+    // ---- workspace ---------------------------------------------------------------------------------
+    const int64_t nseq = 2 * npairs;
+    const size_t seq_units = (size_t)((q_bytes + t_bytes) / 32 + nseq + 64);
+    if (seq_units * 2 > 0xFFFFFFF0ull) { set_error("sw_batch: batch too large (packed pool exceeds 2^32 units)"); return DB200_ERR_ARG; }
+    const size_t nb = (size_t)SW_NSEG * SW_LBINS;
+    const int bstride = ((max_query_len > 0 ? max_query_len : 0) + 63) & ~31;
+    const size_t bwarps = (size_t)e->sm_count * SW_MULTI_MAX_WARPS_PER_SM;
+    const size_t trace_cap = e->trace_pool_bytes;
+    const int64_t cig_pool_cap = cigar_cap > 0 ? cigar_cap : (q_bytes + t_bytes + 2 * npairs);
+
+    int32_t *units = ws.alloc<int32_t>(nseq + 16);
+    int64_t *unit_off = ws.alloc<int64_t>(nseq + 16);
+    int64_t *scan_tmp = ws.alloc<int64_t>(scan_tmp_count(nseq) * 2);
+    uint32_t *pool = ws.alloc<uint32_t>(seq_units * 4 * 2);
+    PairMeta *meta = ws.alloc<PairMeta>(npairs);
+    PairMeta *rmeta = ws.alloc<PairMeta>(npairs);
+    PairState *state = ws.alloc<PairState>(npairs);
+    PassOut *fwd = ws.alloc<PassOut>(npairs);
+    PassOut *rev = ws.alloc<PassOut>(npairs);
+    int32_t *tasks_f = ws.alloc<int32_t>(npairs);
+    int32_t *tasks_r = ws.alloc<int32_t>(npairs);
+    int32_t *amb_f = ws.alloc<int32_t>(npairs);
+    int32_t *amb_r = ws.alloc<int32_t>(npairs);
+    int64_t *colmax_off = ws.alloc<int64_t>(npairs + 1);
+    int64_t *cig_off_tmp = ws.alloc<int64_t>(npairs + 1);
+    int32_t *lens = ws.alloc<int32_t>(npairs);
+    int16_t *colmax = ws.alloc<int16_t>((size_t)(t_bytes + npairs) * 2);
+    int32_t *bins = ws.alloc<int32_t>(nb * 6 + 1024);
+    uint32_t *cigar_pool = ws.alloc<uint32_t>((size_t)cig_pool_cap + 16);
+    int32_t *counters = ws.alloc<int32_t>(4096);
+    uint32_t *boundary = ws.alloc<uint32_t>(bwarps * (size_t)bstride + 64);
+    uint8_t *trace = ws.alloc<uint8_t>(trace_cap);
+    if (!units || !unit_off || !scan_tmp || !pool || !meta || !rmeta || !state || !fwd || !rev || !tasks_f || !tasks_r || !amb_f ||
+        !amb_r || !colmax_off || !cig_off_tmp || !lens || !colmax || !bins || !cigar_pool || !counters || !boundary || !trace) {
+        set_error("sw_batch: device workspace allocation failed");
+        return DB200_ERR_NOMEM;
+    }
+    int32_t *hist_f = bins, *start_f = bins + nb, *fill_f = bins + 2 * nb;
+    int32_t *hist_r = bins + 3 * nb, *start_r = bins + 4 * nb, *fill_r = bins + 5 * nb;
+    int32_t *segs = bins + 6 * nb;
+    int32_t *seg_begin_f = segs, *seg_count_f = segs + SW_NSEG, *seg_begin_r = segs + 2 * SW_NSEG, *seg_count_r = segs + 3 * SW_NSEG;
+    int32_t *amb_count_f = segs + 4 * SW_NSEG, *amb_count_r = segs + 5 * SW_NSEG;
+    // counters: [0..127] work counters of pass launches, [128] unit cursor, [130..131] trace cursor (u64),
+    // [132..133] cigar cursor (u64), [134] overflow flag
+    DB200_CUDA_CHECK(cudaMemsetAsync(bins, 0, (nb * 6 + 1024) * sizeof(int32_t), st));
+    DB200_CUDA_CHECK(cudaMemsetAsync(counters, 0, 4096 * sizeof(int32_t), st));
+    uint32_t *unit_cursor = reinterpret_cast<uint32_t *>(counters + 128);
+    unsigned long long *trace_cursor = reinterpret_cast<unsigned long long *>(counters + 130);
+    unsigned long long *cigar_cursor = reinterpret_cast<unsigned long long *>(counters + 132);
+    int32_t *overflow_flag = counters + 134;
+
+    const int TB = 256;
+    const unsigned gseq = (unsigned)((nseq + TB - 1) / TB), gpair = (unsigned)((npairs + TB - 1) / TB);
+    const unsigned gwarp_seq = (unsigned)((nseq * 32 + TB - 1) / TB), gwarp_pair = (unsigned)((npairs * 32 + TB - 1) / TB);
+
+    // 1. pack ---------------------------------------------------------------------------------------
+    sw_units_kernel<<<gseq, TB, 0, st>>>(d_qoff, d_toff, npairs, units);
+    count_launch(e);
+    exclusive_scan_i32_i64(e, units, unit_off, nseq, scan_tmp, st);
+    sw_pack_kernel<<<gwarp_seq, TB, 0, st>>>(d_qbuf, d_qoff, d_tbuf, d_toff, npairs, unit_off, pool, meta);
+    count_launch(e);
+
+    // 2. bucket -------------------------------------------------------------------------------------
+    InitArgs ia;
+    ia.meta = meta; ia.mask_len = d_mask_len; ia.state = state; ia.npairs = npairs; ia.max_match = max_match; ia.flag = prm->flag;
+    sw_init_kernel<<<gpair, TB, 0, st>>>(ia, hist_f);
+    sw_binscan_kernel<<<1, 32, 0, st>>>(hist_f, start_f, seg_begin_f, seg_count_f);
+    sw_scatter_kernel<<<gpair, TB, 0, st>>>(meta, state, npairs, 0, start_f, fill_f, tasks_f);
+    sw_colmax_len_kernel<<<gpair, TB, 0, st>>>(meta, state, npairs, lens);
+    count_launch(e, 4);
+    exclusive_scan_i32_i64(e, lens, colmax_off, npairs, scan_tmp, st);
+    DB200_CUDA_CHECK(cudaMemsetAsync(fwd, 0, sizeof(PassOut) * npairs, st));
+    DB200_CUDA_CHECK(cudaMemsetAsync(rev, 0, sizeof(PassOut) * npairs, st));
+
+    PassArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.pool = reinterpret_cast<const uint4 *>(pool);
+    pa.colmax = colmax; pa.colmax_off = colmax_off;
+    pa.boundary = boundary; pa.boundary_stride = bstride;
+    pa.sc = sc;
+    int counter_idx = 0;
+    const bool can_multi = max_query_len > 0;
+
+    // 3. forward pass per segment, then the exact re-run of pairs with an ambiguous end row -----------
+    for (int seg = 0; seg < SW_NSEG; ++seg) {
+        const int cfg = seg >> 1, cmx = seg & 1;
+        if (cfg == SW_NCFG - 1 && !can_multi) continue;
+        pa.meta = meta; pa.tasks = tasks_f; pa.seg_begin = seg_begin_f; pa.seg_count = seg_count_f; pa.seg = seg;
+        pa.counter = counters + (counter_idx++);
+        pa.out = fwd;
+        pa.amb_list = amb_f; pa.amb_count = amb_count_f + 2 * cfg; pa.amb_base_seg = 2 * cfg;
+        const int rc = cmx ? launch_cfg<true, false>(e, cfg, pa, st) : launch_cfg<false, false>(e, cfg, pa, st);
+        if (rc) return rc;
+    }
+    for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
+        if (cfg == SW_NCFG - 1 && !can_multi) continue;
+        pa.meta = meta; pa.tasks = amb_f; pa.seg_begin = seg_begin_f; pa.seg_count = amb_count_f; pa.seg = 2 * cfg;
+        pa.counter = counters + (counter_idx++);
+        pa.out = fwd;
+        const int rc = launch_cfg<false, true>(e, cfg, pa, st);
+        if (rc) return rc;
+    }
+
+    // 4. reversed problems ----------------------------------------------------------------------------
+    MidArgs ma;
+    ma.fwd = fwd; ma.meta = meta; ma.rmeta = rmeta; ma.state = state; ma.npairs = npairs;
+    ma.bias = bias; ma.score_size = prm->score_size; ma.flag = prm->flag; ma.filters = prm->filters;
+    ma.max_match = max_match; ma.gap_open = prm->gap_open; ma.gap_extend = prm->gap_extend;
+    ma.unit_cursor = unit_cursor; ma.unit_base = (uint32_t)seq_units;
+    sw_mid_kernel<<<gpair, TB, 0, st>>>(ma, hist_r);
+    sw_reverse_extract_kernel<<<gwarp_pair, TB, 0, st>>>(meta, rmeta, state, fwd, npairs, pool);
+    sw_binscan_kernel<<<1, 32, 0, st>>>(hist_r, start_r, seg_begin_r, seg_count_r);
+    sw_scatter_kernel<<<gpair, TB, 0, st>>>(rmeta, state, npairs, 1, start_r, fill_r, tasks_r);
+    count_launch(e, 4);
+    for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
+        if (cfg == SW_NCFG - 1 && !can_multi) continue;
+        pa.meta = rmeta; pa.tasks = tasks_r; pa.seg_begin = seg_begin_r; pa.seg_count = seg_count_r; pa.seg = 2 * cfg;
+        pa.counter = counters + (counter_idx++);
+        pa.out = rev;
+        pa.amb_list = amb_r; pa.amb_count = amb_count_r + 2 * cfg; pa.amb_base_seg = 2 * cfg;
+        const int rc = launch_cfg<false, false>(e, cfg, pa, st);
+        if (rc) return rc;
+    }
+    for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
+        if (cfg == SW_NCFG - 1 && !can_multi) continue;
+        pa.meta = rmeta; pa.tasks = amb_r; pa.seg_begin = seg_begin_r; pa.seg_count = amb_count_r; pa.seg = 2 * cfg;
+        pa.counter = counters + (counter_idx++);
+        pa.out = rev;
+        const int rc = launch_cfg<false, true>(e, cfg, pa, st);
+        if (rc) return rc;
+    }
+
+    // 5. finalize + traceback + cigar compaction ---------------------------------------------------------
+    FinalArgs fa;
+    fa.fwd = fwd; fa.rev = rev; fa.meta = meta; fa.state = state; fa.colmax = colmax; fa.colmax_off = colmax_off;
+    fa.results = d_results; fa.status_out = nullptr; fa.npairs = npairs;
+    fa.flag = prm->flag; fa.filters = prm->filters; fa.filterd = prm->filterd;
+    sw_finalize_kernel<<<gpair, TB, 0, st>>>(fa);
+    TraceArgs ta;
+    ta.pool = reinterpret_cast<const uint4 *>(pool); ta.meta = meta; ta.state = state; ta.results = d_results; ta.npairs = npairs;
+    ta.sc = sc; ta.scratch = trace; ta.scratch_cursor = trace_cursor; ta.scratch_cap = trace_cap;
+    ta.cigar_pool = cigar_pool; ta.cigar_cursor = cigar_cursor; ta.cigar_cap = (unsigned long long)cig_pool_cap;
+    ta.overflow_flag = overflow_flag;
+    sw_traceback_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, st>>>(ta);
+    sw_cigar_len_kernel<<<gpair, TB, 0, st>>>(state, npairs, lens);
+    count_launch(e, 3);
+    int64_t *off_out = d_cigar_off ? d_cigar_off : cig_off_tmp;
+    exclusive_scan_i32_i64(e, lens, off_out, npairs, scan_tmp, st);
+    sw_cigar_gather_kernel<<<gpair, TB, 0, st>>>(state, npairs, off_out, cigar_pool, d_cigar_buf, cigar_cap, d_status, overflow_flag);
+    count_launch(e);
+    DB200_CUDA_CHECK(cudaGetLastError());
+    if (cigar_total) {
+        DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_total, off_out + npairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        DB200_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return DB200_OK;
+}
+
+}  // namespace db200

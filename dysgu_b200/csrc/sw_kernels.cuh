@@ -1,0 +1,364 @@
+// Smith-Waterman device kernels for sm_100a.
+//
+// What they compute is the observable behaviour of dysgu's vendored striped Smith-Waterman
+// (reference: dysgu/scikitbio/ssw.c:124-346, 372-548 scoring passes; 550-728 banded traceback;
+// 772-857 driver) - not its SIMD layout.  The design is B200-first:
+//
+//   * The target ("ref", DP columns) is DISTRIBUTED over virtual lanes, the query ("read", DP rows)
+//     is STREAMED.  Each thread carries two virtual lanes in the two int16 halves of its 32-bit
+//     registers (s16x2), skewed by one row, so every DPX instruction (VIADDMNMX.S16x2[.RELU],
+//     VIMNMX.S16x2) updates two independent cells.  A group of G threads (G = 1..32) forms a
+//     wavefront of 2G virtual lanes x K columns; 32/G pairs share a warp.
+//   * The per-pair substitution profile lives in shared memory, laid out so that every LDS.128
+//     of a quarter warp hits 32 distinct banks; sequences are read as packed 4-bit codes with
+//     128-bit / 32-bit loads.
+//   * Targets longer than 2*G*K columns are processed in column tiles ("passes"); the right-edge
+//     column of a tile travels to the next pass through a per-warp boundary array.
+//   * Tie-breaking of the reference (first column holding the maximum, then the smallest row in
+//     that column) is reproduced from a per-lane running maximum plus per-column maxima; the rare
+//     pair with several maximal columns inside one virtual lane is re-run by the WATCH variant.
+#pragma once
+#include "engine.cuh"
+
+namespace db200 {
+
+constexpr int SW_PAD_CODE = 5;       // nibble used for padding; scores SW_NEG against everything
+constexpr int SW_NEG = -16384;
+constexpr int SW_NCFG = 7;           // kernel configurations (K, G)
+constexpr int SW_LBINS = 512;        // length bins per (config, colmax) segment, 32 rows each
+constexpr int SW_NSEG = SW_NCFG * 2; // (config, needs column maxima)
+constexpr int SW_MULTI_MAX_WARPS_PER_SM = 8; // bounds the per-warp boundary scratch of the column-tiled kernel
+
+struct PairMeta {      // one alignment problem on packed sequences
+    uint32_t q_unit;   // offset of the streamed sequence in the nibble pool, in 16-byte units (32 bases)
+    uint32_t t_unit;   // offset of the distributed sequence
+    int32_t m;         // streamed length (rows)
+    int32_t n;         // distributed length (columns)
+};
+
+struct PassOut {       // result of one scoring pass
+    int32_t score;
+    int32_t end_t;     // column of the best cell (first column holding the maximum)
+    int32_t end_q;     // smallest row holding the maximum in that column
+    int32_t amb;       // several maximal columns inside one virtual lane: end_q must be recomputed
+};
+
+struct SwScoring {
+    int16_t mat[36];   // 6x6: ACGTN + pad; row = distributed code, column = streamed code
+    int32_t gap_open, gap_extend;
+};
+
+struct PassArgs {
+    const uint4 *pool;
+    const PairMeta *meta;
+    const int32_t *tasks;      // pair ids ordered by (segment, length bin)
+    const int32_t *seg_begin;  // [SW_NSEG] first task of each segment
+    const int32_t *seg_count;  // [SW_NSEG]
+    int32_t seg;
+    int32_t *counter;          // work counter of this launch
+    PassOut *out;
+    int16_t *colmax;           // COLMAX: per-column maxima then last-row values, at colmax_off[pair]
+    const int64_t *colmax_off;
+    uint32_t *boundary;        // MULTI: per-warp right-edge column
+    int32_t boundary_stride;
+    int32_t *amb_list;         // pairs whose end_q is ambiguous (appended at seg_begin[amb_base_seg])
+    int32_t *amb_count;
+    int32_t amb_base_seg;
+    SwScoring sc;
+};
+
+__device__ __forceinline__ uint32_t pack16(int v) { return (uint32_t)(v & 0xFFFF) * 0x10001u; }
+__device__ __forceinline__ int lo16(uint32_t x) { return (int)(int16_t)(x & 0xFFFF); }
+__device__ __forceinline__ int hi16(uint32_t x) { return (int)(int16_t)(x >> 16); }
+
+__device__ __forceinline__ uint32_t unit_word(const uint4 &u, int w)
+{
+    return w == 0 ? u.x : (w == 1 ? u.y : (w == 2 ? u.z : u.w));
+}
+
+// 4-bit code at position idx (>= 0) of a packed sequence starting at unit `unit`
+__device__ __forceinline__ int pool_code(const uint4 *pool, uint32_t unit, int idx)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(pool + unit);
+    return (int)((w[idx >> 3] >> ((idx & 7) * 4)) & 15u);
+}
+
+template <int K, int G, bool COLMAX, bool MULTI, bool WATCH>
+__global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
+{
+    constexpr int V = 2 * G;          // virtual lanes per group
+    constexpr int C = V * K;          // columns per pass
+    constexpr int NCH = K / 8;        // 16-byte chunks (8 int16 scores) per half strip
+    constexpr int GROUPS = 32 / G;    // pairs per warp
+    constexpr int ROW = 2 * NCH * 32; // uint4 per profile row (one streamed code) per warp
+    constexpr int UNITS = (2 * K) / 32;
+    static_assert(K % 16 == 0, "K must be a multiple of 16");
+    static_assert(!MULTI || G == 32, "column tiling runs one pair per warp");
+
+    extern __shared__ uint4 smem[];
+    __shared__ int16_t mat_s[36];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lig = lane % G, grp = lane / G;
+    uint4 *prof = smem + warp * (6 * ROW);
+    if (threadIdx.x < 36) mat_s[threadIdx.x] = a.sc.mat[threadIdx.x];
+    __syncthreads();
+
+    const uint32_t nGE2 = pack16(-a.sc.gap_extend), nGO2 = pack16(-a.sc.gap_open);
+    const int seg_begin = a.seg_begin[a.seg], seg_count = a.seg_count[a.seg];
+    const unsigned FULL = 0xFFFFFFFFu;
+    uint32_t *bnd = nullptr;
+    if (MULTI) bnd = a.boundary + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)a.boundary_stride;
+
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.counter, GROUPS);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= seg_count) break;
+        const int ti = base + grp;
+        const bool active = ti < seg_count;
+        const int pair = active ? a.tasks[seg_begin + ti] : -1;
+        PairMeta pm;
+        pm.q_unit = 0; pm.t_unit = 0; pm.m = 0; pm.n = 0;
+        if (active) pm = a.meta[pair];
+        const int m = pm.m, n = pm.n;
+        const uint32_t *qw = reinterpret_cast<const uint32_t *>(a.pool + pm.q_unit);
+        const int q_words = ((m + 31) >> 5) << 2;
+
+        int watch_score = -1, watch_slot = -1;
+        if (WATCH && active) { watch_score = a.out[pair].score; watch_slot = a.out[pair].end_t; }
+
+        int steps = m + V - 1;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, o));
+        const int npass = MULTI ? max(1, (n + C - 1) / C) : 1;
+
+        int run_score = -1, run_slot = 0, run_row = 0, run_amb = 0, run_wrow = -1;
+
+        for (int ps = 0; ps < npass; ++ps) {
+            // ---- profile of this pass's columns -> shared memory -------------------------------
+            __syncwarp();
+            {
+                const int j0 = ps * C + lig * 2 * K;
+                uint4 tu[UNITS];
+#pragma unroll
+                for (int u = 0; u < UNITS; ++u) {
+                    const int jb = j0 + u * 32;
+                    if (jb < n) tu[u] = a.pool[pm.t_unit + (jb >> 5)];
+                    else tu[u] = make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        int tc[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int jj = h * K + ch * 8 + e; // position inside this lane's 2K columns
+                            tc[e] = (int)((unit_word(tu[jj >> 5], (jj >> 3) & 3) >> ((jj & 7) * 4)) & 15u);
+                            tc[e] = min(tc[e], SW_PAD_CODE) * 6;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint32_t s0 = (uint16_t)mat_s[tc[2 * e] + c];
+                                const uint32_t s1 = (uint16_t)mat_s[tc[2 * e + 1] + c];
+                                w[e] = s0 | (s1 << 16);
+                            }
+                            prof[(c * 2 + h) * NCH * 32 + ch * 32 + lane] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+
+            // ---- state ---------------------------------------------------------------------------
+            uint32_t H[K], U[K], HmO[K], vmax[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { H[k] = 0; U[k] = 0; HmO[k] = 0; vmax[k] = 0; }
+            uint32_t best2 = 0;
+            int bstep_lo = 0, bstep_hi = 0;
+            uint32_t OH = 0, OV = 0, prevIn = 0;
+            int wstep_lo = -1, wstep_hi = -1;
+            int kstar_lo = -1, kstar_hi = -1;
+            if (WATCH) {
+                const int b0 = ps * C + (2 * lig) * K;
+                if (watch_slot >= b0 && watch_slot < b0 + K) kstar_lo = watch_slot - b0;
+                if (watch_slot >= b0 + K && watch_slot < b0 + 2 * K) kstar_hi = watch_slot - b0 - K;
+            }
+
+            // streamed codes: this lane's low half sits at row t - 2*lig
+            const int phi4 = ((-2 * lig) & 7) * 4;
+            int widx = (-2 * lig) >> 3; // floor
+            uint32_t prevw = (widx >= 0 && widx < q_words) ? qw[widx] : 0x55555555u;
+            uint32_t cur = 0;
+            const uint4 *row_hi = prof + SW_PAD_CODE * ROW + NCH * 32 + lane; // row -1: padding
+            uint32_t bchunk = 0, wchunk = 0;
+
+            for (int t = 0; t < steps; ++t) {
+                if ((t & 7) == 0) {
+                    ++widx;
+                    const uint32_t neww = (widx >= 0 && widx < q_words) ? qw[widx] : 0x55555555u;
+                    cur = __funnelshift_r(prevw, neww, phi4);
+                    prevw = neww;
+                }
+                const int c_lo = min((int)(cur & 15u), SW_PAD_CODE);
+                cur >>= 4;
+                const uint4 *row_lo = prof + c_lo * ROW + lane;
+
+                // ---- inputs from the preceding virtual lane ---------------------------------------
+                uint32_t sh = OH, sv = OV;
+                if (G > 1) {
+                    sh = __shfl_up_sync(FULL, OH, 1, G);
+                    sv = __shfl_up_sync(FULL, OV, 1, G);
+                }
+                if (MULTI) {
+                    if ((t & 31) == 0) bchunk = (ps > 0 && t + lane < m) ? bnd[t + lane] : 0u;
+                    const uint32_t y = __shfl_sync(FULL, bchunk, t & 31);
+                    if (lig == 0) { sh = y << 16; sv = y & 0xFFFF0000u; }
+                } else {
+                    if (lig == 0) { sh = 0; sv = 0; }
+                }
+                const uint32_t inH = __funnelshift_l(sh, OH, 16); // lo <- previous lane's hi, hi <- own lo
+                const uint32_t inV = __funnelshift_l(sv, OV, 16);
+
+                uint32_t Vv = inV;
+                uint32_t diag = prevIn;
+                prevIn = inH;
+                uint32_t m2 = 0;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const uint4 pl = row_lo[ch * 32];
+                    const uint4 ph = row_hi[ch * 32];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int k = ch * 8 + e;
+                        const uint32_t wl = unit_word(pl, e >> 1), wh = unit_word(ph, e >> 1);
+                        const uint32_t s = __byte_perm(wl, wh, (e & 1) ? 0x7632 : 0x5410);
+                        U[k] = __viaddmax_s16x2_relu(U[k], nGE2, HmO[k]);
+                        const uint32_t Hp = __viaddmax_s16x2_relu(diag, s, U[k]);
+                        diag = H[k];
+                        HmO[k] = __vadd2(Hp, nGO2);
+                        H[k] = __vmaxs2(Hp, Vv);
+                        Vv = __viaddmax_s16x2(Vv, nGE2, HmO[k]);
+                        vmax[k] = __vmaxs2(vmax[k], H[k]);
+                        m2 = __vmaxs2(m2, H[k]);
+                    }
+                }
+                OH = H[K - 1];
+                OV = Vv;
+                row_hi = row_lo + NCH * 32;
+
+                // ---- running maximum of each virtual lane (strict improvement -> step) ------------
+                const uint32_t nb = __vmaxs2(best2, m2);
+                const uint32_t chg = nb ^ best2;
+                if (chg & 0x0000FFFFu) bstep_lo = t;
+                if (chg & 0xFFFF0000u) bstep_hi = t;
+                best2 = nb;
+
+                if (WATCH) {
+                    uint32_t hs_lo = 0xFFFFFFFFu, hs_hi = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        if (k == kstar_lo) hs_lo = H[k] & 0xFFFFu;
+                        if (k == kstar_hi) hs_hi = H[k] >> 16;
+                    }
+                    if (wstep_lo < 0 && hs_lo == (uint32_t)watch_score) wstep_lo = t;
+                    if (wstep_hi < 0 && hs_hi == (uint32_t)watch_score) wstep_hi = t;
+                }
+
+                if (COLMAX) {
+                    // last-row values H(m-1, j): lo half is at row t-2*lig, hi half one row behind
+                    const unsigned d = (unsigned)(t - 2 * lig - (m - 1));
+                    if (d <= 1u && active) {
+                        int16_t *lr = a.colmax + a.colmax_off[pair] + n;
+                        const int jb = ps * C + (2 * lig + (int)d) * K;
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                            if (jb + k < n) lr[jb + k] = (int16_t)(d ? (H[k] >> 16) : (H[k] & 0xFFFFu));
+                    }
+                }
+
+                if (MULTI) {
+                    // right-edge column of this pass (virtual lane V-1 = hi half of lane 31), row t-(V-1)
+                    const int r = t - (V - 1);
+                    const uint32_t x = __byte_perm(OH, OV, 0x7632);
+                    const uint32_t val = __shfl_sync(FULL, x, 31);
+                    if (r >= 0) {
+                        if (lane == (r & 31)) wchunk = val;
+                        if ((r & 31) == 31 || t == steps - 1) {
+                            const int r0 = r & ~31;
+                            if (lane <= (r & 31) && r0 + lane < m && ps + 1 < npass) bnd[r0 + lane] = wchunk;
+                        }
+                    }
+                }
+            }
+
+            // ---- end of pass: column maxima, lane winners -----------------------------------------
+            if (COLMAX && active) {
+                int16_t *cm = a.colmax + a.colmax_off[pair];
+                const int jb = ps * C + 2 * lig * K;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (jb + k < n) cm[jb + k] = (int16_t)(vmax[k] & 0xFFFFu);
+                    if (jb + K + k < n) cm[jb + K + k] = (int16_t)(vmax[k] >> 16);
+                }
+            }
+            const int lb_lo = (int)(best2 & 0xFFFFu), lb_hi = (int)(best2 >> 16);
+            int k1_lo = 0, cnt_lo = 0, k1_hi = 0, cnt_hi = 0;
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) {
+                if ((int)(vmax[k] & 0xFFFFu) == lb_lo) { k1_lo = k; ++cnt_lo; }
+                if ((int)(vmax[k] >> 16) == lb_hi) { k1_hi = k; ++cnt_hi; }
+            }
+            const int comp_lo = (lb_lo << 8) | (255 - 2 * lig);
+            const int comp_hi = (lb_hi << 8) | (255 - (2 * lig + 1));
+            int gmax = max(comp_lo, comp_hi);
+#pragma unroll
+            for (int o = G / 2; o >= 1; o >>= 1) gmax = max(gmax, __shfl_xor_sync(FULL, gmax, o));
+            const int vw = 255 - (gmax & 255);
+            const int src = grp * G + (vw >> 1);
+            const int hsel = vw & 1;
+            int d_k1 = hsel ? k1_hi : k1_lo, d_cnt = hsel ? cnt_hi : cnt_lo, d_step = hsel ? bstep_hi : bstep_lo;
+            d_k1 = __shfl_sync(FULL, d_k1, src);
+            d_cnt = __shfl_sync(FULL, d_cnt, src);
+            d_step = __shfl_sync(FULL, d_step, src);
+            const int p_score = gmax >> 8;
+            if (p_score > run_score) {
+                run_score = p_score;
+                run_slot = ps * C + vw * K + d_k1;
+                run_row = d_step - vw;
+                run_amb = d_cnt > 1;
+            }
+            if (WATCH) {
+                int w = -1;
+                if (wstep_lo >= 0) w = wstep_lo - 2 * lig;
+                if (wstep_hi >= 0) w = wstep_hi - (2 * lig + 1);
+#pragma unroll
+                for (int o = G / 2; o >= 1; o >>= 1) w = max(w, __shfl_xor_sync(FULL, w, o));
+                if (w >= 0) run_wrow = w;
+            }
+        }
+
+        if (active && lig == 0) {
+            if (WATCH) {
+                a.out[pair].end_q = run_wrow;
+                a.out[pair].amb = run_wrow < 0 ? 2 : 0;
+            } else {
+                PassOut o;
+                o.score = run_score;
+                o.end_t = run_slot;
+                o.end_q = run_row;
+                o.amb = (run_amb && run_score > 0) ? 1 : 0;
+                a.out[pair] = o;
+                if (o.amb) {
+                    const int pos = atomicAdd(a.amb_count, 1);
+                    a.amb_list[a.seg_begin[a.amb_base_seg] + pos] = pair;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace db200

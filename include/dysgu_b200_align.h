@@ -1,0 +1,227 @@
+/*
+ * dysgu_b200_align.h - C ABI of the B200-native batched alignment engine (libdysgu_b200_align.so).
+ *
+ * Drop-in boundary for the one data-parallel hot path of kcleal/dysgu: the many independent
+ * alignments issued through StripedSmithWaterman(query)(target) and edlib.align(...).
+ * Plain pointers and sizes only; no torch / Python types.  Every entry point cites the reference
+ * interface it replaces (paths relative to the reference checkout, dysgu v1.9.0).
+ *
+ * Conventions
+ *   - Sequences travel as CSR batches: a byte buffer plus int64 offsets[npairs+1]; sequence i is
+ *     buf[off[i] .. off[i+1]).  SW sequences are raw ASCII (encoded on the device exactly like
+ *     _ssw_wrapper.pyx:60-68: A/a/U/u=0 C/c=1 G/g=2 T/t=3, anything else=4); edit-distance
+ *     sequences are raw bytes compared case-sensitively (edlib.pyx:12-54, edlib.cpp:1433-1472).
+ *   - *_host entry points take host pointers and perform H2D / compute / D2H internally.
+ *   - *_device entry points take device pointers on `device` and enqueue everything on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream); outputs are device
+ *     pointers too.  They return after enqueueing unless stated otherwise.
+ *   - All functions return DB200_OK (0) or a negative DB200_ERR_* code; db200_last_error() gives
+ *     a thread-local message.  There is no CPU fallback: without a CUDA device every compute
+ *     entry point fails with DB200_ERR_CUDA.
+ */
+#ifndef DYSGU_B200_ALIGN_H
+#define DYSGU_B200_ALIGN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DB200_OK 0
+#define DB200_ERR_CUDA -1      /* no device / CUDA runtime error */
+#define DB200_ERR_ARG -2       /* invalid argument */
+#define DB200_ERR_NOMEM -3     /* device or host allocation failed */
+#define DB200_ERR_CAPACITY -4  /* caller-provided output buffer too small */
+#define DB200_ERR_INTERNAL -5
+
+/* per-pair status values written to the status arrays */
+#define DB200_PAIR_OK 0
+#define DB200_PAIR_EMPTY 1          /* an empty sequence: the reference reads out of bounds here (ssw.c:195) */
+#define DB200_PAIR_OVERFLOW 2       /* score_size==0 and the 8-bit score saturated: ssw_align returns NULL (ssw.c:803-806) */
+#define DB200_PAIR_SCORE_RANGE 3    /* best possible score does not fit int16 */
+#define DB200_PAIR_UNSUPPORTED 4
+#define DB200_PAIR_NOSCRATCH 5       /* device scratch / output pool exhausted for this pair: retry in a smaller batch */
+
+/* ------------------------------------------------------------------------------------------ */
+/* engine                                                                                       */
+/* ------------------------------------------------------------------------------------------ */
+int db200_device_count(void);
+/* Creates (lazily, per process - safe after fork) the engine state for `device`. */
+int db200_init(int device);
+void db200_shutdown(void);
+const char *db200_last_error(void);
+const char *db200_version(void);
+/* Bytes currently held by the grow-only device workspace of `device`. */
+int64_t db200_workspace_bytes(int device);
+/* Kernel launches issued by this library on `device` since the last call with reset != 0. */
+int64_t db200_kernel_launches(int device, int reset);
+/* Page-locked host memory for the *_host entry points (plain malloc'd buffers work too, slower). */
+void *db200_host_alloc(int64_t bytes);
+void db200_host_free(void *p);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Smith-Waterman (replaces ssw_init + ssw_align + align_destroy: ssw.h:72-125, ssw.c:743-862)  */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t match;       /* used when mat == NULL: 5x5 ACGTN matrix, N scores 0 (_ssw_wrapper.pyx:681-693) */
+    int32_t mismatch;
+    int32_t gap_open;    /* weight_gapO of ssw_align (positive) */
+    int32_t gap_extend;  /* weight_gapE of ssw_align (positive) */
+    int32_t score_size;  /* ssw_init score_size: 0 = 8-bit only, 1 = 16-bit only, 2 = both */
+    int32_t flag;        /* ssw_align flag (ssw.h:91-100); the wrapper passes 1 for every dysgu call site */
+    int32_t filters;     /* ssw_align filters */
+    int32_t filterd;     /* ssw_align filterd */
+    const int8_t *mat;   /* optional host pointer to a 5x5 substitution matrix in ACGTN order, or NULL */
+    int32_t n;           /* edge length of mat (must be 5 when mat != NULL) */
+} db200_sw_params;
+
+/*
+ * Fixed-size result record, one per pair; mirrors s_align (ssw.h:38-48).
+ * Wrapper view (_ssw_wrapper.pyx:130-175): score1 = optimal_alignment_score, score2 =
+ * suboptimal_alignment_score, read_* = query_*, ref_* = target_*.
+ */
+typedef struct {
+    int32_t score1;
+    int32_t score2;
+    int32_t ref_begin1;
+    int32_t ref_end1;
+    int32_t read_begin1;
+    int32_t read_end1;
+    int32_t ref_end2;
+    int32_t cigar_len;
+} db200_sw_result;
+
+/*
+ * Align npairs (query_i, target_i).  query = the profiled sequence ("read"), target = the sequence
+ * passed at call time ("ref").  mask_len[i] is the maskLen argument of ssw_align (NULL: the
+ * wrapper's mask_auto rule max(len(query)/2, 15), _ssw_wrapper.pyx:583-588).
+ * Cigars (BAM encoding len<<4|op, op M/I/D = 0/1/2) are written back to back into cigar_buf in pair
+ * order; cigar_off[i]..cigar_off[i+1] delimits pair i.  cigar_buf may be NULL when no cigar is
+ * wanted (then cigar_len is still reported and cigar_off filled).
+ */
+int db200_sw_batch_host(int device, const db200_sw_params *params,
+                        const uint8_t *qbuf, const int64_t *qoff,
+                        const uint8_t *tbuf, const int64_t *toff, int64_t npairs,
+                        const int32_t *mask_len,
+                        db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap,
+                        int64_t *cigar_off, int32_t *status);
+
+/*
+ * Same with every buffer resident in device memory.  q_bytes / t_bytes are the total buffer
+ * lengths (qoff[npairs], toff[npairs]) and max_query_len an upper bound of the query lengths -
+ * known to the caller, needed to size the workspace without a device round trip (0 disables
+ * the column-tiled kernel, i.e. targets longer than 1024 are then reported as unsupported).
+ * Everything is enqueued on `stream`; the call only synchronises when cigar_total is non-NULL
+ * (it then receives the number of cigar ops).
+ */
+int db200_sw_batch_device(int device, const db200_sw_params *params,
+                          const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
+                          const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
+                          int32_t max_query_len, const int32_t *d_mask_len,
+                          db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
+                          int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, void *stream);
+
+/*
+ * Legacy single-pair entry points with the reference's signatures (ssw.h:72-125), implemented as
+ * "batch of one" so that an unmodified Cython wrapper can link against this library.
+ * `read` / `ref` are already-encoded int8 codes (0..4) as produced by the wrapper.
+ */
+typedef struct {
+    uint16_t score1;
+    uint16_t score2;
+    int32_t ref_begin1;
+    int32_t ref_end1;
+    int32_t read_begin1;
+    int32_t read_end1;
+    int32_t ref_end2;
+    uint32_t *cigar;
+    int32_t cigarLen;
+} db200_s_align; /* layout-identical to s_align */
+typedef struct db200_s_profile db200_s_profile;
+
+db200_s_profile *db200_ssw_init(const int8_t *read, int32_t readLen, const int8_t *mat, int32_t n, int8_t score_size);
+void db200_init_destroy(db200_s_profile *p);
+db200_s_align *db200_ssw_align(const db200_s_profile *prof, const int8_t *ref, int32_t refLen,
+                               uint8_t weight_gapO, uint8_t weight_gapE, uint8_t flag,
+                               uint16_t filters, int32_t filterd, int32_t maskLen);
+void db200_align_destroy(db200_s_align *a);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Edit distance (replaces edlibAlign + edlibFreeAlignResult: edlib.h:146-271, edlib.cpp:141-296)*/
+/* ------------------------------------------------------------------------------------------ */
+#define DB200_ED_MODE_NW 0   /* EDLIB_MODE_NW  */
+#define DB200_ED_MODE_SHW 1  /* EDLIB_MODE_SHW */
+#define DB200_ED_MODE_HW 2   /* EDLIB_MODE_HW  */
+#define DB200_ED_TASK_DISTANCE 0
+#define DB200_ED_TASK_LOC 1
+#define DB200_ED_TASK_PATH 2 /* not provided by the device path (no dysgu caller requests it) */
+#define DB200_ED_NO_START INT32_MIN /* start location left unset (edlib.pyx:140: None) */
+
+typedef struct {
+    int32_t mode;
+    int32_t task;
+    int32_t k;                   /* -1: unlimited, as EdlibAlignConfig.k */
+    const char *eq_pairs;        /* additionalEqualities as 2*n_eq_pairs bytes (first, second), or NULL */
+    int32_t n_eq_pairs;
+} db200_ed_params;
+
+/* mirrors EdlibAlignResult minus the pointers (edlib.h:162-218) */
+typedef struct {
+    int32_t status;          /* EDLIB_STATUS_OK / EDLIB_STATUS_ERROR */
+    int32_t edit_distance;   /* -1 if larger than k */
+    int32_t alphabet_length;
+    int32_t num_locations;
+} db200_ed_result;
+
+/*
+ * locations are written as (start, end) int32 pairs, back to back in pair order;
+ * loc_off[i]..loc_off[i+1] delimits pair i (units: locations).  start == DB200_ED_NO_START where
+ * edlib leaves startLocations NULL.  k may be NULL (params->k applies to every pair).
+ */
+int db200_ed_batch_host(int device, const db200_ed_params *params,
+                        const uint8_t *qbuf, const int64_t *qoff,
+                        const uint8_t *tbuf, const int64_t *toff, int64_t npairs,
+                        const int32_t *k,
+                        db200_ed_result *results, int32_t *loc_buf, int64_t loc_cap,
+                        int64_t *loc_off);
+
+int db200_ed_batch_device(int device, const db200_ed_params *params,
+                          const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
+                          const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
+                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_k,
+                          db200_ed_result *d_results, int32_t *d_loc_buf, int64_t loc_cap,
+                          int64_t *d_loc_off, int64_t *loc_total, void *stream);
+
+/* Legacy single-pair entry point with edlib's signature (edlib.h:146-271). */
+typedef struct { char first; char second; } db200_EdlibEqualityPair;
+typedef struct {
+    int k;
+    int mode;
+    int task;
+    const db200_EdlibEqualityPair *additionalEqualities;
+    int additionalEqualitiesLength;
+} db200_EdlibAlignConfig; /* layout-identical to EdlibAlignConfig */
+typedef struct {
+    int status;
+    int editDistance;
+    int *endLocations;
+    int *startLocations;
+    int numLocations;
+    unsigned char *alignment;
+    int alignmentLength;
+    int alphabetLength;
+} db200_EdlibAlignResult; /* layout-identical to EdlibAlignResult */
+
+db200_EdlibAlignConfig db200_edlibNewAlignConfig(int k, int mode, int task,
+                                                 const db200_EdlibEqualityPair *additionalEqualities,
+                                                 int additionalEqualitiesLength);
+db200_EdlibAlignConfig db200_edlibDefaultAlignConfig(void);
+db200_EdlibAlignResult db200_edlibAlign(const char *query, int queryLength, const char *target, int targetLength,
+                                        const db200_EdlibAlignConfig config);
+void db200_edlibFreeAlignResult(db200_EdlibAlignResult result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYSGU_B200_ALIGN_H */

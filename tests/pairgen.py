@@ -57,13 +57,13 @@ def sw_pairs(seed: int, n: int, max_len: int = 400):
         elif kind == 1:  # unrelated random
             add(rand_dna(rng, rng.randint(1, max_len)), rand_dna(rng, rng.randint(1, max_len)))
         elif kind == 2:  # window / clip (long query, short target), clip lower-case
-            q = rand_dna(rng, rng.randint(max_len // 2, max_len))
-            L = rng.randint(9, min(150, len(q)))
+            q = rand_dna(rng, rng.randint(max(max_len // 2, 10), max(max_len, 10)))
+            L = rng.randint(min(9, len(q)), min(150, len(q)))
             s = rng.randint(0, len(q) - L)
             add(q, mutate(rng, q[s:s + L], 0.02, 0.01, 0.01).lower() or "a")
         elif kind == 3:  # clip / window (short query, long target)
-            t = rand_dna(rng, rng.randint(max_len // 2, max_len))
-            L = rng.randint(9, min(150, len(t)))
+            t = rand_dna(rng, rng.randint(max(max_len // 2, 10), max(max_len, 10)))
+            L = rng.randint(min(9, len(t)), min(150, len(t)))
             s = rng.randint(0, len(t) - L)
             add(mutate(rng, t[s:s + L], 0.02, 0.01, 0.01) or "A", t)
         elif kind == 4:  # tandem duplication in the target (ties, second best)
@@ -75,7 +75,7 @@ def sw_pairs(seed: int, n: int, max_len: int = 400):
             t = rand_dna(rng, rng.randint(0, 40)) + u + rand_dna(rng, rng.randint(0, 40))
             add(rand_dna(rng, rng.randint(0, 30)) + u * rng.randint(2, 4) + rand_dna(rng, rng.randint(0, 30)), t)
         elif kind == 6:  # N's and non-ACGT bytes, mixed case
-            q = rand_dna(rng, rng.randint(10, max_len))
+            q = rand_dna(rng, rng.randint(10, max(max_len, 10)))
             t = mutate(rng, q, 0.05, 0.02, 0.02) or "A"
             add(mixed_case(rng, sprinkle(rng, q, 0.05, "NnXRY-*")), mixed_case(rng, sprinkle(rng, t, 0.05, "NnKM.")))
         elif kind == 7:  # no match at all / all-N
@@ -92,7 +92,7 @@ def sw_pairs(seed: int, n: int, max_len: int = 400):
                 t[rng.randrange(L)] = "N"
             add(rand_dna(rng, rng.randint(0, 20)) + q + rand_dna(rng, rng.randint(0, 20)), "".join(t))
         elif kind == 9:  # indel-rich (band doubling in the traceback)
-            q = rand_dna(rng, rng.randint(50, max_len))
+            q = rand_dna(rng, rng.randint(min(50, max_len), max(max_len, 10)))
             add(q, mutate(rng, q, 0.03, 0.08, 0.08) or "A")
         elif kind == 10:  # low complexity / homopolymer / dinucleotide
             u = rng.choice(["A", "AC", "AT", "CAG", "AAAT"])
@@ -100,7 +100,7 @@ def sw_pairs(seed: int, n: int, max_len: int = 400):
             t = mutate(rng, (u * (max_len // len(u)))[:rng.randint(5, max_len)], 0.03, 0.01, 0.01) or "A"
             add(q, t)
         elif kind == 11:  # large deletion / insertion inside an otherwise identical pair
-            q = rand_dna(rng, rng.randint(80, max_len))
+            q = rand_dna(rng, rng.randint(min(80, max(max_len, 45)), max(max_len, 45)))
             a = rng.randint(20, len(q) - 20)
             gap = rng.randint(1, 60)
             if rng.random() < 0.5:
@@ -111,7 +111,7 @@ def sw_pairs(seed: int, n: int, max_len: int = 400):
             q = rand_dna(rng, rng.randint(1, max_len))
             add(q, q)
         else:            # generic related pair, 10-20 % mixed error
-            q = rand_dna(rng, rng.randint(20, max_len))
+            q = rand_dna(rng, rng.randint(min(20, max_len), max(max_len, 10)))
             e = rng.uniform(0.0, 0.2)
             add(q, mutate(rng, q, e * 0.6, e * 0.2, e * 0.2) or "A")
     return qs[:n], ts[:n]
