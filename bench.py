@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 alignment engine (contract: see the task description).
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU cores on host threads
+
+Workload (BASELINE.json configs[1]): synthetic paired-end soft-clip re-mapping,
+StripedSmithWaterman(query = 1000/1500/2000 bp reference window, 2,-8,6,1)(target = 15-300 bp soft clip),
+score + begin/end coordinates + cigar for every pair (flag = 1, what dysgu's wrapper always passes).
+One step = one pass of the whole pipeline over one batch of pairs (per GPU).
+
+Metric: alignment GCUPS = sum(len(query) * len(target)) / time, forward matrix counted once.
+  value : device-timed (CUDA events on the launching stream), inputs resident in HBM
+  e2e   : the same metric through the host C-ABI call (db200_sw_batch_host) with pinned host buffers,
+          H2D and D2H inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "alignment GCUPS (device-timed)"
+UNIT = "GCUPS"
+# lane-instructions of the minimal packed Smith-Waterman cell update: 7 s16x2 instructions per 2 cells
+# (U, H', H'-gapO, H, V, profile merge, running max) - see DESIGN.md "roofline"
+SW_LANE_OPS_PER_CELL = 3.5
+# measured on this pool's B200s by dysgu_b200/int_peak (profiles/r01_int_peak.json): VIADDMNMX.S16x2 lane-ops/s
+INT_PEAK_FALLBACK = 1.81e13
+
+
+def load_measured_peaks():
+    out = {"hbm_gbs": 6650.0, "source": "fallback"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            out["hbm_gbs"] = float(d.get("hbm_gbs", out["hbm_gbs"]))
+            out["source"] = "measured"
+        except Exception:
+            pass
+    ip = os.path.join(ROOT, "profiles", "r01_int_peak.json")
+    out["int_lane_ops"] = INT_PEAK_FALLBACK
+    if os.path.exists(ip):
+        try:
+            d = json.load(open(ip))
+            out["int_lane_ops"] = float(d["lane_ops_per_s"]["viaddmnmx_s16x2_relu"])
+        except Exception:
+            pass
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_array(L, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = L.db200_host_alloc(max(n, 1))
+    if not ptr:
+        raise RuntimeError("pinned allocation failed")
+    buf = (C.c_uint8 * max(n, 1)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def make_workload(pairs: int, seed: int):
+    from dysgu_b200 import workloads
+    q, t, prm = workloads.remap_windows(pairs, seed=seed)
+    cells = float((q.lengths.astype(np.float64) * t.lengths.astype(np.float64)).sum())
+    return q, t, prm, cells
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref, compiled unmodified from the reference checkout)
+    on all host threads, same workload definition, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    try:
+        from oracle import oracle as O
+        O.driver_lib()
+    except Exception as exc:  # the oracle always exists in this tier; report loudly if the prebuilt files are missing
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not loadable: %s" % str(exc)[:120]}))
+        return 0
+    cores = os.cpu_count() or 1
+    sample = args.ref_pairs
+    q, t, prm, cells = make_workload(sample, seed=20261021)
+    qcsr, tcsr = (q.buf, q.off), (t.buf, t.off)
+
+    def step():
+        r = O.ref_sw(qcsr, tcsr, prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"], nthreads=cores, csr=True)
+        return r.seconds
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    inner = 0.0
+    for _ in range(args.steps):
+        inner += step()
+    wall = time.perf_counter() - t0
+    value = cells * args.steps / inner / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * inner / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": "remap_windows: SSW(window 1000/1500/2000 bp; 2,-8,6,1)(soft clip 15-300 bp), score+coords+cigar",
+                   "pairs_per_step": sample, "cells_per_step": cells},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": "%d pairs per step of the same workload, ssw_init+ssw_align per pair (C level, ssw.c compiled -O2)" % sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from dysgu_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the alignment engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group(backend="nccl", device_id=dev)
+    L = _lib.lib()
+    _lib.check(L.db200_init(local_rank), "db200_init")
+
+    # ---- per-rank shard of the workload (pairs are independent: weak scaling, no collective on the data path)
+    pairs = args.pairs
+    q, t, prm, cells = make_workload(pairs, seed=20261021 + rank)
+    n = len(q)
+    q_bytes, t_bytes = int(q.off[-1]), int(t.off[-1])
+    max_q = int(q.lengths.max())
+
+    prm_c = _lib.SwParams()
+    prm_c.match, prm_c.mismatch, prm_c.gap_open, prm_c.gap_extend = prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"]
+    prm_c.score_size, prm_c.flag = 2, 1
+
+    # ---- device-resident arm --------------------------------------------------------------------------
+    d_q = torch.from_numpy(q.buf).to(dev)
+    d_t = torch.from_numpy(t.buf).to(dev)
+    d_qoff = torch.from_numpy(q.off).to(dev)
+    d_toff = torch.from_numpy(t.off).to(dev)
+    cig_cap = int(4 * n + 1024)
+    d_res = torch.zeros((n, 8), dtype=torch.int32, device=dev)
+    d_cig = torch.zeros(cig_cap, dtype=torch.int32, device=dev)
+    d_coff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def device_step():
+        rc = L.db200_sw_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
+                                     d_toff.data_ptr(), t_bytes, n, max_q, None, d_res.data_ptr(), d_cig.data_ptr(), cig_cap,
+                                     d_coff.data_ptr(), d_status.data_ptr(), None, C.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "db200_sw_batch_device")
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    bad = int((d_status != 0).sum().item())
+    if bad:
+        raise SystemExit("bench.py: %d pairs reported a non-zero status" % bad)
+    checksum = int(d_res[:, 0].sum().item())
+
+    L.db200_profile_enable(local_rank, 1)
+    L.db200_kernel_launches(local_rank, 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = int(L.db200_kernel_launches(local_rank, 1))
+    stage_ms = (C.c_float * 16)()
+    L.db200_profile_collect(local_rank, stage_ms, 16)
+    L.db200_profile_enable(local_rank, 0)
+    stage_ms = [float(x) for x in stage_ms]
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    total_cells = cells * world  # every rank processes a shard of the same size and shape distribution
+    if dist is not None:
+        tc = torch.tensor([cells], dtype=torch.float64, device=dev)
+        dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+        total_cells = float(tc.item())
+    value = total_cells * args.steps / (ms_max * 1e-3) / 1e9
+
+    # ---- end-to-end arm: host C-ABI call, pinned host buffers, H2D + D2H inside the timed region --------------
+    hq = pinned_array(L, (q_bytes,), np.uint8); hq[:] = q.buf
+    ht = pinned_array(L, (t_bytes,), np.uint8); ht[:] = t.buf
+    hqo = pinned_array(L, (n + 1,), np.int64); hqo[:] = q.off
+    hto = pinned_array(L, (n + 1,), np.int64); hto[:] = t.off
+    hres = pinned_array(L, (n, 8), np.int32)
+    hcig = pinned_array(L, (cig_cap,), np.uint32)
+    hcoff = pinned_array(L, (n + 1,), np.int64)
+    hstat = pinned_array(L, (n,), np.int32)
+
+    def host_step():
+        rc = L.db200_sw_batch_host(local_rank, C.byref(prm_c), hq.ctypes.data, hqo.ctypes.data, ht.ctypes.data, hto.ctypes.data, n,
+                                   None, hres.ctypes.data, hcig.ctypes.data, cig_cap, hcoff.ctypes.data, hstat.ctypes.data)
+        _lib.check(rc, "db200_sw_batch_host")
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_step()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+    e2e_value = total_cells * e2e_steps / float(tdt.item()) / 1e9
+    if int(hres[:, 0].astype(np.int64).sum()) != checksum:
+        raise SystemExit("bench.py: host and device arms disagree")
+    ncig = int(hcoff[n])
+    h2d = q_bytes + t_bytes + 2 * 8 * (n + 1)
+    d2h = 32 * n + 4 * n + 8 * (n + 1) + 4 * ncig
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (forward scoring pass) ---------------------------------------------
+    peaks = load_measured_peaks()
+    fwd_ms = stage_ms[3] / args.steps          # forward sw_pass_kernel launches of one step (this rank)
+    fwd_lane_ops = cells * SW_LANE_OPS_PER_CELL
+    achieved = fwd_lane_ops / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None
+    peak = peaks["int_lane_ops"] / 1e12
+    alg_bytes = (q_bytes + t_bytes) / 2.0 + 16.0 * n   # packed 4-bit codes in, one PassOut record out
+    roofline = {
+        "bound": "int_alu", "kernel": "sw_pass_kernel (forward scoring pass, all length buckets)",
+        "achieved": achieved, "peak": peak, "unit": "Tlaneop/s (s16x2 DPX lane-instructions)",
+        "frac": (achieved / peak) if achieved else None, "peak_source": "measured: dysgu_b200/int_peak on this pool (profiles/r01_int_peak.json)",
+        "ops_per_cell": SW_LANE_OPS_PER_CELL, "kernel_ms_per_step": fwd_ms, "kernel_gcups": cells / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None,
+        "hbm_algorithmic_gbs": alg_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None, "hbm_peak_gbs": peaks["hbm_gbs"],
+        "hbm_peak_source": peaks["source"], "traffic": None,
+        "stage_ms_per_step": {k: v / args.steps for k, v in zip(
+            ["begin", "pack", "bucket", "forward", "forward_rerun", "reverse_prep", "reverse", "reverse_rerun", "finalize",
+             "traceback", "cigar"], stage_ms[:11])},
+    }
+
+    # ---- CPU baseline (rank 0, N = 1 only): the reference cores on all host threads, bounded sample ------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import oracle as O
+            cores = os.cpu_count() or 1
+            sample = min(n, args.ref_pairs)
+            qs, ts = q.take(np.arange(sample)), t.take(np.arange(sample))
+            scell = float((qs.lengths.astype(np.float64) * ts.lengths.astype(np.float64)).sum())
+            O.ref_sw((qs.buf, qs.off), (ts.buf, ts.off), prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"],
+                     nthreads=cores, csr=True)  # warm
+            r = O.ref_sw((qs.buf, qs.off), (ts.buf, ts.off), prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"],
+                         nthreads=cores, csr=True)
+            cpu_baseline = {"value": scell / r.seconds / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+                            "sample": "first %d pairs of the step's batch, ssw_init+ssw_align per pair at C level (ssw.c -O2), %.1f s" % (sample, r.seconds)}
+            # spot parity on the sample against the reference itself
+            mism = int((r.fixed[:, :7] != hres[:sample, :7]).any(axis=1).sum())
+            cpu_baseline["parity_mismatches_on_sample"] = mism
+        except Exception as exc:
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % str(exc)[:100]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+        "data": "synthetic",
+        "config": {"workload": "remap_windows: SSW(window 1000/1500/2000 bp; 2,-8,6,1)(soft clip 15-300 bp), score+coords+cigar",
+                   "pairs_per_step_per_gpu": n, "cells_per_step_per_gpu": cells, "input_bytes_per_step_per_gpu": q_bytes + t_bytes,
+                   "l2": "inputs larger than L2 (%.0f MB per step)" % ((q_bytes + t_bytes) / 1e6), "sharding": "pairs by rank, no collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": 1e3 * float(tdt.item()) / e2e_steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "checksum_score1": checksum,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1 << 19, help="pairs per step per GPU")
+    ap.add_argument("--ref-pairs", type=int, default=40000, help="pairs per step of the CPU reference sample")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,11 +1,465 @@
-// Edit-distance pipeline (placeholder until the Myers kernels land in this file).
+// Batched edit-distance pipeline on the device: alphabet / Peq build -> bucket -> Myers forward pass ->
+// best score + end locations -> (HW, task >= locations) reverse passes for the start locations.
+//
+// Reference behaviour being reproduced (dysgu v1.9.0): edlib.pyx:57-156 (wrapper), edlib.cpp:141-296
+// (driver: alphabet, empty sequences, k handling, start locations), 355-381 (Peq), 546-709, 735-944.
 #include "ed_kernels.cuh"
+
 namespace db200 {
-int ed_batch_device_impl(Engine *, Arena &, const db200_ed_params *, const uint8_t *, const int64_t *, int64_t, const uint8_t *,
-                         const int64_t *, int64_t, int64_t, int32_t, int32_t, const int32_t *, db200_ed_result *, int32_t *, int64_t,
-                         int64_t *, int64_t *, cudaStream_t)
+
+static const int ED_CFG_WL[ED_NCFG] = {1, 2, 4, 4, 4, 4, 4, 4, 8, 16, 32};
+static const int ED_CFG_G[ED_NCFG] = {1, 1, 1, 2, 4, 8, 16, 32, 32, 32, 32};
+__device__ __constant__ int d_ed_cfg_words[ED_NCFG] = {1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024};
+
+__device__ __forceinline__ int ed_cfg_for(int W)
 {
-    set_error("edit distance: not built yet");
-    return DB200_ERR_INTERNAL;
+    int c = 0;
+    while (c < ED_NCFG - 1 && d_ed_cfg_words[c] < W) ++c;
+    return c;
 }
+
+struct EdPrepArgs {
+    const uint8_t *qbuf, *tbuf;
+    const int64_t *qoff, *toff;
+    const int32_t *k;      // may be null
+    int32_t k_default;
+    int32_t mode, task;
+    int64_t npairs;
+    EdPair *pairs;
+    int32_t *peq_words;    // per pair, for the scan
+    int32_t *hlog_words;
+    int32_t *hist;         // [ED_NCFG * ED_LBINS]
+    db200_ed_result *results;
+};
+
+// one warp per pair: symbol sets, sizes, special cases (edlib.cpp:153-179)
+__global__ void ed_prep_kernel(EdPrepArgs a)
+{
+    __shared__ uint32_t bm[8][16]; // per warp: 8 words query set, 8 words target set
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (p >= a.npairs) return;
+    if (lane < 16) bm[warp][lane] = 0;
+    __syncwarp();
+    const int64_t q0 = a.qoff[p], t0 = a.toff[p];
+    const int m = (int)(a.qoff[p + 1] - q0), n = (int)(a.toff[p + 1] - t0);
+    for (int i = lane; i < m; i += 32) { const uint8_t c = a.qbuf[q0 + i]; atomicOr(&bm[warp][c >> 5], 1u << (c & 31)); }
+    for (int i = lane; i < n; i += 32) { const uint8_t c = a.tbuf[t0 + i]; atomicOr(&bm[warp][8 + (c >> 5)], 1u << (c & 31)); }
+    __syncwarp();
+    int au = 0, at = 0;
+    if (lane < 8) { au = __popc(bm[warp][lane] | bm[warp][8 + lane]); at = __popc(bm[warp][8 + lane]); }
+    for (int o = 4; o >= 1; o >>= 1) { au += __shfl_xor_sync(0xFFFFFFFFu, au, o); at += __shfl_xor_sync(0xFFFFFFFFu, at, o); }
+    au = __shfl_sync(0xFFFFFFFFu, au, 0);
+    at = __shfl_sync(0xFFFFFFFFu, at, 0);
+    if (lane != 0) return;
+    EdPair pr;
+    memset(&pr, 0, sizeof(pr));
+    pr.q_off = q0; pr.t_off = t0; pr.m = m; pr.n = n;
+    pr.W = (m + 63) >> 6;
+    pr.At = at;
+    pr.alphabet = au;
+    pr.k = a.k ? a.k[p] : a.k_default;
+    pr.best = -1;
+    pr.cfg = ed_cfg_for(pr.W);
+    db200_ed_result r;
+    r.status = 0; r.edit_distance = -1; r.alphabet_length = au; r.num_locations = 0;
+    int pw = 0, hw = 0;
+    if (m == 0 || n == 0) {
+        pr.special = 1;
+        pr.nloc = 1;
+        if (a.mode == DB200_ED_MODE_NW) pr.best = max(m, n);
+        else if (a.mode == DB200_ED_MODE_SHW || a.mode == DB200_ED_MODE_HW) pr.best = m;
+        else { pr.nloc = 0; r.status = 1; }
+        r.edit_distance = pr.best;
+        r.num_locations = pr.nloc;
+    } else if (a.mode != DB200_ED_MODE_NW && a.mode != DB200_ED_MODE_SHW && a.mode != DB200_ED_MODE_HW) {
+        pr.special = 1; r.status = 1;
+    } else if (pr.W > d_ed_cfg_words[ED_NCFG - 1]) {
+        pr.special = 1; r.status = 1; // queries beyond 65536 symbols are not provided by the device path
+    } else {
+        const bool need_rev = (a.mode == DB200_ED_MODE_HW && a.task >= DB200_ED_TASK_LOC);
+        pw = at * pr.W * (need_rev ? 2 : 1);
+        hw = (a.mode != DB200_ED_MODE_NW) ? ((n + 15) >> 4) : 0;
+        const int lb = min(n >> 6, ED_LBINS - 1);
+        atomicAdd(&a.hist[pr.cfg * ED_LBINS + (ED_LBINS - 1 - lb)], 1);
+    }
+    a.pairs[p] = pr;
+    a.peq_words[p] = pw;
+    a.hlog_words[p] = hw;
+    a.results[p] = r;
 }
+
+struct EdBuildArgs {
+    const uint8_t *qbuf, *tbuf;
+    EdPair *pairs;
+    const int64_t *peq_off, *hlog_off;
+    int64_t npairs;
+    uint64_t *peq;
+    uint8_t *tcodes;
+    int32_t mode, task;
+    const uint8_t *eq_pairs;   // device copy of (first, second) bytes
+    int32_t n_eq_pairs;
+    const int32_t *bin_start;
+    int32_t *bin_fill;
+    int32_t *tasks;
+};
+
+// one warp per pair: target symbols -> dense row ids, re-coded target, match vectors of the query
+// (forward and, for HW start locations, reversed), bucket scatter.  edlib.cpp:355-381, 1433-1472, 60-91.
+__global__ void ed_build_kernel(EdBuildArgs a)
+{
+    __shared__ uint8_t rank_s[8][256];
+    __shared__ uint32_t tset[8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (p >= a.npairs) return;
+    EdPair pr = a.pairs[p];
+    if (pr.special) return;
+    pr.peq_off = a.peq_off[p];
+    pr.hlog_off = a.hlog_off[p];
+    const uint8_t *q = a.qbuf + pr.q_off, *t = a.tbuf + pr.t_off;
+    if (lane < 8) tset[warp][lane] = 0;
+    __syncwarp();
+    for (int i = lane; i < pr.n; i += 32) { const uint8_t c = t[i]; atomicOr(&tset[warp][c >> 5], 1u << (c & 31)); }
+    __syncwarp();
+    // rank of every byte among the target's symbols (0xFF: not a target symbol)
+    for (int c = lane; c < 256; c += 32) {
+        const uint32_t wbits = tset[warp][c >> 5];
+        int r = 0xFF;
+        if ((wbits >> (c & 31)) & 1u) {
+            r = __popc(wbits & ((1u << (c & 31)) - 1u));
+            for (int w = 0; w < (c >> 5); ++w) r += __popc(tset[warp][w]);
+        }
+        rank_s[warp][c] = (uint8_t)r;
+    }
+    __syncwarp();
+    uint8_t *tc = a.tcodes + pr.t_off;
+    for (int i = lane; i < pr.n; i += 32) tc[i] = rank_s[warp][t[i]];
+    const bool need_rev = (a.mode == DB200_ED_MODE_HW && a.task >= DB200_ED_TASK_LOC);
+    const int W = pr.W, m = pr.m, At = pr.At;
+    uint64_t *peq = a.peq + pr.peq_off;
+    const int total = At * W * (need_rev ? 2 : 1);
+    for (int i = lane; i < total; i += 32) peq[i] = 0ull;
+    __syncwarp();
+    // each lane owns whole words, so no atomics are needed
+    for (int dir = 0; dir < (need_rev ? 2 : 1); ++dir) {
+        uint64_t *tab = peq + (int64_t)dir * At * W;
+        for (int w = lane; w < W; w += 32) {
+            for (int b = 0; b < 64; ++b) {
+                const int i = w * 64 + b;
+                if (i >= m) break;
+                const uint8_t c = dir ? q[m - 1 - i] : q[i];
+                const int r = rank_s[warp][c];
+                if (r != 0xFF) tab[(int64_t)r * W + w] |= 1ull << b;
+                for (int e = 0; e < a.n_eq_pairs; ++e) {   // additionalEqualities: symmetric, not transitive
+                    const uint8_t x = a.eq_pairs[2 * e], y = a.eq_pairs[2 * e + 1];
+                    if (c == x && rank_s[warp][y] != 0xFF) tab[(int64_t)rank_s[warp][y] * W + w] |= 1ull << b;
+                    if (c == y && rank_s[warp][x] != 0xFF) tab[(int64_t)rank_s[warp][x] * W + w] |= 1ull << b;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        a.pairs[p] = pr;
+        const int lb = min(pr.n >> 6, ED_LBINS - 1);
+        const int key = pr.cfg * ED_LBINS + (ED_LBINS - 1 - lb);
+        const int pos = a.bin_start[key] + atomicAdd(&a.bin_fill[key], 1);
+        a.tasks[pos] = (int32_t)p;
+    }
+}
+
+__global__ void ed_binscan_kernel(const int32_t *hist, int32_t *bin_start, int32_t *seg_begin, int32_t *seg_count)
+{
+    __shared__ int32_t tot[ED_NCFG];
+    const int tid = threadIdx.x;
+    if (tid < ED_NCFG) {
+        int s = 0;
+        for (int b = 0; b < ED_LBINS; ++b) s += hist[tid * ED_LBINS + b];
+        tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid < ED_NCFG) {
+        int acc = 0;
+        for (int c = 0; c < tid; ++c) acc += tot[c];
+        seg_begin[tid] = acc;
+        seg_count[tid] = tot[tid];
+        for (int b = 0; b < ED_LBINS; ++b) { bin_start[tid * ED_LBINS + b] = acc; acc += hist[tid * ED_LBINS + b]; }
+    }
+}
+
+struct EdCountArgs {
+    EdPair *pairs;
+    const uint32_t *hlog;
+    const int32_t *nw_score;
+    db200_ed_result *results;
+    int32_t *nloc;
+    int32_t *rev_count;   // [ED_NCFG] start-location tasks per config
+    int64_t npairs;
+    int32_t mode, task;
+};
+
+// thread per pair: best score over the last row and the number of end locations (edlib.cpp:663-698, 930-938)
+__global__ void ed_count_kernel(EdCountArgs a)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= a.npairs) return;
+    EdPair &pr = a.pairs[p];
+    if (pr.special) { a.nloc[p] = pr.nloc; return; }
+    int best = -1, cnt = 0, ntask = 0;
+    if (a.mode == DB200_ED_MODE_NW) {
+        const int d = a.nw_score[p];
+        if (pr.k < 0 || d <= pr.k) { best = d; cnt = 1; }
+    } else {
+        const uint32_t *hl = a.hlog + pr.hlog_off;
+        const bool col_m1 = (pr.m & 63) != 0;
+        int score = pr.m;
+        int mn = col_m1 ? pr.m : 0x7FFFFFFF;
+        int c = col_m1 ? 1 : 0;
+        for (int j = 0; j < pr.n; ++j) {
+            const uint32_t d = (hl[j >> 4] >> ((j & 15) * 2)) & 3u;
+            score += (int)(d & 1u) - (int)(d >> 1);
+            if (score < mn) { mn = score; c = 1; }
+            else if (score == mn) ++c;
+        }
+        if (pr.k < 0 || mn <= pr.k) {
+            best = mn; cnt = c;
+            ntask = cnt - ((col_m1 && mn == pr.m) ? 1 : 0); // the -1 end location needs no reverse pass
+        }
+    }
+    pr.best = best;
+    pr.nloc = cnt;
+    a.nloc[p] = cnt;
+    a.results[p].edit_distance = best;
+    a.results[p].num_locations = cnt;
+    if (a.mode == DB200_ED_MODE_HW && a.task >= DB200_ED_TASK_LOC && ntask > 0) atomicAdd(&a.rev_count[pr.cfg], ntask);
+}
+
+__global__ void ed_revscan_kernel(const int32_t *rev_count, int32_t *rev_begin)
+{
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int c = 0; c < ED_NCFG; ++c) { rev_begin[c] = acc; acc += rev_count[c]; }
+    }
+}
+
+struct EdEmitArgs {
+    EdPair *pairs;
+    const uint32_t *hlog;
+    const int64_t *loc_off;
+    int32_t *loc_buf;
+    int64_t loc_cap;
+    int32_t *loc_pair;
+    const int32_t *rev_begin;
+    int32_t *rev_fill;
+    int32_t *rev_tasks;
+    int32_t *overflow;
+    int64_t npairs;
+    int32_t mode, task;
+};
+
+// thread per pair: end locations in ascending order; start locations that need no DP (edlib.cpp:214-267)
+__global__ void ed_emit_kernel(EdEmitArgs a)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= a.npairs) return;
+    EdPair &pr = a.pairs[p];
+    const int64_t o = a.loc_off[p];
+    pr.loc_off = o;
+    if (pr.nloc <= 0) return;
+    if (o + pr.nloc > a.loc_cap) { atomicExch(a.overflow, 1); return; }
+    int32_t *out = a.loc_buf + 2 * o;
+    if (pr.special) {
+        out[0] = DB200_ED_NO_START;
+        out[1] = (a.mode == DB200_ED_MODE_NW) ? pr.n - 1 : -1;
+        return;
+    }
+    const int start_fixed = (a.task >= DB200_ED_TASK_LOC) ? 0 : DB200_ED_NO_START;
+    if (a.mode == DB200_ED_MODE_NW) { out[0] = start_fixed; out[1] = pr.n - 1; return; }
+    const uint32_t *hl = a.hlog + pr.hlog_off;
+    const bool want_rev = (a.mode == DB200_ED_MODE_HW && a.task >= DB200_ED_TASK_LOC);
+    int w = 0;
+    int score = pr.m;
+    if ((pr.m & 63) != 0 && score == pr.best) { out[0] = start_fixed; out[1] = -1; ++w; }
+    for (int j = 0; j < pr.n; ++j) {
+        const uint32_t d = (hl[j >> 4] >> ((j & 15) * 2)) & 3u;
+        score += (int)(d & 1u) - (int)(d >> 1);
+        if (score == pr.best) {
+            out[2 * w] = start_fixed;
+            out[2 * w + 1] = j;
+            if (want_rev) {
+                const int64_t idx = o + w;
+                a.loc_pair[idx] = (int32_t)p;
+                const int pos = a.rev_begin[pr.cfg] + atomicAdd(&a.rev_fill[pr.cfg], 1);
+                a.rev_tasks[pos] = (int32_t)idx;
+            }
+            ++w;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int WL, int G, bool REV>
+static int launch_myers(Engine *e, const EdArgs &a, cudaStream_t st)
+{
+    static int blocks_cached[16] = {0};
+    int &blocks = blocks_cached[e->device & 15];
+    if (blocks == 0) {
+        int per_sm = 0;
+        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ed_myers_kernel<WL, G, REV>, 128, 0));
+        if (per_sm < 1) per_sm = 1;
+        blocks = e->sm_count * per_sm;
+    }
+    ed_myers_kernel<WL, G, REV><<<blocks, 128, 0, st>>>(a);
+    count_launch(e);
+    DB200_CUDA_CHECK(cudaGetLastError());
+    return DB200_OK;
+}
+
+template <bool REV>
+static int launch_ed_cfg(Engine *e, int cfg, const EdArgs &a, cudaStream_t st)
+{
+    switch (cfg) {
+        case 0: return launch_myers<1, 1, REV>(e, a, st);
+        case 1: return launch_myers<2, 1, REV>(e, a, st);
+        case 2: return launch_myers<4, 1, REV>(e, a, st);
+        case 3: return launch_myers<4, 2, REV>(e, a, st);
+        case 4: return launch_myers<4, 4, REV>(e, a, st);
+        case 5: return launch_myers<4, 8, REV>(e, a, st);
+        case 6: return launch_myers<4, 16, REV>(e, a, st);
+        case 7: return launch_myers<4, 32, REV>(e, a, st);
+        case 8: return launch_myers<8, 32, REV>(e, a, st);
+        case 9: return launch_myers<16, 32, REV>(e, a, st);
+        default: return launch_myers<32, 32, REV>(e, a, st);
+    }
+}
+
+int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const uint8_t *d_qbuf, const int64_t *d_qoff,
+                         int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
+                         int32_t max_query_len, int32_t max_target_len, const int32_t *d_k, db200_ed_result *d_results,
+                         int32_t *d_loc_buf, int64_t loc_cap, int64_t *d_loc_off, int64_t *loc_total, cudaStream_t st)
+{
+    if (npairs < 0 || !prm || !d_results) { set_error("ed_batch: bad arguments"); return DB200_ERR_ARG; }
+    if (prm->task == DB200_ED_TASK_PATH) { set_error("ed_batch: task 'path' is not provided by the device path"); return DB200_ERR_ARG; }
+    if (prm->task < 0 || prm->task > 2) { set_error("ed_batch: bad task"); return DB200_ERR_ARG; }
+    if (npairs == 0) {
+        if (d_loc_off) DB200_CUDA_CHECK(cudaMemsetAsync(d_loc_off, 0, sizeof(int64_t), st));
+        if (loc_total) *loc_total = 0;
+        return DB200_OK;
+    }
+    if (npairs > (int64_t)1 << 30) { set_error("ed_batch: at most 2^30 pairs per call"); return DB200_ERR_ARG; }
+    if (!d_loc_buf || !d_loc_off) { set_error("ed_batch: location buffers are required"); return DB200_ERR_ARG; }
+    (void)max_target_len;
+    const bool need_rev = (prm->mode == DB200_ED_MODE_HW && prm->task >= DB200_ED_TASK_LOC);
+    // match-vector storage: rows = distinct target symbols (<= 256, and <= target length), W words each.
+    // Upper bound without a device round trip: min(256, n) * ceil(m/64) per pair <= (t_bytes_pair) * W ...
+    // we bound rows by min(256, max alphabet) using the caller-provided lengths.
+    const int64_t Wmax = ((int64_t)std::max(max_query_len, 1) + 63) / 64;
+    const size_t nbins = (size_t)ED_NCFG * ED_LBINS;
+
+    EdPair *pairs = ws.alloc<EdPair>(npairs);
+    int32_t *peq_words = ws.alloc<int32_t>(npairs);
+    int32_t *hlog_words = ws.alloc<int32_t>(npairs);
+    int64_t *peq_off = ws.alloc<int64_t>(npairs + 1);
+    int64_t *hlog_off = ws.alloc<int64_t>(npairs + 1);
+    int64_t *scan_tmp = ws.alloc<int64_t>(scan_tmp_count(npairs) * 2);
+    int32_t *bins = ws.alloc<int32_t>(nbins * 3 + 256);
+    int32_t *tasks = ws.alloc<int32_t>(npairs);
+    uint8_t *tcodes = ws.alloc<uint8_t>((size_t)t_bytes + 64);
+    uint32_t *hlog = ws.alloc<uint32_t>((size_t)(t_bytes / 16 + npairs + 64));
+    int32_t *nw_score = ws.alloc<int32_t>(npairs);
+    int32_t *nloc = ws.alloc<int32_t>(npairs);
+    int32_t *loc_pair = ws.alloc<int32_t>((size_t)std::max<int64_t>(loc_cap, 1));
+    int32_t *rev_tasks = ws.alloc<int32_t>((size_t)std::max<int64_t>(loc_cap, 1));
+    uint8_t *eq_dev = ws.alloc<uint8_t>(2 * (size_t)std::max(prm->n_eq_pairs, 1));
+    if (!pairs || !peq_words || !hlog_words || !peq_off || !hlog_off || !scan_tmp || !bins || !tasks || !tcodes || !hlog ||
+        !nw_score || !nloc || !loc_pair || !rev_tasks || !eq_dev) {
+        set_error("ed_batch: device workspace allocation failed");
+        return DB200_ERR_NOMEM;
+    }
+    int32_t *hist = bins, *bin_start = bins + nbins, *bin_fill = bins + 2 * nbins;
+    int32_t *small = bins + 3 * nbins;
+    int32_t *seg_begin = small, *seg_count = small + 16, *rev_count = small + 32, *rev_begin = small + 48, *rev_fill = small + 64;
+    int32_t *counters = small + 96; // 32 work counters
+    int32_t *overflow = small + 160;
+    DB200_CUDA_CHECK(cudaMemsetAsync(bins, 0, (nbins * 3 + 256) * sizeof(int32_t), st));
+    if (prm->n_eq_pairs > 0)
+        DB200_CUDA_CHECK(cudaMemcpyAsync(eq_dev, prm->eq_pairs, 2 * (size_t)prm->n_eq_pairs, cudaMemcpyHostToDevice, st));
+
+    const int TB = 256;
+    const unsigned gpair = (unsigned)((npairs + TB - 1) / TB), gwarp = (unsigned)((npairs * 32 + TB - 1) / TB);
+    prof_mark(e, st, ST_BEGIN);
+
+    EdPrepArgs pa;
+    pa.qbuf = d_qbuf; pa.tbuf = d_tbuf; pa.qoff = d_qoff; pa.toff = d_toff; pa.k = d_k; pa.k_default = prm->k;
+    pa.mode = prm->mode; pa.task = prm->task; pa.npairs = npairs; pa.pairs = pairs; pa.peq_words = peq_words;
+    pa.hlog_words = hlog_words; pa.hist = hist; pa.results = d_results;
+    ed_prep_kernel<<<gwarp, TB, 0, st>>>(pa);
+    count_launch(e);
+    exclusive_scan_i32_i64(e, peq_words, peq_off, npairs, scan_tmp, st);
+    exclusive_scan_i32_i64(e, hlog_words, hlog_off, npairs, scan_tmp, st);
+    ed_binscan_kernel<<<1, 32, 0, st>>>(hist, bin_start, seg_begin, seg_count);
+    count_launch(e);
+
+    // The Peq pool size depends on the data (distinct target symbols); it is the one quantity read back.
+    int64_t peq_total = 0;
+    DB200_CUDA_CHECK(cudaMemcpyAsync(&peq_total, peq_off + npairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    DB200_CUDA_CHECK(cudaStreamSynchronize(st));
+    (void)Wmax;
+    uint64_t *peq = ws.alloc<uint64_t>((size_t)peq_total + 64);
+    if (!peq) { set_error("ed_batch: device workspace allocation failed (Peq, %lld words)", (long long)peq_total); return DB200_ERR_NOMEM; }
+
+    EdBuildArgs ba;
+    ba.qbuf = d_qbuf; ba.tbuf = d_tbuf; ba.pairs = pairs; ba.peq_off = peq_off; ba.hlog_off = hlog_off; ba.npairs = npairs;
+    ba.peq = peq; ba.tcodes = tcodes; ba.mode = prm->mode; ba.task = prm->task; ba.eq_pairs = eq_dev; ba.n_eq_pairs = prm->n_eq_pairs;
+    ba.bin_start = bin_start; ba.bin_fill = bin_fill; ba.tasks = tasks;
+    ed_build_kernel<<<gwarp, TB, 0, st>>>(ba);
+    count_launch(e);
+    prof_mark(e, st, ST_ED_PREP);
+
+    EdArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.pairs = pairs; ea.peq = peq; ea.tcodes = tcodes; ea.hlog = hlog; ea.mode = prm->mode; ea.nw_score = nw_score;
+    ea.loc_pair = loc_pair; ea.loc_buf = d_loc_buf;
+    int ci = 0;
+    for (int cfg = 0; cfg < ED_NCFG; ++cfg) {
+        ea.tasks = tasks; ea.seg_begin = seg_begin; ea.seg_count = seg_count; ea.seg = cfg; ea.counter = counters + (ci++);
+        const int rc = launch_ed_cfg<false>(e, cfg, ea, st);
+        if (rc) return rc;
+    }
+    prof_mark(e, st, ST_ED_FORWARD);
+
+    EdCountArgs ca;
+    ca.pairs = pairs; ca.hlog = hlog; ca.nw_score = nw_score; ca.results = d_results; ca.nloc = nloc; ca.rev_count = rev_count;
+    ca.npairs = npairs; ca.mode = prm->mode; ca.task = prm->task;
+    ed_count_kernel<<<gpair, TB, 0, st>>>(ca);
+    ed_revscan_kernel<<<1, 32, 0, st>>>(rev_count, rev_begin);
+    count_launch(e, 2);
+    exclusive_scan_i32_i64(e, nloc, d_loc_off, npairs, scan_tmp, st);
+    EdEmitArgs ma;
+    ma.pairs = pairs; ma.hlog = hlog; ma.loc_off = d_loc_off; ma.loc_buf = d_loc_buf; ma.loc_cap = loc_cap; ma.loc_pair = loc_pair;
+    ma.rev_begin = rev_begin; ma.rev_fill = rev_fill; ma.rev_tasks = rev_tasks; ma.overflow = overflow; ma.npairs = npairs;
+    ma.mode = prm->mode; ma.task = prm->task;
+    ed_emit_kernel<<<gpair, TB, 0, st>>>(ma);
+    count_launch(e);
+    prof_mark(e, st, ST_ED_OUTPUT);
+
+    if (need_rev) {
+        for (int cfg = 0; cfg < ED_NCFG; ++cfg) {
+            ea.tasks = rev_tasks; ea.seg_begin = rev_begin; ea.seg_count = rev_count; ea.seg = cfg; ea.counter = counters + (ci++);
+            const int rc = launch_ed_cfg<true>(e, cfg, ea, st);
+            if (rc) return rc;
+        }
+    }
+    prof_mark(e, st, ST_ED_STARTS);
+    DB200_CUDA_CHECK(cudaGetLastError());
+    if (loc_total) {
+        int32_t ovf = 0;
+        DB200_CUDA_CHECK(cudaMemcpyAsync(loc_total, d_loc_off + npairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(&ovf, overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        DB200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (ovf) { set_error("ed_batch: location buffer too small (%lld needed)", (long long)*loc_total); return DB200_ERR_CAPACITY; }
+    }
+    return DB200_OK;
+}
+
+}  // namespace db200

@@ -1,2 +1,169 @@
+// Bit-parallel edit distance kernels for sm_100a (Myers 1999 / Hyyro block formulation).
+//
+// They compute the observable results of dysgu's vendored edlib (reference:
+// dysgu/edlib/src/edlib.cpp:141-296 driver, 411-443 word step, 546-709 HW/SHW, 735-944 NW):
+// edit distance, every end location, and for HW the smallest start of each end location.
+// The reference's Ukkonen band only skips cells that are provably > k, so the full-column
+// evaluation done here yields identical results.
+//
+// Layout: the query's vertical delta vectors live in registers, WL 64-bit words per thread; a group
+// of G threads (G = 1..32) covers 64*G*WL query symbols and runs a wavefront over the target
+// columns (thread l works on column t-l at step t), the horizontal delta of a word boundary
+// travels to the next thread with __shfl_up_sync.  32/G pairs share a warp.  The match vectors
+// (Peq, one row per distinct target symbol) are built once per pair by ed_build_kernel.
 #pragma once
 #include "engine.cuh"
+
+namespace db200 {
+
+constexpr int ED_NCFG = 11;
+constexpr int ED_LBINS = 256;   // target-length bins (64 columns each) per config, longest first
+
+struct EdPair {
+    int64_t q_off, t_off;   // offsets into the raw query / target byte buffers
+    int64_t peq_off;        // u64 words: Peq rows [At][W]; reversed-query rows follow when needed
+    int64_t hlog_off;       // u32 words: 2-bit horizontal deltas of the last row, 16 columns per word
+    int32_t m, n;
+    int32_t W;              // 64-bit words of the query
+    int32_t At;             // distinct target symbols = Peq rows
+    int32_t alphabet;       // distinct symbols of query and target (alphabetLength)
+    int32_t k;              // -1: unlimited
+    int32_t best;           // edit distance (or -1)
+    int32_t nloc;
+    int64_t loc_off;
+    int32_t special;        // 1: handled without DP (an empty sequence)
+    int32_t cfg;
+};
+
+struct EdArgs {
+    const EdPair *pairs;
+    const uint64_t *peq;
+    const uint8_t *tcodes;       // target re-coded as Peq row indices (same layout as the raw target buffer)
+    uint32_t *hlog;
+    const int32_t *tasks;        // forward: pair ids; reverse: location indices
+    const int32_t *seg_begin;
+    const int32_t *seg_count;
+    int32_t seg;
+    int32_t *counter;
+    int32_t mode;                // DB200_ED_MODE_*
+    int32_t *nw_score;           // forward, NW: final score per pair
+    // reverse (start locations)
+    const int32_t *loc_pair;     // location index -> pair
+    int32_t *loc_buf;            // (start, end) pairs
+};
+
+// One Myers column step on a 64-bit word.  hin/hout are (plus, minus) bit pairs.
+__device__ __forceinline__ void myers_word(uint64_t &Pv, uint64_t &Mv, uint64_t Eq, uint32_t hin_p, uint32_t hin_m, uint32_t &hout_p,
+                                           uint32_t &hout_m, uint64_t &Ph_raw, uint64_t &Mh_raw)
+{
+    const uint64_t Xv = Eq | Mv;
+    Eq |= (uint64_t)hin_m;
+    const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+    uint64_t Ph = Mv | ~(Xh | Pv);
+    uint64_t Mh = Pv & Xh;
+    Ph_raw = Ph;
+    Mh_raw = Mh;
+    hout_p = (uint32_t)(Ph >> 63);
+    hout_m = (uint32_t)(Mh >> 63);
+    Ph = (Ph << 1) | (uint64_t)hin_p;
+    Mh = (Mh << 1) | (uint64_t)hin_m;
+    Pv = Mh | ~(Xv | Ph);
+    Mv = Ph & Xv;
+}
+
+template <int WL, int G, bool REV>
+__global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
+{
+    constexpr int GROUPS = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int lig = lane % G, grp = lane / G;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int seg_begin = a.seg_begin[a.seg], seg_count = a.seg_count[a.seg];
+
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.counter, GROUPS);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= seg_count) break;
+        const int ti = base + grp;
+        const bool active = ti < seg_count;
+        int task = active ? a.tasks[seg_begin + ti] : -1;
+        int pair = -1, end = 0, ncols = 0;
+        EdPair pr;
+        memset(&pr, 0, sizeof(pr));
+        if (active) {
+            pair = REV ? a.loc_pair[task] : task;
+            pr = a.pairs[pair];
+            if (REV) {
+                end = a.loc_buf[2 * (int64_t)task + 1];
+                ncols = min(end + 1, pr.m + pr.best);   // longer windows cannot reach the distance again
+            } else {
+                ncols = pr.n;
+            }
+        }
+        const int W = pr.W, m = pr.m;
+        const int w0 = lig * WL;
+        const int nw = max(0, min(WL, W - w0));
+        const bool has_last = active && nw > 0 && (w0 + nw == W);
+        const int last_w = nw - 1;
+        const int last_bit = (m - 1) & 63;
+        const uint64_t *peq = a.peq + pr.peq_off + (REV ? (int64_t)pr.At * W : 0) + w0;
+        const uint8_t *tc = a.tcodes + pr.t_off;
+        const uint32_t hin0 = (REV || a.mode != DB200_ED_MODE_HW) ? 1u : 0u; // SHW / NW: gap before the query costs
+
+        uint64_t Pv[WL], Mv[WL];
+#pragma unroll
+        for (int w = 0; w < WL; ++w) { Pv[w] = ~0ull; Mv[w] = 0ull; }
+        int score = m;
+        int rmin = (m & 63) ? m : 0x7FFFFFFF; // column -1 is only a candidate when the last word is padded (edlib.cpp:663-676)
+        int rpos = -1;
+        uint32_t logw = 0;
+        uint32_t *hlog = a.hlog + pr.hlog_off;
+
+        int steps = ncols + G - 1;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, o));
+        uint32_t carry = 0; // bit0 = plus, bit1 = minus: horizontal delta leaving this thread's words
+
+        for (int t = 0; t < steps; ++t) {
+            const int j = t - lig;
+            const bool valid = active && nw > 0 && j >= 0 && j < ncols;
+            uint32_t cin = carry;
+            if (G > 1) cin = __shfl_up_sync(FULL, carry, 1, G);
+            if (lig == 0) cin = hin0;
+            if (valid) {
+                const int c = REV ? tc[end - j] : tc[j];
+                const uint64_t *row = peq + (int64_t)c * W;
+                uint32_t hp = cin & 1u, hm = (cin >> 1) & 1u;
+                uint64_t Ph_l = 0, Mh_l = 0;
+#pragma unroll
+                for (int w = 0; w < WL; ++w) {
+                    if (w < nw) {
+                        uint32_t op, om;
+                        uint64_t Phr, Mhr;
+                        myers_word(Pv[w], Mv[w], __ldg(row + w), hp, hm, op, om, Phr, Mhr);
+                        hp = op; hm = om;
+                        if (w == last_w) { Ph_l = Phr; Mh_l = Mhr; }
+                    }
+                }
+                carry = hp | (hm << 1);
+                if (has_last) {
+                    const int dp = (int)((Ph_l >> last_bit) & 1ull), dm = (int)((Mh_l >> last_bit) & 1ull);
+                    score += dp - dm;
+                    if (REV) {
+                        if (score <= rmin) { rmin = score; rpos = j; }
+                    } else if (a.mode != DB200_ED_MODE_NW) {
+                        logw |= (uint32_t)(dp | (dm << 1)) << ((j & 15) * 2);
+                        if ((j & 15) == 15 || j == ncols - 1) { hlog[j >> 4] = logw; logw = 0; }
+                    }
+                }
+            }
+        }
+        if (has_last) {
+            if (REV) a.loc_buf[2 * (int64_t)task] = end - rpos;
+            else if (a.mode == DB200_ED_MODE_NW) a.nw_score[pair] = score;
+        }
+    }
+}
+
+}  // namespace db200

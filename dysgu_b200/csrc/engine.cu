@@ -104,6 +104,20 @@ Engine *get_engine(int device)
     return e;
 }
 
+// ---- stage profiling ---------------------------------------------------------------------------------
+void prof_mark(Engine *e, cudaStream_t st, int stage)
+{
+    if (!e->profiling) return;
+    if (e->ev_used == e->ev_pool.size()) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        e->ev_pool.push_back(ev);
+    }
+    cudaEvent_t ev = e->ev_pool[e->ev_used++];
+    cudaEventRecord(ev, st);
+    e->marks.push_back({stage, ev});
+}
+
 // ---- exclusive scan (int32 -> int64), three small kernels ---------------------------------------------
 __global__ void scan_block_sums(const int32_t *in, int64_t n, int64_t *sums)
 {
@@ -228,6 +242,35 @@ int64_t db200_kernel_launches(int device, int reset)
     const int64_t n = e->launches;
     if (reset) e->launches = 0;
     return n;
+}
+
+int db200_profile_enable(int device, int on)
+{
+    Engine *e = get_engine(device);
+    if (!e) return DB200_ERR_CUDA;
+    e->profiling = on != 0;
+    e->marks.clear();
+    e->ev_used = 0;
+    return DB200_OK;
+}
+
+// Accumulated milliseconds per stage since the last collect; stage i of `ms` is the time between the
+// mark that opened stage i and the next mark.  Synchronises the device.
+int db200_profile_collect(int device, float *ms, int nstages)
+{
+    Engine *e = get_engine(device);
+    if (!e) return DB200_ERR_CUDA;
+    DB200_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < nstages; ++i) ms[i] = 0.f;
+    for (size_t i = 1; i < e->marks.size(); ++i) {
+        const int stage = e->marks[i].stage;      // the mark names the stage that just finished
+        if (stage == ST_BEGIN) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e->marks[i - 1].ev, e->marks[i].ev) == cudaSuccess && stage < nstages) ms[stage] += t;
+    }
+    e->marks.clear();
+    e->ev_used = 0;
+    return DB200_OK;
 }
 
 void *db200_host_alloc(int64_t bytes)
@@ -389,6 +432,135 @@ void db200_align_destroy(db200_s_align *a)
     if (!a) return;
     free(a->cigar);
     free(a);
+}
+
+// ---- edit distance ------------------------------------------------------------------------------------
+int db200_ed_batch_device(int device, const db200_ed_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
+                          const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs, int32_t max_query_len,
+                          int32_t max_target_len, const int32_t *d_k, db200_ed_result *d_results, int32_t *d_loc_buf, int64_t loc_cap,
+                          int64_t *d_loc_off, int64_t *loc_total, void *stream)
+{
+    Engine *e = get_engine(device);
+    if (!e) return DB200_ERR_CUDA;
+    e->arena[0].reset();
+    return ed_batch_device_impl(e, e->arena[0], params, d_qbuf, d_qoff, q_bytes, d_tbuf, d_toff, t_bytes, npairs, max_query_len,
+                                max_target_len, d_k, d_results, d_loc_buf, loc_cap, d_loc_off, loc_total, (cudaStream_t)stream);
+}
+
+int db200_ed_batch_host(int device, const db200_ed_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
+                        const int64_t *toff, int64_t npairs, const int32_t *k, db200_ed_result *results, int32_t *loc_buf,
+                        int64_t loc_cap, int64_t *loc_off)
+{
+    Engine *e = get_engine(device);
+    if (!e) return DB200_ERR_CUDA;
+    if (npairs < 0 || !params || !qoff || !toff || !results || !loc_buf || !loc_off) { set_error("ed_batch_host: bad arguments"); return DB200_ERR_ARG; }
+    loc_off[0] = 0;
+    cudaStream_t st = e->stream;
+    const int64_t MAX_CHUNK_PAIRS = (int64_t)1 << 20;
+    const int64_t MAX_CHUNK_BYTES = (int64_t)2 << 30;
+    int64_t written = 0;
+    std::vector<int64_t> offs;
+    for (int64_t c0 = 0; c0 < npairs;) {
+        int64_t c1 = c0, bytes = 0;
+        int32_t maxq = 0, maxt = 0;
+        while (c1 < npairs && c1 - c0 < MAX_CHUNK_PAIRS) {
+            const int64_t ql = qoff[c1 + 1] - qoff[c1], tl = toff[c1 + 1] - toff[c1];
+            if (ql < 0 || tl < 0 || ql > 0x7FFFFFF0 || tl > 0x7FFFFFF0) { set_error("ed_batch_host: bad offsets at pair %lld", (long long)c1); return DB200_ERR_ARG; }
+            if (c1 > c0 && bytes + ql + tl > MAX_CHUNK_BYTES) break;
+            bytes += ql + tl;
+            maxq = std::max<int32_t>(maxq, (int32_t)ql);
+            maxt = std::max<int32_t>(maxt, (int32_t)tl);
+            ++c1;
+        }
+        const int64_t n = c1 - c0;
+        const int64_t qb = qoff[c1] - qoff[c0], tb = toff[c1] - toff[c0];
+        offs.resize((size_t)(2 * (n + 1)));
+        for (int64_t i = 0; i <= n; ++i) { offs[(size_t)i] = qoff[c0 + i] - qoff[c0]; offs[(size_t)(n + 1 + i)] = toff[c0 + i] - toff[c0]; }
+        Arena &io = e->io[0];
+        io.reset();
+        e->arena[0].reset();
+        const int64_t cap = std::min<int64_t>(std::max<int64_t>(loc_cap - written, 0), tb + 2 * n + 16);
+        uint8_t *d_q = io.alloc<uint8_t>((size_t)qb + 16), *d_t = io.alloc<uint8_t>((size_t)tb + 16);
+        int64_t *d_off = io.alloc<int64_t>((size_t)(2 * (n + 1)));
+        int32_t *d_k = k ? io.alloc<int32_t>((size_t)n) : nullptr;
+        db200_ed_result *d_res = io.alloc<db200_ed_result>((size_t)n);
+        int64_t *d_loff = io.alloc<int64_t>((size_t)n + 1);
+        int32_t *d_loc = io.alloc<int32_t>((size_t)(2 * cap + 16));
+        if (!d_q || !d_t || !d_off || (k && !d_k) || !d_res || !d_loff || !d_loc) { set_error("ed_batch_host: device allocation failed"); return DB200_ERR_NOMEM; }
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_q, qbuf + qoff[c0], (size_t)qb, cudaMemcpyHostToDevice, st));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_t, tbuf + toff[c0], (size_t)tb, cudaMemcpyHostToDevice, st));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_off, offs.data(), sizeof(int64_t) * (size_t)(2 * (n + 1)), cudaMemcpyHostToDevice, st));
+        if (k) DB200_CUDA_CHECK(cudaMemcpyAsync(d_k, k + c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        int64_t total = 0;
+        int rc = ed_batch_device_impl(e, e->arena[0], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, maxt, d_k, d_res, d_loc, cap,
+                                      d_loff, &total, st);
+        if (rc) return rc;
+        DB200_CUDA_CHECK(cudaMemcpyAsync(results + c0, d_res, sizeof(db200_ed_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(loc_off + c0, d_loff, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+        if (total > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(loc_buf + 2 * written, d_loc, sizeof(int32_t) * 2 * (size_t)total, cudaMemcpyDeviceToHost, st));
+        DB200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (written) for (int64_t i = 0; i <= n; ++i) loc_off[c0 + i] += written;
+        written += total;
+        c0 = c1;
+    }
+    loc_off[npairs] = written;
+    return DB200_OK;
+}
+
+// ---- legacy single-pair edlib entry points (edlib.h:146-271) ------------------------------------------------
+db200_EdlibAlignConfig db200_edlibNewAlignConfig(int k, int mode, int task, const db200_EdlibEqualityPair *additionalEqualities,
+                                                 int additionalEqualitiesLength)
+{
+    db200_EdlibAlignConfig c;
+    c.k = k; c.mode = mode; c.task = task;
+    c.additionalEqualities = additionalEqualities;
+    c.additionalEqualitiesLength = additionalEqualitiesLength;
+    return c;
+}
+
+db200_EdlibAlignConfig db200_edlibDefaultAlignConfig(void) { return db200_edlibNewAlignConfig(-1, DB200_ED_MODE_NW, DB200_ED_TASK_DISTANCE, nullptr, 0); }
+
+db200_EdlibAlignResult db200_edlibAlign(const char *query, int queryLength, const char *target, int targetLength,
+                                        const db200_EdlibAlignConfig config)
+{
+    db200_EdlibAlignResult r;
+    memset(&r, 0, sizeof(r));
+    r.status = 1;
+    r.editDistance = -1;
+    if (queryLength < 0 || targetLength < 0) return r;
+    db200_ed_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.mode = config.mode; prm.task = config.task; prm.k = config.k;
+    prm.eq_pairs = reinterpret_cast<const char *>(config.additionalEqualities);
+    prm.n_eq_pairs = config.additionalEqualities ? config.additionalEqualitiesLength : 0;
+    int64_t qoff[2] = {0, queryLength}, toff[2] = {0, targetLength}, loff[2] = {0, 0};
+    db200_ed_result res;
+    std::vector<int32_t> loc((size_t)(2 * (targetLength + 4)));
+    const uint8_t dummy = 0;
+    int rc = db200_ed_batch_host(0, &prm, queryLength ? (const uint8_t *)query : &dummy, qoff, targetLength ? (const uint8_t *)target : &dummy,
+                                 toff, 1, nullptr, &res, loc.data(), targetLength + 4, loff);
+    if (rc != DB200_OK) return r;
+    r.status = res.status;
+    r.editDistance = res.edit_distance;
+    r.alphabetLength = res.alphabet_length;
+    r.numLocations = res.num_locations;
+    if (res.num_locations > 0) {
+        r.endLocations = (int *)malloc(sizeof(int) * (size_t)res.num_locations);
+        const bool starts = loc[0] != DB200_ED_NO_START;
+        if (starts) r.startLocations = (int *)malloc(sizeof(int) * (size_t)res.num_locations);
+        for (int i = 0; i < res.num_locations; ++i) {
+            r.endLocations[i] = loc[(size_t)(2 * i + 1)];
+            if (starts) r.startLocations[i] = loc[(size_t)(2 * i)];
+        }
+    }
+    return r;
+}
+
+void db200_edlibFreeAlignResult(db200_EdlibAlignResult result)
+{
+    free(result.endLocations);
+    free(result.startLocations);
+    free(result.alignment);
 }
 
 }  // extern "C"

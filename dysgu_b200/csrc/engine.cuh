@@ -7,6 +7,7 @@
 #include <string.h>
 #include <string>
 #include <algorithm>
+#include <vector>
 
 #include "../../include/dysgu_b200_align.h"
 
@@ -57,12 +58,23 @@ struct Engine {
     size_t pinned_cap = 0;
     void *pinned_out[2] = {nullptr, nullptr};
     size_t pinned_out_cap[2] = {0, 0};
-    size_t trace_pool_bytes = (size_t)1 << 30;  // scratch of the banded traceback (DB200_TRACE_POOL_MB)
+    size_t trace_pool_bytes = (size_t)1 << 30;
+    // optional stage profiling (CUDA events recorded on the launching stream between pipeline stages)
+    bool profiling = false;
+    struct Mark { int stage; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;  // scratch of the banded traceback (DB200_TRACE_POOL_MB)
 };
 
 Engine *get_engine(int device);  // nullptr + error set on failure
 
 inline void count_launch(Engine *e, int n = 1) { e->launches += n; }
+
+// stage ids reported by db200_profile_collect (a mark closes the stage named by the PREVIOUS mark)
+enum Stage { ST_BEGIN = 0, ST_PACK, ST_BUCKET, ST_FORWARD, ST_FORWARD_WATCH, ST_REVERSE_PREP, ST_REVERSE, ST_REVERSE_WATCH,
+             ST_FINALIZE, ST_TRACEBACK, ST_CIGAR, ST_ED_PREP, ST_ED_FORWARD, ST_ED_STARTS, ST_ED_OUTPUT, ST_COUNT };
+void prof_mark(Engine *e, cudaStream_t st, int stage);
 
 // Exclusive scan of int32 counts into int64 offsets (offsets[n] = total).  n up to 2^31.
 // tmp must hold ceil(n / 1024) + 1 int64 values.

@@ -653,12 +653,14 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     const unsigned gwarp_seq = (unsigned)((nseq * 32 + TB - 1) / TB), gwarp_pair = (unsigned)((npairs * 32 + TB - 1) / TB);
 
     // 1. pack ---------------------------------------------------------------------------------------
+    prof_mark(e, st, ST_BEGIN);
     sw_units_kernel<<<gseq, TB, 0, st>>>(d_qoff, d_toff, npairs, units);
     count_launch(e);
     exclusive_scan_i32_i64(e, units, unit_off, nseq, scan_tmp, st);
     sw_pack_kernel<<<gwarp_seq, TB, 0, st>>>(d_qbuf, d_qoff, d_tbuf, d_toff, npairs, unit_off, pool, meta);
     count_launch(e);
 
+    prof_mark(e, st, ST_PACK);
     // 2. bucket -------------------------------------------------------------------------------------
     InitArgs ia;
     ia.meta = meta; ia.mask_len = d_mask_len; ia.state = state; ia.npairs = npairs; ia.max_match = max_match; ia.flag = prm->flag;
@@ -671,6 +673,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     DB200_CUDA_CHECK(cudaMemsetAsync(fwd, 0, sizeof(PassOut) * npairs, st));
     DB200_CUDA_CHECK(cudaMemsetAsync(rev, 0, sizeof(PassOut) * npairs, st));
 
+    prof_mark(e, st, ST_BUCKET);
     PassArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.pool = reinterpret_cast<const uint4 *>(pool);
@@ -691,6 +694,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         const int rc = cmx ? launch_cfg<true, false>(e, cfg, pa, st) : launch_cfg<false, false>(e, cfg, pa, st);
         if (rc) return rc;
     }
+    prof_mark(e, st, ST_FORWARD);
     for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
         if (cfg == SW_NCFG - 1 && !can_multi) continue;
         pa.meta = meta; pa.tasks = amb_f; pa.seg_begin = seg_begin_f; pa.seg_count = amb_count_f; pa.seg = 2 * cfg;
@@ -700,6 +704,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         if (rc) return rc;
     }
 
+    prof_mark(e, st, ST_FORWARD_WATCH);
     // 4. reversed problems ----------------------------------------------------------------------------
     MidArgs ma;
     ma.fwd = fwd; ma.meta = meta; ma.rmeta = rmeta; ma.state = state; ma.npairs = npairs;
@@ -711,6 +716,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     sw_binscan_kernel<<<1, 32, 0, st>>>(hist_r, start_r, seg_begin_r, seg_count_r);
     sw_scatter_kernel<<<gpair, TB, 0, st>>>(rmeta, state, npairs, 1, start_r, fill_r, tasks_r);
     count_launch(e, 4);
+    prof_mark(e, st, ST_REVERSE_PREP);
     for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
         if (cfg == SW_NCFG - 1 && !can_multi) continue;
         pa.meta = rmeta; pa.tasks = tasks_r; pa.seg_begin = seg_begin_r; pa.seg_count = seg_count_r; pa.seg = 2 * cfg;
@@ -720,6 +726,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         const int rc = launch_cfg<false, false>(e, cfg, pa, st);
         if (rc) return rc;
     }
+    prof_mark(e, st, ST_REVERSE);
     for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
         if (cfg == SW_NCFG - 1 && !can_multi) continue;
         pa.meta = rmeta; pa.tasks = amb_r; pa.seg_begin = seg_begin_r; pa.seg_count = amb_count_r; pa.seg = 2 * cfg;
@@ -729,24 +736,28 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         if (rc) return rc;
     }
 
+    prof_mark(e, st, ST_REVERSE_WATCH);
     // 5. finalize + traceback + cigar compaction ---------------------------------------------------------
     FinalArgs fa;
     fa.fwd = fwd; fa.rev = rev; fa.meta = meta; fa.state = state; fa.colmax = colmax; fa.colmax_off = colmax_off;
     fa.results = d_results; fa.status_out = nullptr; fa.npairs = npairs;
     fa.flag = prm->flag; fa.filters = prm->filters; fa.filterd = prm->filterd;
     sw_finalize_kernel<<<gpair, TB, 0, st>>>(fa);
+    prof_mark(e, st, ST_FINALIZE);
     TraceArgs ta;
     ta.pool = reinterpret_cast<const uint4 *>(pool); ta.meta = meta; ta.state = state; ta.results = d_results; ta.npairs = npairs;
     ta.sc = sc; ta.scratch = trace; ta.scratch_cursor = trace_cursor; ta.scratch_cap = trace_cap;
     ta.cigar_pool = cigar_pool; ta.cigar_cursor = cigar_cursor; ta.cigar_cap = (unsigned long long)cig_pool_cap;
     ta.overflow_flag = overflow_flag;
     sw_traceback_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, st>>>(ta);
+    prof_mark(e, st, ST_TRACEBACK);
     sw_cigar_len_kernel<<<gpair, TB, 0, st>>>(state, npairs, lens);
     count_launch(e, 3);
     int64_t *off_out = d_cigar_off ? d_cigar_off : cig_off_tmp;
     exclusive_scan_i32_i64(e, lens, off_out, npairs, scan_tmp, st);
     sw_cigar_gather_kernel<<<gpair, TB, 0, st>>>(state, npairs, off_out, cigar_pool, d_cigar_buf, cigar_cap, d_status, overflow_flag);
     count_launch(e);
+    prof_mark(e, st, ST_CIGAR);
     DB200_CUDA_CHECK(cudaGetLastError());
     if (cigar_total) {
         DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_total, off_out + npairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));

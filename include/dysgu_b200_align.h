@@ -56,6 +56,12 @@ const char *db200_version(void);
 int64_t db200_workspace_bytes(int device);
 /* Kernel launches issued by this library on `device` since the last call with reset != 0. */
 int64_t db200_kernel_launches(int device, int reset);
+/* Stage profiling: CUDA events between pipeline stages on the launching stream.  `collect` synchronises
+ * the device and returns the accumulated milliseconds per stage (see enum Stage in csrc/engine.cuh:
+ * 1 pack, 2 bucket, 3 forward pass, 4 forward re-run, 5 reverse prep, 6 reverse pass, 7 reverse re-run,
+ * 8 finalize, 9 traceback, 10 cigar, 11 ed prep, 12 ed forward, 13 ed starts, 14 ed output). */
+int db200_profile_enable(int device, int on);
+int db200_profile_collect(int device, float *ms, int nstages);
 /* Page-locked host memory for the *_host entry points (plain malloc'd buffers work too, slower). */
 void *db200_host_alloc(int64_t bytes);
 void db200_host_free(void *p);
