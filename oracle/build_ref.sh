@@ -18,3 +18,27 @@ mkdir -p "$OUT"
 gcc -O2 -std=c99 -fPIC -shared -w -I"$REF/dysgu/scikitbio" "$REF/dysgu/scikitbio/ssw.c" -o "$OUT/libssw_ref.so" -lm
 g++ -O3 -std=c++17 -fPIC -shared -w -I"$REF/dysgu/edlib/src" "$REF/dysgu/edlib/src/edlib.cpp" -o "$OUT/libedlib_ref.so"
 echo "build_ref: built $OUT/libssw_ref.so $OUT/libedlib_ref.so"
+
+# Optional: the reference's two Cython wrappers (used only to generate wrapper-level golden vectors).
+# Built in a scratch directory; only the extension modules land in oracle/_ref/pyref/dysgu/...
+if python -c "import Cython" 2>/dev/null; then
+    TMP="$(mktemp -d)"
+    PYINC="$(python -c 'import sysconfig; print(sysconfig.get_paths()["include"])')"
+    NPINC="$(python -c 'import numpy; print(numpy.get_include())')"
+    EXT="$(python -c 'import sysconfig; print(sysconfig.get_config_var("EXT_SUFFIX"))')"
+    mkdir -p "$TMP/dysgu/scikitbio" "$TMP/dysgu/edlib" "$OUT/pyref/dysgu/scikitbio" "$OUT/pyref/dysgu/edlib"
+    touch "$TMP/dysgu/__init__.py" "$TMP/dysgu/scikitbio/__init__.py" "$TMP/dysgu/edlib/__init__.py"
+    cp "$REF/dysgu/scikitbio/_ssw_wrapper.pyx" "$TMP/dysgu/scikitbio/"
+    cp "$REF/dysgu/edlib/edlib.pyx" "$REF/dysgu/edlib/edlib.pxd" "$TMP/dysgu/edlib/"
+    ( cd "$TMP" &&
+      cython -3 dysgu/scikitbio/_ssw_wrapper.pyx -o ssw_wrapper.c >/dev/null 2>&1 &&
+      gcc -O2 -fPIC -shared -w -DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION -I"$PYINC" -I"$NPINC" -I"$REF/dysgu/scikitbio" \
+          ssw_wrapper.c "$REF/dysgu/scikitbio/ssw.c" -o "$OUT/pyref/dysgu/scikitbio/_ssw_wrapper$EXT" -lm &&
+      cython --cplus -3 -I . dysgu/edlib/edlib.pyx -o edlib_wrap.cpp >/dev/null 2>&1 &&
+      g++ -O3 -std=c++17 -fPIC -shared -w -I"$PYINC" -I"$REF/dysgu/edlib" -I"$REF/dysgu/edlib/src" -I"$TMP/dysgu/edlib" -I. \
+          edlib_wrap.cpp "$REF/dysgu/edlib/src/edlib.cpp" -o "$OUT/pyref/dysgu/edlib/edlib$EXT" ) \
+      && touch "$OUT/pyref/dysgu/__init__.py" "$OUT/pyref/dysgu/scikitbio/__init__.py" "$OUT/pyref/dysgu/edlib/__init__.py" \
+      && echo "build_ref: built the reference Cython wrappers under $OUT/pyref" \
+      || echo "build_ref: Cython wrappers not built (optional)" >&2
+    rm -rf "$TMP"
+fi

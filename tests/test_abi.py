@@ -1,0 +1,49 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dysgu_b200_align.h declares; compute fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dysgu_b200 import _lib, batch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dysgu_b200_align.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(db200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_version_and_device_count():
+    L = _lib.lib()
+    assert b"sm_100a" in L.db200_version()
+    assert _lib.device_count() >= 0
+
+
+@pytest.mark.skipif(_lib.device_count() > 0, reason="a GPU is present")
+def test_compute_fails_loudly_without_gpu():
+    with pytest.raises(_lib.AlignEngineError, match="no CUDA device"):
+        batch.sw_align_batch([b"ACGT"], [b"ACGT"])
+    with pytest.raises(_lib.AlignEngineError, match="no CUDA device"):
+        batch.ed_align_batch([b"ACGT"], [b"ACGT"])
+    from dysgu_b200.scikitbio import StripedSmithWaterman
+    with pytest.raises(_lib.AlignEngineError):
+        StripedSmithWaterman("ACGT")("ACGT")
+
+
+def test_struct_layouts_match_header():
+    # db200_sw_params: 8 int32 + pointer + int32 (+pad); db200_ed_params: 3 int32 (+pad) + pointer + int32 (+pad)
+    assert C.sizeof(_lib.SwParams) == 48
+    assert C.sizeof(_lib.EdParams) == 32
+    assert batch.SW_FIELDS == ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len")

@@ -1,0 +1,77 @@
+"""CPU: host-side logic - workload generators, CSR helpers, wrapper argument handling, sharding."""
+import numpy as np
+import pytest
+
+from dysgu_b200 import shard, workloads
+from dysgu_b200.edlib import edlib as ed_wrap
+from dysgu_b200.scikitbio import StripedSmithWaterman
+
+
+def test_workloads_are_deterministic_and_shaped():
+    q1, t1, prm = workloads.remap_windows(500, seed=3)
+    q2, t2, _ = workloads.remap_windows(500, seed=3)
+    assert np.array_equal(q1.buf, q2.buf) and np.array_equal(t1.off, t2.off)
+    assert set(np.unique(q1.lengths)) <= {1000, 1500, 2000}
+    assert t1.lengths.min() >= 1 and t1.lengths.max() <= 330
+    assert prm == dict(match=2, mismatch=-8, gap_open=6, gap_extend=1)
+    assert set(np.unique(q1.buf)) <= set(b"ACGT") and set(np.unique(t1.buf)) <= set(b"acgt")
+    a, b, _ = workloads.insertion_linking(200, seed=4, platform="ont")
+    assert len(a) == len(b) == 200 and a.lengths.max() <= 10000
+
+
+def test_seqbatch_take_and_slices():
+    b = workloads.SeqBatch.from_list([b"AAAA", b"", b"CCG", b"T"])
+    assert b.tolist() == [b"AAAA", b"", b"CCG", b"T"]
+    assert b.take([2, 0]).tolist() == [b"CCG", b"AAAA"]
+    s = workloads.slices(workloads.SeqBatch.from_list([b"ACGTACGT", b"TTTTGGGG"]), np.array([1, 4]), np.array([3, 4]))
+    assert s.tolist() == [b"CGT", b"GGGG"]
+
+
+def test_mutate_rates():
+    rng = np.random.default_rng(1)
+    a = workloads.random_dna(rng, np.full(200, 500))
+    b = workloads.mutate(rng, a, 0.0, 0.0, 0.0)
+    assert np.array_equal(a.buf, b.buf)
+    c = workloads.mutate(rng, a, 0.1, 0.0, 0.0)
+    frac = float((a.buf != c.buf).mean())
+    assert 0.07 < frac < 0.13
+    d = workloads.mutate(rng, a, 0.0, 0.05, 0.05)
+    assert abs(int(d.off[-1]) - int(a.off[-1])) < 0.02 * int(a.off[-1])
+
+
+def test_wrapper_argument_errors_match_reference():
+    with pytest.raises(ValueError, match="gap_open_penalty"):
+        StripedSmithWaterman("ACGT", gap_open_penalty=0)
+    with pytest.raises(ValueError, match="gap_extend_penalty"):
+        StripedSmithWaterman("ACGT", gap_extend_penalty=-1)
+    with pytest.raises(Exception, match="substitution matrix"):
+        StripedSmithWaterman("ACGT", protein=True)
+    with pytest.raises(IndexError):
+        StripedSmithWaterman("ACGä")
+    s = StripedSmithWaterman("A" * 100)
+    assert s.mask_length == 50 and s.bit_flag == 1
+    assert StripedSmithWaterman("A" * 10).mask_length == 15
+    assert StripedSmithWaterman("A" * 100, mask_auto=False, mask_length=20).mask_length == 20
+    assert StripedSmithWaterman("ACGT", score_only=True).bit_flag == 0
+    assert StripedSmithWaterman("ACGT", override_skip_babp=True).bit_flag == 9
+    assert StripedSmithWaterman("ACGT", score_filter=10).bit_flag == 2
+    assert StripedSmithWaterman("ACGT", distance_filter=10, score_filter=3).bit_flag == 6
+
+
+def test_edlib_byte_mapping():
+    q, t, eq = ed_wrap._to_bytes("ACGT", b"AC", None)
+    assert q == b"ACGT" and t == b"AC" and eq is None
+    q, t, eq = ed_wrap._to_bytes([12, "x", 12], ["x"], [("x", 12), ("zz", 1)])
+    assert len(q) == 3 and q[0] == q[2] and t[0] == q[1] and len(eq) == 1
+    with pytest.raises(ValueError):
+        ed_wrap._to_bytes(list(range(300)), [1], None)
+
+
+def test_shard_bounds_and_merge():
+    assert shard.shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard.shard_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    b = workloads.SeqBatch.from_list([b"AA", b"C", b"GGG", b"T", b""])
+    parts = [shard.take_shard(b, lo, hi) for lo, hi in shard.shard_bounds(len(b), 2)]
+    assert sum((p.tolist() for p in parts), []) == b.tolist()
+    off, val = shard.merge_csr([np.array([0, 2, 3]), np.array([0, 1, 1, 4])], [np.array([7, 8, 9]), np.array([1, 2, 3, 4])])
+    assert list(off) == [0, 2, 3, 4, 4, 7] and list(val) == [7, 8, 9, 1, 2, 3, 4]
