@@ -12,9 +12,9 @@ namespace db200 {
 // ------------------------------------------------------------------------------------------------
 // kernel configurations: index -> (K columns per virtual lane, G threads per pair)
 // ------------------------------------------------------------------------------------------------
-static const int CFG_K[SW_NCFG] = {16, 16, 16, 16, 16, 16, 32};
-static const int CFG_G[SW_NCFG] = {1, 2, 4, 8, 16, 32, 32};
-__device__ __constant__ int d_cfg_cap[SW_NCFG] = {32, 64, 128, 256, 512, 1024, 2048};
+// columns per pass = 2*G*K; the last configuration tiles longer targets in passes of 2048 columns
+static const int CFG_CAP[SW_NCFG] = {32, 64, 96, 128, 160, 192, 224, 256, 320, 512, 1024, 2048};
+__device__ __constant__ int d_cfg_cap[SW_NCFG] = {32, 64, 96, 128, 160, 192, 224, 256, 320, 512, 1024, 2048};
 
 struct PairState {          // per-pair bookkeeping of the pipeline
     int32_t mask_len;
@@ -529,7 +529,7 @@ __global__ void sw_cigar_gather_kernel(const PairState *state, int64_t npairs, c
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
-template <int K, int G, bool COLMAX, bool MULTI, bool WATCH>
+template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG>
 static int launch_pass(Engine *e, const PassArgs &a, cudaStream_t st)
 {
     constexpr int NCH = K / 8, ROW = 2 * NCH * 32;
@@ -537,31 +537,38 @@ static int launch_pass(Engine *e, const PassArgs &a, cudaStream_t st)
     static int blocks_cached[16] = {0};
     int &blocks = blocks_cached[e->device & 15];
     if (blocks == 0) {
-        DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_pass_kernel<K, G, COLMAX, MULTI, WATCH>,
+        DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_pass_kernel<K, G, COLMAX, MULTI, WATCH>, 128, smem));
+        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG>, 128, smem));
         if (per_sm < 1) per_sm = 1;
         if (MULTI && per_sm * 4 > SW_MULTI_MAX_WARPS_PER_SM) per_sm = SW_MULTI_MAX_WARPS_PER_SM / 4;
         blocks = e->sm_count * per_sm;
     }
-    sw_pass_kernel<K, G, COLMAX, MULTI, WATCH><<<blocks, 128, smem, st>>>(a);
+    sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG><<<blocks, 128, smem, st>>>(a);
     count_launch(e);
     DB200_CUDA_CHECK(cudaGetLastError());
     return DB200_OK;
 }
 
-template <bool COLMAX, bool WATCH>
+template <bool COLMAX, bool WATCH, bool TAG>
 static int launch_cfg(Engine *e, int cfg, const PassArgs &a, cudaStream_t st)
 {
     switch (cfg) {
-        case 0: return launch_pass<16, 1, COLMAX, false, WATCH>(e, a, st);
-        case 1: return launch_pass<16, 2, COLMAX, false, WATCH>(e, a, st);
-        case 2: return launch_pass<16, 4, COLMAX, false, WATCH>(e, a, st);
-        case 3: return launch_pass<16, 8, COLMAX, false, WATCH>(e, a, st);
-        case 4: return launch_pass<16, 16, COLMAX, false, WATCH>(e, a, st);
-        case 5: return launch_pass<16, 32, COLMAX, false, WATCH>(e, a, st);
-        default: return launch_pass<32, 32, COLMAX, true, WATCH>(e, a, st);
+        case 0: return launch_pass<16, 1, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 1: return launch_pass<16, 2, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 2: return launch_pass<16, 3, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 3: return launch_pass<16, 4, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 4: return launch_pass<16, 5, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 5: return launch_pass<16, 6, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 6: return launch_pass<16, 7, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 7: return launch_pass<16, 8, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 8: return launch_pass<16, 10, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 9: return launch_pass<16, 16, COLMAX, false, WATCH, TAG>(e, a, st);
+        case 10: return launch_pass<16, 32, COLMAX, false, WATCH, TAG>(e, a, st);
+        default:
+            if constexpr (TAG) return DB200_ERR_INTERNAL;
+            else return launch_pass<32, 32, COLMAX, true, WATCH, false>(e, a, st);
     }
 }
 
@@ -596,6 +603,13 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
             sc.mat[a * 6 + b] = (a < 5 && b < 5) ? (int16_t)m5[a * 5 + b] : (int16_t)SW_NEG;
     sc.gap_open = prm->gap_open;
     sc.gap_extend = prm->gap_extend;
+    // tagged kernels run on scores scaled by 16 (K = 16 columns per virtual lane -> 4 tag bits)
+    SwScoring sc16 = sc;
+    for (int i = 0; i < 36; ++i) if (sc.mat[i] != SW_NEG) sc16.mat[i] = (int16_t)(sc.mat[i] * 16);
+    sc16.gap_open = sc.gap_open * 16;
+    sc16.gap_extend = sc.gap_extend * 16;
+    bool tag_ok[SW_NCFG];
+    for (int c = 0; c < SW_NCFG; ++c) tag_ok[c] = (c < SW_NCFG - 1) && ((int64_t)max_match * CFG_CAP[c] <= 2047) && max_match > 0;
 
     // ---- workspace ---------------------------------------------------------------------------------
     const int64_t nseq = 2 * npairs;
@@ -691,16 +705,20 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         pa.counter = counters + (counter_idx++);
         pa.out = fwd;
         pa.amb_list = amb_f; pa.amb_count = amb_count_f + 2 * cfg; pa.amb_base_seg = 2 * cfg;
-        const int rc = cmx ? launch_cfg<true, false>(e, cfg, pa, st) : launch_cfg<false, false>(e, cfg, pa, st);
+        int rc;
+        if (cmx) { pa.sc = sc; rc = launch_cfg<true, false, false>(e, cfg, pa, st); }
+        else if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, st); }
+        else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, st); }
         if (rc) return rc;
     }
+    pa.sc = sc;
     prof_mark(e, st, ST_FORWARD);
     for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
         if (cfg == SW_NCFG - 1 && !can_multi) continue;
         pa.meta = meta; pa.tasks = amb_f; pa.seg_begin = seg_begin_f; pa.seg_count = amb_count_f; pa.seg = 2 * cfg;
         pa.counter = counters + (counter_idx++);
         pa.out = fwd;
-        const int rc = launch_cfg<false, true>(e, cfg, pa, st);
+        const int rc = launch_cfg<false, true, false>(e, cfg, pa, st);   // only colmax / untagged segments can append here
         if (rc) return rc;
     }
 
@@ -723,7 +741,9 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         pa.counter = counters + (counter_idx++);
         pa.out = rev;
         pa.amb_list = amb_r; pa.amb_count = amb_count_r + 2 * cfg; pa.amb_base_seg = 2 * cfg;
-        const int rc = launch_cfg<false, false>(e, cfg, pa, st);
+        int rc;
+        if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, st); }
+        else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, st); }
         if (rc) return rc;
     }
     prof_mark(e, st, ST_REVERSE);
@@ -732,7 +752,9 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         pa.meta = rmeta; pa.tasks = amb_r; pa.seg_begin = seg_begin_r; pa.seg_count = amb_count_r; pa.seg = 2 * cfg;
         pa.counter = counters + (counter_idx++);
         pa.out = rev;
-        const int rc = launch_cfg<false, true>(e, cfg, pa, st);
+        pa.sc = sc;
+        if (tag_ok[cfg]) continue;   // tagged passes are never ambiguous
+        const int rc = launch_cfg<false, true, false>(e, cfg, pa, st);
         if (rc) return rc;
     }
 

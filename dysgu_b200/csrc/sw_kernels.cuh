@@ -24,7 +24,7 @@ namespace db200 {
 
 constexpr int SW_PAD_CODE = 5;       // nibble used for padding; scores SW_NEG against everything
 constexpr int SW_NEG = -16384;
-constexpr int SW_NCFG = 7;           // kernel configurations (K, G)
+constexpr int SW_NCFG = 12;          // kernel configurations (K, G)
 constexpr int SW_LBINS = 512;        // length bins per (config, colmax) segment, 32 rows each
 constexpr int SW_NSEG = SW_NCFG * 2; // (config, needs column maxima)
 constexpr int SW_MULTI_MAX_WARPS_PER_SM = 8; // bounds the per-warp boundary scratch of the column-tiled kernel
@@ -83,17 +83,22 @@ __device__ __forceinline__ int pool_code(const uint4 *pool, uint32_t unit, int i
     return (int)((w[idx >> 3] >> ((idx & 7) * 4)) & 15u);
 }
 
-template <int K, int G, bool COLMAX, bool MULTI, bool WATCH>
+// TAG: scores are pre-scaled by 2^TAGB (host side) and the column index inside the virtual lane rides in the low
+// bits of the running maximum, so the best cell's column and row are exact without per-column maxima.
+template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG>
 __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
 {
     constexpr int V = 2 * G;          // virtual lanes per group
     constexpr int C = V * K;          // columns per pass
     constexpr int NCH = K / 8;        // 16-byte chunks (8 int16 scores) per half strip
-    constexpr int GROUPS = 32 / G;    // pairs per warp
+    constexpr int GROUPS = 32 / G;    // pairs per warp (G need not divide 32: the remaining lanes idle)
+    constexpr int TAGB = (K <= 16) ? 4 : 5;
+    constexpr bool VMAX = !TAG || COLMAX;
     constexpr int ROW = 2 * NCH * 32; // uint4 per profile row (one streamed code) per warp
     constexpr int UNITS = (2 * K) / 32;
     static_assert(K % 16 == 0, "K must be a multiple of 16");
     static_assert(!MULTI || G == 32, "column tiling runs one pair per warp");
+    static_assert(!(TAG && (WATCH || MULTI || COLMAX)), "the tagged variant is the plain single-pass kernel");
 
     extern __shared__ uint4 smem[];
     __shared__ int16_t mat_s[36];
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
         base = __shfl_sync(FULL, base, 0);
         if (base >= seg_count) break;
         const int ti = base + grp;
-        const bool active = ti < seg_count;
+        const bool active = grp < GROUPS && ti < seg_count;
         const int pair = active ? a.tasks[seg_begin + ti] : -1;
         PairMeta pm;
         pm.q_unit = 0; pm.t_unit = 0; pm.m = 0; pm.n = 0;
@@ -174,9 +179,11 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
             __syncwarp();
 
             // ---- state ---------------------------------------------------------------------------
-            uint32_t H[K], U[K], HmO[K], vmax[K];
+            uint32_t H[K], U[K], HmO[K], vmax[VMAX ? K : 1];
 #pragma unroll
-            for (int k = 0; k < K; ++k) { H[k] = 0; U[k] = 0; HmO[k] = 0; vmax[k] = 0; }
+            for (int k = 0; k < K; ++k) { H[k] = 0; U[k] = 0; HmO[k] = 0; }
+#pragma unroll
+            for (int k = 0; k < (VMAX ? K : 1); ++k) vmax[k] = 0;
             uint32_t best2 = 0;
             int bstep_lo = 0, bstep_hi = 0;
             uint32_t OH = 0, OV = 0, prevIn = 0;
@@ -210,8 +217,8 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
                 // ---- inputs from the preceding virtual lane ---------------------------------------
                 uint32_t sh = OH, sv = OV;
                 if (G > 1) {
-                    sh = __shfl_up_sync(FULL, OH, 1, G);
-                    sv = __shfl_up_sync(FULL, OV, 1, G);
+                    sh = __shfl_sync(FULL, OH, lane - 1);
+                    sv = __shfl_sync(FULL, OV, lane - 1);
                 }
                 if (MULTI) {
                     if ((t & 31) == 0) bchunk = (ps > 0 && t + lane < m) ? bnd[t + lane] : 0u;
@@ -242,8 +249,9 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
                         HmO[k] = __vadd2(Hp, nGO2);
                         H[k] = __vmaxs2(Hp, Vv);
                         Vv = __viaddmax_s16x2(Vv, nGE2, HmO[k]);
-                        vmax[k] = __vmaxs2(vmax[k], H[k]);
-                        m2 = __vmaxs2(m2, H[k]);
+                        if (VMAX) vmax[k] = __vmaxs2(vmax[k], H[k]);
+                        if (TAG) m2 = __viaddmax_s16x2(H[k], pack16(K - 1 - k), m2);
+                        else m2 = __vmaxs2(m2, H[k]);
                     }
                 }
                 OH = H[K - 1];
@@ -305,20 +313,32 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
                     if (jb + K + k < n) cm[jb + K + k] = (int16_t)(vmax[k] >> 16);
                 }
             }
-            const int lb_lo = (int)(best2 & 0xFFFFu), lb_hi = (int)(best2 >> 16);
+            int lb_lo = (int)(best2 & 0xFFFFu), lb_hi = (int)(best2 >> 16);
             int k1_lo = 0, cnt_lo = 0, k1_hi = 0, cnt_hi = 0;
+            if (TAG) {
+                k1_lo = K - 1 - (lb_lo & ((1 << TAGB) - 1)); k1_hi = K - 1 - (lb_hi & ((1 << TAGB) - 1));
+                lb_lo >>= TAGB; lb_hi >>= TAGB;
+                cnt_lo = cnt_hi = 1;
+            } else {
 #pragma unroll
-            for (int k = K - 1; k >= 0; --k) {
-                if ((int)(vmax[k] & 0xFFFFu) == lb_lo) { k1_lo = k; ++cnt_lo; }
-                if ((int)(vmax[k] >> 16) == lb_hi) { k1_hi = k; ++cnt_hi; }
+                for (int k = K - 1; k >= 0; --k) {
+                    if ((int)(vmax[k] & 0xFFFFu) == lb_lo) { k1_lo = k; ++cnt_lo; }
+                    if ((int)(vmax[k] >> 16) == lb_hi) { k1_hi = k; ++cnt_hi; }
+                }
             }
             const int comp_lo = (lb_lo << 8) | (255 - 2 * lig);
             const int comp_hi = (lb_hi << 8) | (255 - (2 * lig + 1));
             int gmax = max(comp_lo, comp_hi);
+            {
+                const int mine = gmax;
 #pragma unroll
-            for (int o = G / 2; o >= 1; o >>= 1) gmax = max(gmax, __shfl_xor_sync(FULL, gmax, o));
+                for (int o = 1; o < G; ++o) {
+                    const int other = __shfl_sync(FULL, mine, grp * G + (lig + o) % G);
+                    gmax = max(gmax, other);
+                }
+            }
             const int vw = 255 - (gmax & 255);
-            const int src = grp * G + (vw >> 1);
+            const int src = (grp * G + (vw >> 1)) & 31;
             const int hsel = vw & 1;
             int d_k1 = hsel ? k1_hi : k1_lo, d_cnt = hsel ? cnt_hi : cnt_lo, d_step = hsel ? bstep_hi : bstep_lo;
             d_k1 = __shfl_sync(FULL, d_k1, src);
@@ -335,8 +355,11 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
                 int w = -1;
                 if (wstep_lo >= 0) w = wstep_lo - 2 * lig;
                 if (wstep_hi >= 0) w = wstep_hi - (2 * lig + 1);
+                {
+                    const int mine = w;
 #pragma unroll
-                for (int o = G / 2; o >= 1; o >>= 1) w = max(w, __shfl_xor_sync(FULL, w, o));
+                    for (int o = 1; o < G; ++o) w = max(w, __shfl_sync(FULL, mine, grp * G + (lig + o) % G));
+                }
                 if (w >= 0) run_wrow = w;
             }
         }
