@@ -388,6 +388,24 @@ __global__ void __launch_bounds__(128) sw_traceback_kernel(TraceArgs a)
     const int readLen = res.read_end1 - res.read_begin1 + 1; // rows i
     const int score = res.score1;
     const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
+    if (refLen == readLen) {
+        // Gap-free shortcut.  If the main diagonal of the rectangle already collects the optimal score, every
+        // diagonal cell holds exactly its prefix score (a larger value would lift the corner above the optimum),
+        // so the reference's tie rule "diagonal wins when gaps do not beat it" (ssw.c:625) walks the diagonal and the
+        // cigar is one run of readLen matches.  No band has to be evaluated.
+        int sum = 0;
+        for (int i = 0; i < readLen; ++i)
+            sum += a.sc.mat[pool_code(a.pool, pm.t_unit, res.ref_begin1 + i) * 6 + pool_code(a.pool, pm.q_unit, res.read_begin1 + i)];
+        if (sum == score) {
+            const unsigned long long pos = atomicAdd(a.cigar_cursor, 1ull);
+            if (pos + 1 > a.cigar_cap) { atomicExch(a.overflow_flag, 1); s.status = DB200_PAIR_NOSCRATCH; return; }
+            a.cigar_pool[pos] = ((uint32_t)readLen) << 4;
+            s.cigar_pos = (int64_t)pos;
+            s.cigar_len = 1;
+            res.cigar_len = 1;
+            return;
+        }
+    }
     int bw = abs(refLen - readLen) + 1;
     uint8_t *dir = nullptr;
     int width = 0;
@@ -693,6 +711,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     pa.pool = reinterpret_cast<const uint4 *>(pool);
     pa.colmax = colmax; pa.colmax_off = colmax_off;
     pa.boundary = boundary; pa.boundary_stride = bstride;
+    pa.k65536 = 65536u;
     pa.sc = sc;
     int counter_idx = 0;
     const bool can_multi = max_query_len > 0;

@@ -64,6 +64,7 @@ struct PassArgs {
     int32_t *amb_list;         // pairs whose end_q is ambiguous (appended at seg_begin[amb_base_seg])
     int32_t *amb_count;
     int32_t amb_base_seg;
+    uint32_t k65536;           // 65536 passed at run time so the score merge stays an IMAD
     SwScoring sc;
 };
 
@@ -90,8 +91,12 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
 {
     constexpr int V = 2 * G;          // virtual lanes per group
     constexpr int C = V * K;          // columns per pass
-    constexpr int NCH = K / 8;        // 16-byte chunks (8 int16 scores) per half strip
+    constexpr int NCH = K / 8;        // 16-byte units per half strip (sizing only)
     constexpr int GROUPS = 32 / G;    // pairs per warp (G need not divide 32: the remaining lanes idle)
+    // profile row of one streamed code, per warp: 32-bit word [k][lane] = (score of the low-half column k) |
+    // (score of the high-half column k) << 16.  Every lane owns one bank, so the 16-bit loads below never conflict
+    // whatever mix of rows the lanes read.
+    constexpr int ROW16 = 2 * K * 32; // uint16 entries per row
     constexpr int TAGB = (K <= 16) ? 4 : 5;
     constexpr bool VMAX = !TAG || COLMAX;
     constexpr int ROW = 2 * NCH * 32; // uint4 per profile row (one streamed code) per warp
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
     __shared__ int16_t mat_s[36];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lig = lane % G, grp = lane / G;
-    uint4 *prof = smem + warp * (6 * ROW);
+    uint16_t *prof = reinterpret_cast<uint16_t *>(smem + warp * (6 * ROW));
     if (threadIdx.x < 36) mat_s[threadIdx.x] = a.sc.mat[threadIdx.x];
     __syncthreads();
 
@@ -154,25 +159,13 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) {
-                        int tc[8];
+                    for (int k = 0; k < K; ++k) {
+                        const int jj = h * K + k; // position inside this lane's 2K columns
+                        int tc = (int)((unit_word(tu[jj >> 5], (jj >> 3) & 3) >> ((jj & 7) * 4)) & 15u);
+                        tc = min(tc, SW_PAD_CODE) * 6;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int jj = h * K + ch * 8 + e; // position inside this lane's 2K columns
-                            tc[e] = (int)((unit_word(tu[jj >> 5], (jj >> 3) & 3) >> ((jj & 7) * 4)) & 15u);
-                            tc[e] = min(tc[e], SW_PAD_CODE) * 6;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const uint32_t s0 = (uint16_t)mat_s[tc[2 * e] + c];
-                                const uint32_t s1 = (uint16_t)mat_s[tc[2 * e + 1] + c];
-                                w[e] = s0 | (s1 << 16);
-                            }
-                            prof[(c * 2 + h) * NCH * 32 + ch * 32 + lane] = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
+                        for (int c = 0; c < 6; ++c)
+                            prof[c * ROW16 + (k * 32 + lane) * 2 + h] = (uint16_t)mat_s[tc + c];
                     }
                 }
             }
@@ -200,7 +193,7 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
             int widx = (-2 * lig) >> 3; // floor
             uint32_t prevw = (widx >= 0 && widx < q_words) ? qw[widx] : 0x55555555u;
             uint32_t cur = 0;
-            const uint4 *row_hi = prof + SW_PAD_CODE * ROW + NCH * 32 + lane; // row -1: padding
+            const uint16_t *row_hi = prof + SW_PAD_CODE * ROW16 + lane * 2 + 1; // row -1: padding
             uint32_t bchunk = 0, wchunk = 0;
 
             for (int t = 0; t < steps; ++t) {
@@ -210,9 +203,9 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
                     cur = __funnelshift_r(prevw, neww, phi4);
                     prevw = neww;
                 }
-                const int c_lo = min((int)(cur & 15u), SW_PAD_CODE);
+                const int c_lo = (int)(cur & 15u); // the pool only holds codes 0..5
                 cur >>= 4;
-                const uint4 *row_lo = prof + c_lo * ROW + lane;
+                const uint16_t *row_lo = prof + c_lo * ROW16 + lane * 2;
 
                 // ---- inputs from the preceding virtual lane ---------------------------------------
                 uint32_t sh = OH, sv = OV;
@@ -235,14 +228,12 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
                 prevIn = inH;
                 uint32_t m2 = 0;
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                    const uint4 pl = row_lo[ch * 32];
-                    const uint4 ph = row_hi[ch * 32];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int k = ch * 8 + e;
-                        const uint32_t wl = unit_word(pl, e >> 1), wh = unit_word(ph, e >> 1);
-                        const uint32_t s = __byte_perm(wl, wh, (e & 1) ? 0x7632 : 0x5410);
+                for (int k = 0; k < K; ++k) {
+                    {
+                        // both halves' scores: two zero-extending 16-bit shared loads merged by one IMAD (FMA pipe),
+                        // keeping the ALU pipe for the DPX recurrence
+                        const uint32_t wl = row_lo[k * 64], wh = row_hi[k * 64];
+                        const uint32_t s = wh * a.k65536 + wl;
                         U[k] = __viaddmax_s16x2_relu(U[k], nGE2, HmO[k]);
                         const uint32_t Hp = __viaddmax_s16x2_relu(diag, s, U[k]);
                         diag = H[k];
@@ -256,9 +247,11 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
                 }
                 OH = H[K - 1];
                 OV = Vv;
-                row_hi = row_lo + NCH * 32;
+                row_hi = row_lo + 1;
 
                 // ---- running maximum of each virtual lane (strict improvement -> step) ------------
+                // (__vibmax_s16x2's predicate outputs would save four instructions here, but the variant built with
+                //  it produced wrong rows on B200 with CUDA 12.9, so the strict-improvement test stays explicit)
                 const uint32_t nb = __vmaxs2(best2, m2);
                 const uint32_t chg = nb ^ best2;
                 if (chg & 0x0000FFFFu) bstep_lo = t;
