@@ -92,6 +92,11 @@ Engine *get_engine(int device)
         delete e;
         return nullptr;
     }
+    for (int i = 0; i < Engine::NAUX; ++i) {
+        cudaStreamCreateWithFlags(&e->aux[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
@@ -102,6 +107,22 @@ Engine *get_engine(int device)
     e->ready = true;
     g_engines[device] = e;
     return e;
+}
+
+int aux_fork(Engine *e, cudaStream_t st)
+{
+    DB200_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
+    for (int i = 0; i < Engine::NAUX; ++i) DB200_CUDA_CHECK(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
+    return DB200_OK;
+}
+
+int aux_join(Engine *e, cudaStream_t st)
+{
+    for (int i = 0; i < Engine::NAUX; ++i) {
+        DB200_CUDA_CHECK(cudaEventRecord(e->ev_join[i], e->aux[i]));
+        DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join[i], 0));
+    }
+    return DB200_OK;
 }
 
 // ---- stage profiling ---------------------------------------------------------------------------------
@@ -303,7 +324,39 @@ int db200_sw_batch_device(int device, const db200_sw_params *params, const uint8
                                 (cudaStream_t)stream);
 }
 
-// Host entry point: chunks of pairs are copied to the device, aligned and copied back.
+// Host entry point.  The batch is cut into chunks that flow through a two-slot pipeline: while chunk i is being
+// aligned on the compute stream, chunk i+1 is copied to the device on the copy stream (pinned host buffers make
+// the copies asynchronous).  Fixed-size results travel back right behind the kernels; the variable-size cigar
+// block of a chunk is fetched once its length is known, one chunk later, so the pipeline never drains.
+struct SwSlot {
+    int64_t c0 = 0, n = 0;
+    uint32_t *d_cig = nullptr;
+    int64_t cig_bound = 0;
+    bool busy = false;
+};
+
+static int sw_finalize_slot(Engine *e, int slot, SwSlot &sl, uint32_t *cigar_buf, int64_t cigar_cap, int64_t *cigar_off,
+                            int64_t &cig_written, cudaStream_t st)
+{
+    if (!sl.busy) return DB200_OK;
+    DB200_CUDA_CHECK(cudaEventSynchronize(e->ev_done[slot]));
+    const int64_t total = reinterpret_cast<int64_t *>(e->pinned_out[slot])[0];
+    if (cigar_buf) {
+        if (total > sl.cig_bound || cig_written + total > cigar_cap) {
+            cudaStreamSynchronize(st);
+            set_error("sw_batch_host: cigar buffer too small");
+            return DB200_ERR_CAPACITY;
+        }
+        if (total > 0)
+            DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_buf + cig_written, sl.d_cig, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    }
+    // entries [c0, c0+n) only: entry c0+n belongs to the next chunk's copy (or is set at the very end)
+    if (cigar_off && cig_written) for (int64_t i = 0; i < sl.n; ++i) cigar_off[sl.c0 + i] += cig_written;
+    cig_written += total;
+    sl.busy = false;
+    return DB200_OK;
+}
+
 int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
                         const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
                         int64_t cigar_cap, int64_t *cigar_off, int32_t *status)
@@ -312,16 +365,19 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     if (!e) return DB200_ERR_CUDA;
     if (npairs < 0 || !params || !qoff || !toff || !results) { set_error("sw_batch_host: bad arguments"); return DB200_ERR_ARG; }
     if (cigar_off) cigar_off[0] = 0;
-    cudaStream_t st = e->stream;
-    const int64_t MAX_CHUNK_PAIRS = (int64_t)1 << 20;
-    const int64_t MAX_CHUNK_BYTES = (int64_t)3 << 30;
+    cudaStream_t st = e->stream, cst = e->copy_stream;
+    const int64_t MAX_CHUNK_BYTES = (int64_t)1 << 30;
+    int64_t chunk_pairs = npairs / 4;
+    if (chunk_pairs < 32768) chunk_pairs = 32768;
+    if (chunk_pairs > 131072) chunk_pairs = 131072;
+    if (const char *cp = getenv("DB200_HOST_CHUNK_PAIRS")) { const int64_t v = atoll(cp); if (v > 0) chunk_pairs = v; }
     int64_t cig_written = 0;
-    std::vector<int64_t> offs;
-    for (int64_t c0 = 0; c0 < npairs;) {
-        int64_t c1 = c0;
-        int64_t bytes = 0;
+    SwSlot slots[2];
+    int iter = 0;
+    for (int64_t c0 = 0; c0 < npairs; ++iter) {
+        int64_t c1 = c0, bytes = 0;
         int32_t maxq = 0;
-        while (c1 < npairs && c1 - c0 < MAX_CHUNK_PAIRS) {
+        while (c1 < npairs && c1 - c0 < chunk_pairs) {
             const int64_t ql = qoff[c1 + 1] - qoff[c1], tl = toff[c1 + 1] - toff[c1];
             if (ql < 0 || tl < 0 || ql > 0x7FFFFFF0 || tl > 0x7FFFFFF0) { set_error("sw_batch_host: bad offsets at pair %lld", (long long)c1); return DB200_ERR_ARG; }
             if (c1 > c0 && bytes + ql + tl > MAX_CHUNK_BYTES) break;
@@ -329,14 +385,28 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
             maxq = std::max<int32_t>(maxq, (int32_t)ql);
             ++c1;
         }
+        const int slot = iter & 1;
+        SwSlot &sl = slots[slot];
+        int rc = sw_finalize_slot(e, slot, sl, cigar_buf, cigar_cap, cigar_off, cig_written, st); // chunk iter-2
+        if (rc) return rc;
         const int64_t n = c1 - c0;
         const int64_t qb = qoff[c1] - qoff[c0], tb = toff[c1] - toff[c0];
-        offs.resize((size_t)(2 * (n + 1)));
-        for (int64_t i = 0; i <= n; ++i) { offs[(size_t)i] = qoff[c0 + i] - qoff[c0]; offs[(size_t)(n + 1 + i)] = toff[c0 + i] - toff[c0]; }
-        Arena &io = e->io[0];
+        // pinned staging of the rebased offsets (+ the slot's cigar-total word in front)
+        const size_t stage_bytes = 64 + sizeof(int64_t) * (size_t)(2 * (n + 1));
+        if (e->pinned_out_cap[slot] < stage_bytes) {
+            if (e->pinned_out[slot]) cudaFreeHost(e->pinned_out[slot]);
+            e->pinned_out[slot] = nullptr;
+            e->pinned_out_cap[slot] = 0;
+            DB200_CUDA_CHECK(cudaHostAlloc(&e->pinned_out[slot], stage_bytes * 2, cudaHostAllocDefault));
+            e->pinned_out_cap[slot] = stage_bytes * 2;
+        }
+        int64_t *total_word = reinterpret_cast<int64_t *>(e->pinned_out[slot]);
+        int64_t *offs = total_word + 8;
+        for (int64_t i = 0; i <= n; ++i) { offs[i] = qoff[c0 + i] - qoff[c0]; offs[n + 1 + i] = toff[c0 + i] - toff[c0]; }
+        Arena &io = e->io[slot];
         io.reset();
-        e->arena[0].reset();
-        const int64_t cig_bound = std::min<int64_t>(cigar_buf ? std::max<int64_t>(cigar_cap - cig_written, 0) : 0, qb + tb + 2 * n);
+        e->arena[slot].reset();
+        const int64_t cig_bound = cigar_buf ? std::min<int64_t>(cigar_cap, qb + tb + 2 * n) : 0;
         uint8_t *d_q = io.alloc<uint8_t>((size_t)qb + 16), *d_t = io.alloc<uint8_t>((size_t)tb + 16);
         int64_t *d_off = io.alloc<int64_t>((size_t)(2 * (n + 1)));
         int32_t *d_mask = mask_len ? io.alloc<int32_t>((size_t)n) : nullptr;
@@ -348,26 +418,31 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
             set_error("sw_batch_host: device allocation failed");
             return DB200_ERR_NOMEM;
         }
-        DB200_CUDA_CHECK(cudaMemcpyAsync(d_q, qbuf + qoff[c0], (size_t)qb, cudaMemcpyHostToDevice, st));
-        DB200_CUDA_CHECK(cudaMemcpyAsync(d_t, tbuf + toff[c0], (size_t)tb, cudaMemcpyHostToDevice, st));
-        DB200_CUDA_CHECK(cudaMemcpyAsync(d_off, offs.data(), sizeof(int64_t) * (size_t)(2 * (n + 1)), cudaMemcpyHostToDevice, st));
-        if (mask_len) DB200_CUDA_CHECK(cudaMemcpyAsync(d_mask, mask_len + c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-        int64_t total = 0;
-        int rc = sw_batch_device_impl(e, e->arena[0], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, d_mask, d_res, d_cig,
-                                      cig_bound, d_coff, d_status, &total, st);
+        // H2D on the copy stream
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_q, qbuf + qoff[c0], (size_t)qb, cudaMemcpyHostToDevice, cst));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_t, tbuf + toff[c0], (size_t)tb, cudaMemcpyHostToDevice, cst));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_off, offs, sizeof(int64_t) * (size_t)(2 * (n + 1)), cudaMemcpyHostToDevice, cst));
+        if (mask_len) DB200_CUDA_CHECK(cudaMemcpyAsync(d_mask, mask_len + c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, cst));
+        DB200_CUDA_CHECK(cudaEventRecord(e->ev_copy[slot], cst));
+        DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_copy[slot], 0));
+        rc = sw_batch_device_impl(e, e->arena[slot], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, d_mask, d_res, d_cig,
+                                  cig_bound, d_coff, d_status, nullptr, st);
         if (rc) return rc;
         DB200_CUDA_CHECK(cudaMemcpyAsync(results + c0, d_res, sizeof(db200_sw_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (status) DB200_CUDA_CHECK(cudaMemcpyAsync(status + c0, d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (cigar_off) DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_off + c0, d_coff, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
-        if (cigar_buf) {
-            if (total > cig_bound) { cudaStreamSynchronize(st); set_error("sw_batch_host: cigar buffer too small"); return DB200_ERR_CAPACITY; }
-            if (total > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_buf + cig_written, d_cig, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
-        }
-        DB200_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (cigar_off && cig_written) for (int64_t i = 0; i <= n; ++i) cigar_off[c0 + i] += cig_written;
-        cig_written += total;
+        DB200_CUDA_CHECK(cudaMemcpyAsync(total_word, d_coff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        DB200_CUDA_CHECK(cudaEventRecord(e->ev_done[slot], st));
+        sl.c0 = c0; sl.n = n; sl.d_cig = d_cig; sl.cig_bound = cig_bound; sl.busy = true;
         c0 = c1;
     }
+    // drain in submission order
+    for (int k = 0; k < 2; ++k) {
+        const int slot = (iter + k) & 1;
+        const int rc = sw_finalize_slot(e, slot, slots[slot], cigar_buf, cigar_cap, cigar_off, cig_written, st);
+        if (rc) return rc;
+    }
+    DB200_CUDA_CHECK(cudaStreamSynchronize(st));
     if (cigar_off) cigar_off[npairs] = cig_written;
     return DB200_OK;
 }

@@ -48,6 +48,10 @@ struct Engine {
     bool ready = false;
     cudaStream_t stream = nullptr;       // used by the *_host entry points
     cudaStream_t copy_stream = nullptr;  // H2D prefetch of the next chunk
+    static constexpr int NAUX = 8;       // side streams: independent length buckets run concurrently so that the
+    cudaStream_t aux[NAUX] = {};         // drain phase of one bucket overlaps the bulk of the next
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[NAUX] = {};
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
     Arena arena[2];                      // compute workspace (one per in-flight chunk)
@@ -75,6 +79,9 @@ inline void count_launch(Engine *e, int n = 1) { e->launches += n; }
 enum Stage { ST_BEGIN = 0, ST_PACK, ST_BUCKET, ST_FORWARD, ST_FORWARD_WATCH, ST_REVERSE_PREP, ST_REVERSE, ST_REVERSE_WATCH,
              ST_FINALIZE, ST_TRACEBACK, ST_CIGAR, ST_ED_PREP, ST_ED_FORWARD, ST_ED_STARTS, ST_ED_OUTPUT, ST_COUNT };
 void prof_mark(Engine *e, cudaStream_t st, int stage);
+// fork: side streams wait for everything enqueued on `st` so far; join: `st` waits for all side streams
+int aux_fork(Engine *e, cudaStream_t st);
+int aux_join(Engine *e, cudaStream_t st);
 
 // Exclusive scan of int32 counts into int64 offsets (offsets[n] = total).  n up to 2^31.
 // tmp must hold ceil(n / 1024) + 1 int64 values.

@@ -717,19 +717,23 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     const bool can_multi = max_query_len > 0;
 
     // 3. forward pass per segment, then the exact re-run of pairs with an ambiguous end row -----------
-    for (int seg = 0; seg < SW_NSEG; ++seg) {
+    { const int rc = aux_fork(e, st); if (rc) return rc; }
+    int aux_i = 0;
+    for (int seg = SW_NSEG - 1; seg >= 0; --seg) {   // widest buckets first: their drain overlaps the narrower ones
         const int cfg = seg >> 1, cmx = seg & 1;
         if (cfg == SW_NCFG - 1 && !can_multi) continue;
+        cudaStream_t ls = e->aux[(aux_i++) % Engine::NAUX];
         pa.meta = meta; pa.tasks = tasks_f; pa.seg_begin = seg_begin_f; pa.seg_count = seg_count_f; pa.seg = seg;
         pa.counter = counters + (counter_idx++);
         pa.out = fwd;
         pa.amb_list = amb_f; pa.amb_count = amb_count_f + 2 * cfg; pa.amb_base_seg = 2 * cfg;
         int rc;
-        if (cmx) { pa.sc = sc; rc = launch_cfg<true, false, false>(e, cfg, pa, st); }
-        else if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, st); }
-        else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, st); }
+        if (cmx) { pa.sc = sc; rc = launch_cfg<true, false, false>(e, cfg, pa, ls); }
+        else if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
+        else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, ls); }
         if (rc) return rc;
     }
+    { const int rc = aux_join(e, st); if (rc) return rc; }
     pa.sc = sc;
     prof_mark(e, st, ST_FORWARD);
     for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
@@ -754,17 +758,20 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     sw_scatter_kernel<<<gpair, TB, 0, st>>>(rmeta, state, npairs, 1, start_r, fill_r, tasks_r);
     count_launch(e, 4);
     prof_mark(e, st, ST_REVERSE_PREP);
-    for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
+    { const int rc = aux_fork(e, st); if (rc) return rc; }
+    for (int cfg = SW_NCFG - 1; cfg >= 0; --cfg) {
         if (cfg == SW_NCFG - 1 && !can_multi) continue;
+        cudaStream_t ls = e->aux[(aux_i++) % Engine::NAUX];
         pa.meta = rmeta; pa.tasks = tasks_r; pa.seg_begin = seg_begin_r; pa.seg_count = seg_count_r; pa.seg = 2 * cfg;
         pa.counter = counters + (counter_idx++);
         pa.out = rev;
         pa.amb_list = amb_r; pa.amb_count = amb_count_r + 2 * cfg; pa.amb_base_seg = 2 * cfg;
         int rc;
-        if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, st); }
-        else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, st); }
+        if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
+        else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, ls); }
         if (rc) return rc;
     }
+    { const int rc = aux_join(e, st); if (rc) return rc; }
     prof_mark(e, st, ST_REVERSE);
     for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
         if (cfg == SW_NCFG - 1 && !can_multi) continue;
