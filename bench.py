@@ -364,6 +364,10 @@ def run_ours(args):
 
 
 def main():
+    # keep stdout clean for the single JSON line: libraries (NCCL prints its version) write to fd 1 as well
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
