@@ -104,6 +104,9 @@ Engine *get_engine(int device)
     const char *mb = getenv("DB200_TRACE_POOL_MB");
     e->trace_pool_bytes = (size_t)(mb ? atol(mb) : 1024) << 20;
     if (e->trace_pool_bytes < ((size_t)16 << 20)) e->trace_pool_bytes = (size_t)16 << 20;
+    const char *sb = getenv("DB200_TRACE_SLAB_MB");
+    e->trace_slab_bytes = (size_t)(sb ? atol(sb) : 4096) << 20;
+    if (e->trace_slab_bytes < ((size_t)64 << 20)) e->trace_slab_bytes = (size_t)64 << 20;
     e->ready = true;
     g_engines[device] = e;
     return e;

@@ -62,7 +62,8 @@ struct Engine {
     size_t pinned_cap = 0;
     void *pinned_out[2] = {nullptr, nullptr};
     size_t pinned_out_cap[2] = {0, 0};
-    size_t trace_pool_bytes = (size_t)1 << 30;
+    size_t trace_pool_bytes = (size_t)1 << 30;  // scratch of the scalar banded traceback (DB200_TRACE_POOL_MB)
+    size_t trace_slab_bytes = (size_t)4 << 30;  // per-block slabs of the wide banded traceback (DB200_TRACE_SLAB_MB)
     // optional stage profiling (CUDA events recorded on the launching stream between pipeline stages)
     bool profiling = false;
     struct Mark { int stage; cudaEvent_t ev; };

@@ -345,176 +345,9 @@ __global__ void sw_finalize_kernel(FinalArgs a)
     if (a.status_out) a.status_out[p] = s.status;
 }
 
-// ------------------------------------------------------------------------------------------------
-// 5. banded traceback, one thread per pair (behaviour of banded_sw, ssw.c:550-728)
-// ------------------------------------------------------------------------------------------------
-struct TraceArgs {
-    const uint4 *pool;
-    const PairMeta *meta;
-    PairState *state;
-    db200_sw_result *results;
-    int64_t npairs;
-    SwScoring sc;
-    uint8_t *scratch;              // bump-allocated per attempt: direction nibbles + rolling rows
-    unsigned long long *scratch_cursor;
-    unsigned long long scratch_cap;
-    uint32_t *cigar_pool;
-    unsigned long long *cigar_cursor;
-    unsigned long long cigar_cap;
-    int32_t *overflow_flag;
-};
-
-// direction nibble: bits 0-1 = H source (0 diagonal, 1 vertical state E, 2 horizontal state F),
-// bit 2 = E opened from H (code 3) else extended (2), bit 3 = F opened from H (code 5) else extended (4)
-__global__ void __launch_bounds__(128) sw_traceback_kernel(TraceArgs a)
-{
-    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= a.npairs) return;
-    PairState &s = a.state[p];
-    if (s.status != DB200_PAIR_OK || !s.want_cigar) return;
-    db200_sw_result &res = a.results[p];
-    const PairMeta pm = a.meta[p];
-    if (res.score1 == 0) {
-        // 1x1 rectangle with score 0: the reference's only observable output is 1M (ssw.c:844-847, 690-698)
-        const unsigned long long pos = atomicAdd(a.cigar_cursor, 1ull);
-        if (pos + 1 > a.cigar_cap) { atomicExch(a.overflow_flag, 1); s.status = DB200_PAIR_NOSCRATCH; return; }
-        a.cigar_pool[pos] = 16u;
-        s.cigar_pos = (int64_t)pos;
-        s.cigar_len = 1;
-        res.cigar_len = 1;
-        return;
-    }
-    const int refLen = res.ref_end1 - res.ref_begin1 + 1;    // columns j
-    const int readLen = res.read_end1 - res.read_begin1 + 1; // rows i
-    const int score = res.score1;
-    const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
-    if (refLen == readLen) {
-        // Gap-free shortcut.  If the main diagonal of the rectangle already collects the optimal score, every
-        // diagonal cell holds exactly its prefix score (a larger value would lift the corner above the optimum),
-        // so the reference's tie rule "diagonal wins when gaps do not beat it" (ssw.c:625) walks the diagonal and the
-        // cigar is one run of readLen matches.  No band has to be evaluated.
-        int sum = 0;
-        for (int i = 0; i < readLen; ++i)
-            sum += a.sc.mat[pool_code(a.pool, pm.t_unit, res.ref_begin1 + i) * 6 + pool_code(a.pool, pm.q_unit, res.read_begin1 + i)];
-        if (sum == score) {
-            const unsigned long long pos = atomicAdd(a.cigar_cursor, 1ull);
-            if (pos + 1 > a.cigar_cap) { atomicExch(a.overflow_flag, 1); s.status = DB200_PAIR_NOSCRATCH; return; }
-            a.cigar_pool[pos] = ((uint32_t)readLen) << 4;
-            s.cigar_pos = (int64_t)pos;
-            s.cigar_len = 1;
-            res.cigar_len = 1;
-            return;
-        }
-    }
-    int bw = abs(refLen - readLen) + 1;
-    uint8_t *dir = nullptr;
-    int width = 0;
-    while (true) {
-        width = min(2 * bw + 1, refLen);
-        // scratch per attempt: direction nibbles + two rolling rows of (H, E), band-relative
-        const unsigned long long dir_bytes = ((((unsigned long long)readLen * (unsigned long long)width + 1) / 2) + 15) & ~15ull;
-        const unsigned long long row_bytes = (unsigned long long)(width + 2) * 4ull * sizeof(int32_t);
-        const unsigned long long need = dir_bytes + row_bytes;
-        const unsigned long long off = atomicAdd(a.scratch_cursor, need);
-        if (off + need > a.scratch_cap) { atomicExch(a.overflow_flag, 2); s.status = DB200_PAIR_NOSCRATCH; return; }
-        dir = a.scratch + off;
-        int32_t *Hp = reinterpret_cast<int32_t *>(a.scratch + off + dir_bytes);
-        int32_t *Ep = Hp + (width + 2), *Hc = Ep + (width + 2), *Ec = Hc + (width + 2);
-        int best = 0;
-        int pbeg = 0, pend = -1;
-        for (int i = 0; i < readLen; ++i) {
-            const int beg = max(0, i - bw), end = min(refLen - 1, i + bw);
-            const int qc = pool_code(a.pool, pm.q_unit, res.read_begin1 + i);
-            int f = 0, hleft = 0;
-            const unsigned long long rowbase = (unsigned long long)i * (unsigned long long)width;
-            for (int j = beg; j <= end; ++j) {
-                const bool up_in = (i > 0 && j >= pbeg && j <= pend);
-                const bool dg_in = (i > 0 && j - 1 >= pbeg && j - 1 <= pend);
-                const int hup = up_in ? Hp[j - pbeg] : 0, eup = up_in ? Ep[j - pbeg] : 0;
-                const int hdg = dg_in ? Hp[j - 1 - pbeg] : 0;
-                int t1 = (i == 0) ? -gapO : hup - gapO;
-                int t2 = (i == 0) ? -gapE : eup - gapE;
-                const int e = t1 > t2 ? t1 : t2;
-                const int e_open = t1 > t2;
-                t1 = hleft - gapO;
-                t2 = f - gapE;
-                f = t1 > t2 ? t1 : t2;
-                const int f_open = t1 > t2;
-                const int e1 = e > 0 ? e : 0, f1 = f > 0 ? f : 0;
-                const int g = e1 > f1 ? e1 : f1;
-                const int tc = pool_code(a.pool, pm.t_unit, res.ref_begin1 + j);
-                const int d = hdg + a.sc.mat[tc * 6 + qc];
-                const int h = g > d ? g : d;
-                if (h > best) best = h;
-                const int src = (g <= d) ? 0 : (e1 > f1 ? 1 : 2);
-                const uint8_t nib = (uint8_t)(src | (e_open << 2) | (f_open << 3));
-                const unsigned long long cell = rowbase + (unsigned long long)(j - beg);
-                uint8_t &byte = dir[cell >> 1];
-                byte = (cell & 1) ? (uint8_t)((byte & 0x0F) | (nib << 4)) : (uint8_t)((byte & 0xF0) | nib);
-                Hc[j - beg] = h; Ec[j - beg] = e;
-                hleft = h;
-            }
-            int32_t *t = Hp; Hp = Hc; Hc = t;
-            t = Ep; Ep = Ec; Ec = t;
-            pbeg = beg; pend = end;
-        }
-        if (best >= score) break;
-        bw *= 2;
-    }
-    // ---- walk twice: first count the runs, then write them in final (reversed) order ------------------
-    int ncig = 0;
-    unsigned long long cpos = 0;
-    for (int phase = 0; phase < 2; ++phase) {
-        int i = readLen - 1, j = refLen - 1;
-        int run = 0, prev = 0, op = 0, state = 2; // state: 0 = in E, 1 = in F, 2 = in H
-        int l = 0;
-        bool bad = false;
-        while (i > 0) {
-            const int beg = max(0, i - bw);
-            const int x = j - beg;
-            if (x < 0 || x >= width || j < 0) { bad = true; break; } // the reference would read out of bounds here
-            const unsigned long long cell = (unsigned long long)i * (unsigned long long)width + (unsigned long long)x;
-            const int nib = (dir[cell >> 1] >> ((cell & 1) * 4)) & 15;
-            int code;
-            if (state == 2) { const int src = nib & 3; code = src == 0 ? 1 : (src == 1 ? ((nib & 4) ? 3 : 2) : ((nib & 8) ? 5 : 4)); }
-            else if (state == 0) code = (nib & 4) ? 3 : 2;
-            else code = (nib & 8) ? 5 : 4;
-            switch (code) {
-                case 1: --i; --j; state = 2; op = 0; break;
-                case 2: --i; state = 0; op = 1; break;
-                case 3: --i; state = 2; op = 1; break;
-                case 4: --j; state = 1; op = 2; break;
-                default: --j; state = 2; op = 2; break;
-            }
-            if (op == prev) ++run;
-            else {
-                if (phase == 1) a.cigar_pool[cpos + (unsigned long long)(ncig - 1 - l)] = ((uint32_t)run << 4) | (uint32_t)prev;
-                ++l;
-                prev = op;
-                run = 1;
-            }
-        }
-        if (bad) { s.status = DB200_PAIR_UNSUPPORTED; res.cigar_len = 0; return; }
-        if (op == 0) {
-            if (phase == 1) a.cigar_pool[cpos + (unsigned long long)(ncig - 1 - l)] = ((uint32_t)(run + 1)) << 4;
-            ++l;
-        } else {
-            if (phase == 1) {
-                a.cigar_pool[cpos + (unsigned long long)(ncig - 1 - l)] = ((uint32_t)run << 4) | (uint32_t)op;
-                a.cigar_pool[cpos + (unsigned long long)(ncig - 2 - l)] = 16u;
-            }
-            l += 2;
-        }
-        if (phase == 0) {
-            ncig = l;
-            cpos = atomicAdd(a.cigar_cursor, (unsigned long long)ncig);
-            if (cpos + (unsigned long long)ncig > a.cigar_cap) { atomicExch(a.overflow_flag, 1); s.status = DB200_PAIR_NOSCRATCH; return; }
-        }
-    }
-    s.cigar_pos = (int64_t)cpos;
-    s.cigar_len = ncig;
-    res.cigar_len = ncig;
-}
+}  // namespace db200
+#include "sw_trace.cuh"
+namespace db200 {
 
 __global__ void sw_colmax_len_kernel(const PairMeta *meta, const PairState *state, int64_t npairs, int32_t *lens)
 {
@@ -661,8 +494,15 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     int32_t *counters = ws.alloc<int32_t>(4096);
     uint32_t *boundary = ws.alloc<uint32_t>(bwarps * (size_t)bstride + 64);
     uint8_t *trace = ws.alloc<uint8_t>(trace_cap);
+    const int wide_blocks = std::min(e->sm_count * 4, 1024);
+    const size_t slab_bytes = (e->trace_slab_bytes / (size_t)wide_blocks) & ~(size_t)255;
+    uint8_t *slab = ws.alloc<uint8_t>(slab_bytes * (size_t)wide_blocks);
+    int32_t *narrow_list = ws.alloc<int32_t>(npairs);
+    int32_t *medium_list = ws.alloc<int32_t>(npairs);
+    int32_t *wide_list = ws.alloc<int32_t>(npairs);
     if (!units || !unit_off || !scan_tmp || !pool || !meta || !rmeta || !state || !fwd || !rev || !tasks_f || !tasks_r || !amb_f ||
-        !amb_r || !colmax_off || !cig_off_tmp || !lens || !colmax || !bins || !cigar_pool || !counters || !boundary || !trace) {
+        !amb_r || !colmax_off || !cig_off_tmp || !lens || !colmax || !bins || !cigar_pool || !counters || !boundary || !trace || !slab ||
+        !narrow_list || !medium_list || !wide_list) {
         set_error("sw_batch: device workspace allocation failed");
         return DB200_ERR_NOMEM;
     }
@@ -728,7 +568,8 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         pa.out = fwd;
         pa.amb_list = amb_f; pa.amb_count = amb_count_f + 2 * cfg; pa.amb_base_seg = 2 * cfg;
         int rc;
-        if (cmx) { pa.sc = sc; rc = launch_cfg<true, false, false>(e, cfg, pa, ls); }
+        if (cmx && tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<true, false, true>(e, cfg, pa, ls); }
+        else if (cmx) { pa.sc = sc; rc = launch_cfg<true, false, false>(e, cfg, pa, ls); }
         else if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
         else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, ls); }
         if (rc) return rc;
@@ -741,7 +582,8 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         pa.meta = meta; pa.tasks = amb_f; pa.seg_begin = seg_begin_f; pa.seg_count = amb_count_f; pa.seg = 2 * cfg;
         pa.counter = counters + (counter_idx++);
         pa.out = fwd;
-        const int rc = launch_cfg<false, true, false>(e, cfg, pa, st);   // only colmax / untagged segments can append here
+        if (tag_ok[cfg]) continue;   // tagged passes are never ambiguous
+        const int rc = launch_cfg<false, true, false>(e, cfg, pa, st);
         if (rc) return rc;
     }
 
@@ -797,7 +639,29 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     ta.sc = sc; ta.scratch = trace; ta.scratch_cursor = trace_cursor; ta.scratch_cap = trace_cap;
     ta.cigar_pool = cigar_pool; ta.cigar_cursor = cigar_cursor; ta.cigar_cap = (unsigned long long)cig_pool_cap;
     ta.overflow_flag = overflow_flag;
-    sw_traceback_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, st>>>(ta);
+    ta.slab = slab; ta.slab_total = (unsigned long long)slab_bytes * (unsigned long long)wide_blocks;
+    ta.list[0] = narrow_list; ta.list[1] = medium_list; ta.list[2] = wide_list;
+    for (int l = 0; l < 3; ++l) { ta.count[l] = counters + 136 + l; ta.counter[l] = counters + 140 + l; }
+    const int warp_blocks = e->sm_count * 24;
+    ta.coop_blocks[0] = 0; ta.coop_blocks[1] = warp_blocks; ta.coop_blocks[2] = wide_blocks;
+    sw_trace_classify_kernel<<<gpair, TB, 0, st>>>(ta);
+    sw_trace_narrow_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, st>>>(ta);
+    {
+        // level 1: one warp per pair (state for 2*62+1 diagonals, 8 KB of walk staging)
+        constexpr int W1 = 254, S1 = 8192;
+        const size_t sm1 = (((size_t)3 * (W1 + 2) * sizeof(int16_t) + 15) & ~(size_t)15) + S1;
+        sw_trace_coop_kernel<32, 1, W1, 0, S1><<<warp_blocks, 32, sm1, st>>>(ta);
+        // level 2: one block per pair (4094 diagonals, both sub-sequences staged, 48 KB of walk staging shared with nothing)
+        constexpr int W2 = TRACE_WMAX, Q2 = TRACE_SEQ_WORDS, S2 = 24576;
+        const size_t sm2 = (((size_t)3 * (W2 + 2) * sizeof(int16_t) + (size_t)Q2 * 4 + 15) & ~(size_t)15) + S2;
+        static bool attr_done[16] = {false};
+        if (!attr_done[e->device & 15]) {
+            DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_trace_coop_kernel<128, 2, W2, Q2, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            attr_done[e->device & 15] = true;
+        }
+        sw_trace_coop_kernel<128, 2, W2, Q2, S2><<<wide_blocks, 128, sm2, st>>>(ta);
+    }
+    count_launch(e, 4);
     prof_mark(e, st, ST_TRACEBACK);
     sw_cigar_len_kernel<<<gpair, TB, 0, st>>>(state, npairs, lens);
     count_launch(e, 3);

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
     constexpr int UNITS = (2 * K) / 32;
     static_assert(K % 16 == 0, "K must be a multiple of 16");
     static_assert(!MULTI || G == 32, "column tiling runs one pair per warp");
-    static_assert(!(TAG && (WATCH || MULTI || COLMAX)), "the tagged variant is the plain single-pass kernel");
+    static_assert(!(TAG && (WATCH || MULTI)), "the tagged variant is a single-pass kernel");
 
     extern __shared__ uint4 smem[];
     __shared__ int16_t mat_s[36];
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
                         const int jb = ps * C + (2 * lig + (int)d) * K;
 #pragma unroll
                         for (int k = 0; k < K; ++k)
-                            if (jb + k < n) lr[jb + k] = (int16_t)(d ? (H[k] >> 16) : (H[k] & 0xFFFFu));
+                            if (jb + k < n) lr[jb + k] = (int16_t)((d ? (H[k] >> 16) : (H[k] & 0xFFFFu)) >> (TAG ? TAGB : 0));
                     }
                 }
 
@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
                 const int jb = ps * C + 2 * lig * K;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    if (jb + k < n) cm[jb + k] = (int16_t)(vmax[k] & 0xFFFFu);
-                    if (jb + K + k < n) cm[jb + K + k] = (int16_t)(vmax[k] >> 16);
+                    if (jb + k < n) cm[jb + k] = (int16_t)((vmax[k] & 0xFFFFu) >> (TAG ? TAGB : 0));
+                    if (jb + K + k < n) cm[jb + K + k] = (int16_t)((vmax[k] >> 16) >> (TAG ? TAGB : 0));
                 }
             }
             int lb_lo = (int)(best2 & 0xFFFFu), lb_hi = (int)(best2 >> 16);

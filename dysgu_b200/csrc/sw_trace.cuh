@@ -1,0 +1,442 @@
+// Banded traceback / cigar stage (behaviour of banded_sw, ssw.c:550-728), three kernels:
+//   sw_trace_classify_kernel  thread per pair: degenerate and gap-free alignments are emitted directly, the rest is
+//                             split by band width into a "narrow" and a "wide" work list
+//   sw_trace_narrow_kernel    thread per listed pair: scalar banded DP (bands of a few columns, short soft clips)
+//   sw_trace_wide_kernel      block per listed pair: anti-diagonal parallel banded DP (long contigs), state in
+//                             shared memory, directions in a per-block scratch slab
+// All of them reproduce the reference's band rule (cells outside the band read as 0), its tie-breaks
+// (ssw.c:610,615,625-626), the band doubling (ssw.c:571-631) and the walk from the bottom-right corner while
+// i > 0 followed by one closing M (ssw.c:641-707).
+#pragma once
+#include "sw_kernels.cuh"
+
+namespace db200 {
+
+struct TraceArgs {
+    const uint4 *pool;
+    const PairMeta *meta;
+    PairState *state;
+    db200_sw_result *results;
+    int64_t npairs;
+    SwScoring sc;
+    uint8_t *scratch;              // narrow kernel: bump-allocated per attempt
+    unsigned long long *scratch_cursor;
+    unsigned long long scratch_cap;
+    uint8_t *slab;                 // cooperative kernels: one slab per block (levels run one after the other)
+    uint32_t *cigar_pool;
+    unsigned long long *cigar_cursor;
+    unsigned long long cigar_cap;
+    int32_t *overflow_flag;
+    // work lists per level: 0 = scalar (thread per pair), 1 = one warp per pair, 2 = one block per pair
+    int32_t *list[3];
+    int32_t *count[3];
+    int32_t *counter[3];           // work counters of the cooperative kernels
+    int32_t coop_blocks[3];        // grid size per level (slab = slab_total / blocks)
+    unsigned long long slab_total;
+};
+
+// level 0 (thread per pair) only takes tiny jobs: rows x band width below this many cells per attempt;
+// level 1 (warp per pair) takes bands of up to TRACE_WARP_BW columns either side; level 2 (block per pair) the rest
+constexpr int TRACE_NARROW_CELLS = 768;
+constexpr int TRACE_WARP_BW = 62;
+__device__ __forceinline__ int trace_level(int readLen, int refLen, int bw)
+{
+    const int width = min(2 * bw + 1, refLen);
+    if ((long long)readLen * width <= TRACE_NARROW_CELLS) return 0;
+    return bw <= TRACE_WARP_BW ? 1 : 2;
+}
+constexpr int TRACE_WMAX = 4094;       // wide kernel: band diagonals held in shared memory (3 x int16 each)
+constexpr int TRACE_SEQ_WORDS = 6144;  // wide kernel: packed codes of both sub-sequences staged in shared memory (48k bases)
+
+// sequential reader of packed 4-bit codes: one 32-bit load per 8 bases
+struct NibReader {
+    const uint32_t *w;
+    int idx;
+    uint32_t cur;
+    __device__ __forceinline__ NibReader(const uint4 *pool, uint32_t unit, int start)
+        : w(reinterpret_cast<const uint32_t *>(pool + unit)), idx(start) { cur = w[idx >> 3]; }
+    __device__ __forceinline__ int next()
+    {
+        const int c = (int)((cur >> ((idx & 7) * 4)) & 15u);
+        ++idx;
+        if ((idx & 7) == 0) cur = w[idx >> 3];
+        return c;
+    }
+};
+
+__device__ __forceinline__ bool trace_emit_single(const TraceArgs &a, PairState &s, db200_sw_result &res, uint32_t op)
+{
+    const unsigned long long pos = atomicAdd(a.cigar_cursor, 1ull);
+    if (pos + 1 > a.cigar_cap) { atomicExch(a.overflow_flag, 1); s.status = DB200_PAIR_NOSCRATCH; return false; }
+    a.cigar_pool[pos] = op;
+    s.cigar_pos = (int64_t)pos;
+    s.cigar_len = 1;
+    res.cigar_len = 1;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) sw_trace_classify_kernel(TraceArgs a)
+{
+    __shared__ int16_t mat_s[36];
+    if (threadIdx.x < 36) mat_s[threadIdx.x] = a.sc.mat[threadIdx.x];
+    __syncthreads();
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= a.npairs) return;
+    PairState &s = a.state[p];
+    if (s.status != DB200_PAIR_OK || !s.want_cigar) return;
+    db200_sw_result &res = a.results[p];
+    const PairMeta pm = a.meta[p];
+    if (res.score1 == 0) {
+        // 1x1 rectangle with score 0: the reference's only observable output is 1M (ssw.c:844-847, 690-698)
+        trace_emit_single(a, s, res, 16u);
+        return;
+    }
+    const int refLen = res.ref_end1 - res.ref_begin1 + 1;    // columns j
+    const int readLen = res.read_end1 - res.read_begin1 + 1; // rows i
+    if (refLen == readLen) {
+        // Gap-free shortcut.  If the main diagonal of the rectangle already collects the optimal score, every
+        // diagonal cell holds exactly its prefix score (a larger value would lift the corner above the optimum),
+        // so the reference's tie rule "diagonal wins when gaps do not beat it" (ssw.c:625) walks the diagonal and
+        // the cigar is one run of readLen matches.  No band has to be evaluated.
+        NibReader rq(a.pool, pm.q_unit, res.read_begin1), rt(a.pool, pm.t_unit, res.ref_begin1);
+        int sum = 0;
+        for (int i = 0; i < readLen; ++i) {
+            const int qc = rq.next(), tc = rt.next();
+            sum += mat_s[tc * 6 + qc];
+        }
+        if (sum == res.score1) { trace_emit_single(a, s, res, ((uint32_t)readLen) << 4); return; }
+    }
+    const int bw = abs(refLen - readLen) + 1;
+    const int lvl = trace_level(readLen, refLen, bw);
+    a.list[lvl][atomicAdd(a.count[lvl], 1)] = (int32_t)p;
+}
+
+// direction nibble: bits 0-1 = H source (0 diagonal, 1 vertical state E, 2 horizontal state F),
+// bit 2 = E opened from H (code 3) else extended (2), bit 3 = F opened from H (code 5) else extended (4)
+__device__ __forceinline__ int trace_step_code(int nib, int state)
+{
+    if (state == 2) { const int src = nib & 3; return src == 0 ? 1 : (src == 1 ? ((nib & 4) ? 3 : 2) : ((nib & 8) ? 5 : 4)); }
+    if (state == 0) return (nib & 4) ? 3 : 2;
+    return (nib & 8) ? 5 : 4;
+}
+
+__global__ void __launch_bounds__(128) sw_trace_narrow_kernel(TraceArgs a)
+{
+    __shared__ int16_t mat_s[36];
+    if (threadIdx.x < 36) mat_s[threadIdx.x] = a.sc.mat[threadIdx.x];
+    __syncthreads();
+    const int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (li >= *a.count[0]) return;
+    const int p = a.list[0][li];
+    PairState &s = a.state[p];
+    db200_sw_result &res = a.results[p];
+    const PairMeta pm = a.meta[p];
+    const int refLen = res.ref_end1 - res.ref_begin1 + 1;
+    const int readLen = res.read_end1 - res.read_begin1 + 1;
+    const int score = res.score1;
+    const int rbeg = res.read_begin1, tbeg = res.ref_begin1; // local copies: the byte stores below may alias `res`
+    const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
+    int bw = abs(refLen - readLen) + 1;
+    uint8_t *dir = nullptr;
+    int width = 0;
+    while (true) {
+        width = min(2 * bw + 1, refLen);
+        {
+            const int lvl = trace_level(readLen, refLen, bw);
+            if (lvl != 0) { // the band outgrew the scalar kernel: hand the pair to a cooperative kernel
+                a.list[lvl][atomicAdd(a.count[lvl], 1)] = p;
+                return;
+            }
+        }
+        // scratch per attempt: direction nibbles + two rolling rows of (H, E), band-relative
+        const unsigned long long dir_bytes = ((((unsigned long long)readLen * (unsigned long long)width + 1) / 2) + 15) & ~15ull;
+        const unsigned long long row_bytes = (unsigned long long)(width + 2) * 4ull * sizeof(int32_t);
+        const unsigned long long need = dir_bytes + row_bytes;
+        const unsigned long long off = atomicAdd(a.scratch_cursor, need);
+        if (off + need > a.scratch_cap) { atomicExch(a.overflow_flag, 2); s.status = DB200_PAIR_NOSCRATCH; return; }
+        dir = a.scratch + off;
+        int32_t *Hp = reinterpret_cast<int32_t *>(a.scratch + off + dir_bytes);
+        int32_t *Ep = Hp + (width + 2), *Hc = Ep + (width + 2), *Ec = Hc + (width + 2);
+        int best = 0;
+        int pbeg = 0, pend = -1;
+        for (int i = 0; i < readLen; ++i) {
+            const int beg = max(0, i - bw), end = min(refLen - 1, i + bw);
+            const int qc = pool_code(a.pool, pm.q_unit, rbeg + i);
+            NibReader rt(a.pool, pm.t_unit, tbeg + beg);
+            int f = 0, hleft = 0;
+            const unsigned long long rowbase = (unsigned long long)i * (unsigned long long)width;
+            for (int j = beg; j <= end; ++j) {
+                const bool up_in = (i > 0 && j >= pbeg && j <= pend);
+                const bool dg_in = (i > 0 && j - 1 >= pbeg && j - 1 <= pend);
+                const int hup = up_in ? Hp[j - pbeg] : 0, eup = up_in ? Ep[j - pbeg] : 0;
+                const int hdg = dg_in ? Hp[j - 1 - pbeg] : 0;
+                int t1 = (i == 0) ? -gapO : hup - gapO;
+                int t2 = (i == 0) ? -gapE : eup - gapE;
+                const int e = t1 > t2 ? t1 : t2;
+                const int e_open = t1 > t2;
+                t1 = hleft - gapO;
+                t2 = f - gapE;
+                f = t1 > t2 ? t1 : t2;
+                const int f_open = t1 > t2;
+                const int e1 = e > 0 ? e : 0, f1 = f > 0 ? f : 0;
+                const int g = e1 > f1 ? e1 : f1;
+                const int tc = rt.next();
+                const int d = hdg + mat_s[tc * 6 + qc];
+                const int h = g > d ? g : d;
+                if (h > best) best = h;
+                const int src = (g <= d) ? 0 : (e1 > f1 ? 1 : 2);
+                const uint8_t nib = (uint8_t)(src | (e_open << 2) | (f_open << 3));
+                const unsigned long long cell = rowbase + (unsigned long long)(j - beg);
+                uint8_t &byte = dir[cell >> 1];
+                byte = (cell & 1) ? (uint8_t)((byte & 0x0F) | (nib << 4)) : (uint8_t)((byte & 0xF0) | nib);
+                Hc[j - beg] = h; Ec[j - beg] = e;
+                hleft = h;
+            }
+            int32_t *t = Hp; Hp = Hc; Hc = t;
+            t = Ep; Ep = Ec; Ec = t;
+            pbeg = beg; pend = end;
+        }
+        if (best >= score) break;
+        bw *= 2;
+    }
+    // ---- walk twice: first count the runs, then write them in final (reversed) order ------------------
+    int ncig = 0;
+    unsigned long long cpos = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        int i = readLen - 1, j = refLen - 1;
+        int run = 0, prev = 0, op = 0, state = 2; // state: 0 = in E, 1 = in F, 2 = in H
+        int l = 0;
+        bool bad = false;
+        while (i > 0) {
+            const int beg = max(0, i - bw);
+            const int x = j - beg;
+            if (x < 0 || x >= width || j < 0) { bad = true; break; } // the reference would read out of bounds here
+            const unsigned long long cell = (unsigned long long)i * (unsigned long long)width + (unsigned long long)x;
+            const int nib = (dir[cell >> 1] >> ((cell & 1) * 4)) & 15;
+            switch (trace_step_code(nib, state)) {
+                case 1: --i; --j; state = 2; op = 0; break;
+                case 2: --i; state = 0; op = 1; break;
+                case 3: --i; state = 2; op = 1; break;
+                case 4: --j; state = 1; op = 2; break;
+                default: --j; state = 2; op = 2; break;
+            }
+            if (op == prev) ++run;
+            else {
+                if (phase == 1) a.cigar_pool[cpos + (unsigned long long)(ncig - 1 - l)] = ((uint32_t)run << 4) | (uint32_t)prev;
+                ++l;
+                prev = op;
+                run = 1;
+            }
+        }
+        if (bad) { s.status = DB200_PAIR_UNSUPPORTED; res.cigar_len = 0; return; }
+        if (op == 0) {
+            if (phase == 1) a.cigar_pool[cpos + (unsigned long long)(ncig - 1 - l)] = ((uint32_t)(run + 1)) << 4;
+            ++l;
+        } else {
+            if (phase == 1) {
+                a.cigar_pool[cpos + (unsigned long long)(ncig - 1 - l)] = ((uint32_t)run << 4) | (uint32_t)op;
+                a.cigar_pool[cpos + (unsigned long long)(ncig - 2 - l)] = 16u;
+            }
+            l += 2;
+        }
+        if (phase == 0) {
+            ncig = l;
+            cpos = atomicAdd(a.cigar_cursor, (unsigned long long)ncig);
+            if (cpos + (unsigned long long)ncig > a.cigar_cap) { atomicExch(a.overflow_flag, 1); s.status = DB200_PAIR_NOSCRATCH; return; }
+        }
+    }
+    s.cigar_pos = (int64_t)cpos;
+    s.cigar_len = ncig;
+    res.cigar_len = ncig;
+}
+
+// Block per pair.  Cells of one anti-diagonal (i + j = const) are independent; with band diagonal x = j - i + OFF the
+// three neighbours of (i, x) are (i-1, x+1) [vertical], (i, x-1) [horizontal] - both on the previous anti-diagonal -
+// and (i-1, x) [diagonal] two anti-diagonals back, so one value per band diagonal (H, E, F as int16 in shared memory)
+// is all the state the sweep needs.  Slots outside the matrix are never written and stay 0, slots outside the band
+// are the zeroed guard entries, which is exactly the reference's "cells outside the band read as 0".
+template <int T> __device__ __forceinline__ void coop_sync() { if (T == 32) __syncwarp(); else __syncthreads(); }
+
+// T = 32: level 1 (one warp per pair, __syncwarp between anti-diagonals); T = 128: level 2 (one block per pair)
+template <int T, int LEVEL, int WMAX, int SEQW, int STAGEB>
+__global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
+{
+    extern __shared__ int16_t sm[];   // [3][WMAX + 2] band state, SEQW words of packed codes, STAGEB bytes of walk staging
+    __shared__ int16_t mat_s[36];
+    __shared__ int sh_task, sh_best, sh_ncig;
+    __shared__ unsigned long long sh_cpos;
+    int16_t *Hs = sm + 1, *Es = sm + (WMAX + 2) + 1, *Fs = sm + 2 * (WMAX + 2) + 1; // index -1 .. XW are valid
+    for (int k = threadIdx.x; k < 36; k += T) mat_s[k] = a.sc.mat[k];
+    coop_sync<T>();
+    const unsigned long long slab_bytes = (a.slab_total / (unsigned long long)a.coop_blocks[LEVEL]) & ~255ull;
+    uint8_t *slab = a.slab + (unsigned long long)blockIdx.x * slab_bytes;
+    const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
+
+    while (true) {
+        if (threadIdx.x == 0) sh_task = atomicAdd(a.counter[LEVEL], 1);
+        coop_sync<T>();
+        const int ti = sh_task;
+        coop_sync<T>();
+        if (ti >= *a.count[LEVEL]) break;
+        const int p = a.list[LEVEL][ti];
+        PairState &s = a.state[p];
+        db200_sw_result &res = a.results[p];
+        const PairMeta pm = a.meta[p];
+        const int refLen = res.ref_end1 - res.ref_begin1 + 1;
+        const int readLen = res.read_end1 - res.read_begin1 + 1;
+        const int score = res.score1;
+        const int rbeg = res.read_begin1, tbeg = res.ref_begin1; // local copies: the byte stores below may alias `res`
+        const uint32_t *qw = reinterpret_cast<const uint32_t *>(a.pool + pm.q_unit);
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(a.pool + pm.t_unit);
+        // stage the codes of both sub-sequences in shared memory (the large carve-out leaves little L1 for them)
+        {
+            uint32_t *seqs = reinterpret_cast<uint32_t *>(sm + 3 * (WMAX + 2));
+            const int qw0 = rbeg >> 3, qwn = ((rbeg + readLen - 1) >> 3) - qw0 + 1;
+            const int tw0 = tbeg >> 3, twn = ((tbeg + refLen - 1) >> 3) - tw0 + 1;
+            if (SEQW > 0 && qwn + twn <= SEQW) {
+                coop_sync<T>();
+                for (int k = threadIdx.x; k < qwn; k += T) seqs[k] = qw[qw0 + k];
+                for (int k = threadIdx.x; k < twn; k += T) seqs[qwn + k] = tw[tw0 + k];
+                coop_sync<T>();
+                qw = seqs - qw0;           // same indexing as the global arrays
+                tw = seqs + qwn - tw0;
+            }
+        }
+        int bw = abs(refLen - readLen) + 1;
+        // a pair escalated from a lower level already failed every band that level accepts: skip those
+        while (trace_level(readLen, refLen, bw) < LEVEL) bw *= 2;
+        int wst = 0;
+        bool failed = false, escalate = false;
+        while (true) {
+            if (LEVEL == 1 && bw > TRACE_WARP_BW) { escalate = true; break; }
+            const int OFF = min(bw, readLen - 1);
+            const int XW = OFF + min(bw, refLen - 1) + 1;            // band diagonals with at least one cell
+            const int width = min(2 * bw + 1, refLen);
+            wst = (width + 15) & ~15;                                 // one byte per cell, 16-byte aligned rows
+            const unsigned long long dir_bytes = (unsigned long long)readLen * (unsigned long long)wst;
+            const unsigned long long runs_bytes = (unsigned long long)(readLen + refLen + 4) * 4ull;
+            if (XW > WMAX || dir_bytes + runs_bytes + 64 > slab_bytes) {
+                if (LEVEL == 1) escalate = true; else failed = true;   // level 2 has the larger slabs
+                break;
+            }
+            for (int x = threadIdx.x - 1; x <= XW; x += T) { Hs[x] = 0; Es[x] = 0; Fs[x] = 0; }
+            if (threadIdx.x == 0) sh_best = 0;
+            coop_sync<T>();
+            int best = 0;
+            const int last_tau = readLen + refLen - 2;
+            for (int tau = 0; tau <= last_tau; ++tau) {
+                // rows on this anti-diagonal: 0 <= j = tau - i < refLen and |j - i| <= bw
+                const int ilo = max(max(0, tau - refLen + 1), (tau - bw + 1) >> 1);
+                const int ihi = min(min(readLen - 1, tau), (tau + bw) >> 1);
+                for (int i = ilo + (int)threadIdx.x; i <= ihi; i += T) {
+                    const int j = tau - i;
+                    const int x = j - i + OFF;
+                    const int hup = Hs[x + 1], eup = Es[x + 1];
+                    const int hleft = Hs[x - 1], fleft = Fs[x - 1];
+                    const int hdg = Hs[x];
+                    int t1 = (i == 0) ? -gapO : hup - gapO;
+                    int t2 = (i == 0) ? -gapE : eup - gapE;
+                    const int e = t1 > t2 ? t1 : t2;
+                    const int e_open = t1 > t2;
+                    t1 = hleft - gapO;
+                    t2 = fleft - gapE;
+                    const int f = t1 > t2 ? t1 : t2;
+                    const int f_open = t1 > t2;
+                    const int e1 = e > 0 ? e : 0, f1 = f > 0 ? f : 0;
+                    const int g = e1 > f1 ? e1 : f1;
+                    const int qi = rbeg + i, tj = tbeg + j;
+                    const int qc = (int)((qw[qi >> 3] >> ((qi & 7) * 4)) & 15u);
+                    const int tc = (int)((tw[tj >> 3] >> ((tj & 7) * 4)) & 15u);
+                    const int d = hdg + mat_s[tc * 6 + qc];
+                    const int h = g > d ? g : d;
+                    best = max(best, h);
+                    const int src = (g <= d) ? 0 : (e1 > f1 ? 1 : 2);
+                    const uint8_t nib = (uint8_t)(src | (e_open << 2) | (f_open << 3));
+#ifndef DB200_TRACE_NOSTORE
+                    slab[(unsigned long long)i * (unsigned long long)wst + (unsigned long long)(j - max(0, i - bw))] = nib;
+#else
+                    if (h == -12345) slab[0] = nib;
+#endif
+                    Hs[x] = (int16_t)h; Es[x] = (int16_t)e; Fs[x] = (int16_t)f;
+                }
+                coop_sync<T>();
+            }
+            atomicMax(&sh_best, best);
+            coop_sync<T>();
+            const int b = sh_best;
+            coop_sync<T>();
+            if (b >= score) break;
+            bw *= 2;
+        }
+        if (escalate) {
+            if (threadIdx.x == 0) a.list[2][atomicAdd(a.count[2], 1)] = p;
+            coop_sync<T>();
+            continue;
+        }
+        if (failed) {
+            if (threadIdx.x == 0) { atomicExch(a.overflow_flag, 2); s.status = DB200_PAIR_NOSCRATCH; }
+            coop_sync<T>();
+            continue;
+        }
+        // ---- walk: rows are staged through shared memory in chunks (coalesced 16-byte copies), one thread follows
+        //      the directions inside the chunk; runs are collected behind the direction bytes, then copied reversed
+        uint32_t *runs = reinterpret_cast<uint32_t *>(slab + (((unsigned long long)readLen * (unsigned long long)wst + 15) & ~15ull));
+        {
+            uint8_t *stage = reinterpret_cast<uint8_t *>(sm) + (((3u * (WMAX + 2) * sizeof(int16_t) + SEQW * 4u) + 15u) & ~15u);
+            const int stage_rows = max(1, (int)((unsigned)STAGEB / (unsigned)wst));
+            const int width = min(2 * bw + 1, refLen);
+            __shared__ int w_i, w_j, w_run, w_prev, w_op, w_state, w_l, w_bad;
+            if (threadIdx.x == 0) { w_i = readLen - 1; w_j = refLen - 1; w_run = 0; w_prev = 0; w_op = 0; w_state = 2; w_l = 0; w_bad = 0; }
+            coop_sync<T>();
+            while (true) {
+                const int i_hi = w_i;
+                if (i_hi <= 0 || w_bad) break;
+                const int i_lo = max(1, i_hi - stage_rows + 1);
+                const uint4 *src = reinterpret_cast<const uint4 *>(slab + (unsigned long long)i_lo * (unsigned long long)wst);
+                uint4 *dst = reinterpret_cast<uint4 *>(stage);
+                const int n16 = (i_hi - i_lo + 1) * (wst >> 4);
+                for (int k = threadIdx.x; k < n16; k += T) dst[k] = src[k];
+                coop_sync<T>();
+                if (threadIdx.x == 0) {
+                    int i = w_i, j = w_j, run = w_run, prev = w_prev, op = w_op, state = w_state, l = w_l;
+                    while (i >= i_lo) {
+                        const int x = j - max(0, i - bw);
+                        if (x < 0 || x >= width || j < 0) { w_bad = 1; break; } // the reference would read out of bounds here
+                        const int nib = stage[(i - i_lo) * wst + x];
+                        switch (trace_step_code(nib, state)) {
+                            case 1: --i; --j; state = 2; op = 0; break;
+                            case 2: --i; state = 0; op = 1; break;
+                            case 3: --i; state = 2; op = 1; break;
+                            case 4: --j; state = 1; op = 2; break;
+                            default: --j; state = 2; op = 2; break;
+                        }
+                        if (op == prev) ++run;
+                        else { runs[l++] = ((uint32_t)run << 4) | (uint32_t)prev; prev = op; run = 1; }
+                    }
+                    w_i = i; w_j = j; w_run = run; w_prev = prev; w_op = op; w_state = state; w_l = l;
+                }
+                coop_sync<T>();
+            }
+            if (threadIdx.x == 0) {
+                int l = w_l;
+                if (w_bad) { s.status = DB200_PAIR_UNSUPPORTED; res.cigar_len = 0; sh_ncig = -1; }
+                else {
+                    if (w_op == 0) runs[l++] = ((uint32_t)(w_run + 1)) << 4;
+                    else { runs[l++] = ((uint32_t)w_run << 4) | (uint32_t)w_op; runs[l++] = 16u; }
+                    const unsigned long long cpos = atomicAdd(a.cigar_cursor, (unsigned long long)l);
+                    if (cpos + (unsigned long long)l > a.cigar_cap) { atomicExch(a.overflow_flag, 1); s.status = DB200_PAIR_NOSCRATCH; sh_ncig = -1; }
+                    else { sh_ncig = l; sh_cpos = cpos; s.cigar_pos = (int64_t)cpos; s.cigar_len = l; res.cigar_len = l; }
+                }
+            }
+        }
+        coop_sync<T>();
+        const int ncig = sh_ncig;
+        if (ncig > 0) {
+            const unsigned long long cpos = sh_cpos;
+            for (int k = threadIdx.x; k < ncig; k += T) a.cigar_pool[cpos + (unsigned long long)k] = runs[ncig - 1 - k];
+        }
+        coop_sync<T>();
+    }
+}
+
+}  // namespace db200
