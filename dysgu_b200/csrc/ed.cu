@@ -303,13 +303,16 @@ static int launch_myers(Engine *e, const EdArgs &a, cudaStream_t st)
 {
     static int blocks_cached[16] = {0};
     int &blocks = blocks_cached[e->device & 15];
+    const size_t smem = (WL <= 8) ? (size_t)4 * ED_SMEM_SYMS * WL * 32 * sizeof(unsigned long long) : 0;
     if (blocks == 0) {
         int per_sm = 0;
-        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ed_myers_kernel<WL, G, REV>, 128, 0));
+        if (smem > 48 * 1024)
+            DB200_CUDA_CHECK(cudaFuncSetAttribute(ed_myers_kernel<WL, G, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ed_myers_kernel<WL, G, REV>, 128, smem));
         if (per_sm < 1) per_sm = 1;
         blocks = e->sm_count * per_sm;
     }
-    ed_myers_kernel<WL, G, REV><<<blocks, 128, 0, st>>>(a);
+    ed_myers_kernel<WL, G, REV><<<blocks, 128, smem, st>>>(a);
     count_launch(e);
     DB200_CUDA_CHECK(cudaGetLastError());
     return DB200_OK;

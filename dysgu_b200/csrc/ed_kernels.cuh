@@ -71,10 +71,16 @@ __device__ __forceinline__ void myers_word(uint64_t &Pv, uint64_t &Mv, uint64_t 
     Mv = Ph & Xv;
 }
 
+constexpr int ED_SMEM_SYMS = 8;   // match vectors of up to 8 distinct target symbols are staged in shared memory
+
 template <int WL, int G, bool REV>
 __global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
 {
     constexpr int GROUPS = 32 / G;
+    constexpr bool SMEM_PEQ = (WL <= 8);
+    // per warp: [symbol][word][lane] 64-bit entries -> conflict-free LDS.64 whatever symbols the lanes read
+    extern __shared__ unsigned long long ed_sm[];
+    unsigned long long *peq_s = ed_sm + (size_t)(threadIdx.x >> 5) * (SMEM_PEQ ? ED_SMEM_SYMS * WL * 32 : 0);
     const int lane = threadIdx.x & 31;
     const int lig = lane % G, grp = lane / G;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -109,6 +115,29 @@ __global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
         const int last_bit = (m - 1) & 63;
         const uint64_t *peq = a.peq + pr.peq_off + (REV ? (int64_t)pr.At * W : 0) + w0;
         const uint8_t *tc = a.tcodes + pr.t_off;
+        // stage this lane's words of every symbol row (warp-uniform decision so that the shuffles below stay converged)
+        bool use_smem = false;
+        if (SMEM_PEQ) {
+            const int at_max = __reduce_max_sync(FULL, pr.At);
+            use_smem = at_max <= ED_SMEM_SYMS;
+            if (use_smem) {
+                __syncwarp();
+#pragma unroll
+                for (int w = 0; w < WL; ++w)
+                    for (int c = 0; c < pr.At; ++c)
+                        peq_s[(c * WL + w) * 32 + lane] = (w < nw) ? peq[(int64_t)c * W + w] : 0ull;
+                __syncwarp();
+            }
+        }
+        // forward streams read the re-coded target as 32-bit words (4 columns), shifted by the lane's column lag and the
+        // byte misalignment of the pair's buffer; reverse streams (short windows) keep byte loads
+        const int tphase = (int)(((uintptr_t)tc - (uintptr_t)lig) & 3u);
+        const uint32_t *tcw = reinterpret_cast<const uint32_t *>((uintptr_t)tc & ~(uintptr_t)3);
+        const int tmis = (int)((uintptr_t)tc & 3u);
+        int twidx = (tmis - lig) >> 2;   // floor((tmis + (0 - lig)) / 4): word holding column -lig
+        const int twords = (tmis + ncols + 3) >> 2;
+        uint32_t tprev = (!REV && twidx >= 0 && twidx < twords) ? tcw[twidx] : 0u;
+        uint32_t tcur = 0;
         const uint32_t hin0 = (REV || a.mode != DB200_ED_MODE_HW) ? 1u : 0u; // SHW / NW: gap before the query costs
 
         uint64_t Pv[WL], Mv[WL];
@@ -128,12 +157,20 @@ __global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
         for (int t = 0; t < steps; ++t) {
             const int j = t - lig;
             const bool valid = active && nw > 0 && j >= 0 && j < ncols;
+            if (!REV && (t & 3) == 0) {
+                ++twidx;
+                const uint32_t tnew = (twidx >= 0 && twidx < twords) ? tcw[twidx] : 0u;
+                tcur = __funnelshift_r(tprev, tnew, tphase * 8);
+                tprev = tnew;
+            }
+            const int c_fwd = (int)((tcur >> ((t & 3) * 8)) & 0xFFu);
             uint32_t cin = carry;
             if (G > 1) cin = __shfl_up_sync(FULL, carry, 1, G);
             if (lig == 0) cin = hin0;
             if (valid) {
-                const int c = REV ? tc[end - j] : tc[j];
+                const int c = REV ? tc[end - j] : c_fwd;
                 const uint64_t *row = peq + (int64_t)c * W;
+                const unsigned long long *srow = peq_s + (c * WL) * 32 + lane;
                 uint32_t hp = cin & 1u, hm = (cin >> 1) & 1u;
                 uint64_t Ph_l = 0, Mh_l = 0;
 #pragma unroll
@@ -141,7 +178,8 @@ __global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
                     if (w < nw) {
                         uint32_t op, om;
                         uint64_t Phr, Mhr;
-                        myers_word(Pv[w], Mv[w], __ldg(row + w), hp, hm, op, om, Phr, Mhr);
+                        const uint64_t eq = (SMEM_PEQ && use_smem) ? srow[w * 32] : __ldg(row + w);
+                        myers_word(Pv[w], Mv[w], eq, hp, hm, op, om, Phr, Mhr);
                         hp = op; hm = om;
                         if (w == last_w) { Ph_l = Phr; Mh_l = Mhr; }
                     }

@@ -87,6 +87,7 @@ Engine *get_engine(int device)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); delete e; return nullptr; }
     e->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete e;
@@ -368,7 +369,7 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     if (!e) return DB200_ERR_CUDA;
     if (npairs < 0 || !params || !qoff || !toff || !results) { set_error("sw_batch_host: bad arguments"); return DB200_ERR_ARG; }
     if (cigar_off) cigar_off[0] = 0;
-    cudaStream_t st = e->stream, cst = e->copy_stream;
+    cudaStream_t cs[2] = {e->stream, e->stream2}, cst = e->copy_stream;
     const int64_t MAX_CHUNK_BYTES = (int64_t)1 << 30;
     int64_t chunk_pairs = npairs / 4;
     if (chunk_pairs < 32768) chunk_pairs = 32768;
@@ -389,6 +390,7 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
             ++c1;
         }
         const int slot = iter & 1;
+        cudaStream_t st = cs[slot];
         SwSlot &sl = slots[slot];
         int rc = sw_finalize_slot(e, slot, sl, cigar_buf, cigar_cap, cigar_off, cig_written, st); // chunk iter-2
         if (rc) return rc;
@@ -442,10 +444,11 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     // drain in submission order
     for (int k = 0; k < 2; ++k) {
         const int slot = (iter + k) & 1;
-        const int rc = sw_finalize_slot(e, slot, slots[slot], cigar_buf, cigar_cap, cigar_off, cig_written, st);
+        const int rc = sw_finalize_slot(e, slot, slots[slot], cigar_buf, cigar_cap, cigar_off, cig_written, cs[slot]);
         if (rc) return rc;
     }
-    DB200_CUDA_CHECK(cudaStreamSynchronize(st));
+    DB200_CUDA_CHECK(cudaStreamSynchronize(cs[0]));
+    DB200_CUDA_CHECK(cudaStreamSynchronize(cs[1]));
     if (cigar_off) cigar_off[npairs] = cig_written;
     return DB200_OK;
 }

@@ -47,6 +47,7 @@ struct Engine {
     int device = -1;
     bool ready = false;
     cudaStream_t stream = nullptr;       // used by the *_host entry points
+    cudaStream_t stream2 = nullptr;      // second compute stream: consecutive host chunks overlap their stage tails
     cudaStream_t copy_stream = nullptr;  // H2D prefetch of the next chunk
     static constexpr int NAUX = 8;       // side streams: independent length buckets run concurrently so that the
     cudaStream_t aux[NAUX] = {};         // drain phase of one bucket overlaps the bulk of the next

@@ -384,19 +384,19 @@ template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG>
 static int launch_pass(Engine *e, const PassArgs &a, cudaStream_t st)
 {
     constexpr int NCH = K / 8, ROW = 2 * NCH * 32;
-    const size_t smem = (size_t)4 * 6 * ROW * sizeof(uint4);
+    const size_t smem = (size_t)(SW_PASS_THREADS / 32) * 6 * ROW * sizeof(uint4);
     static int blocks_cached[16] = {0};
     int &blocks = blocks_cached[e->device & 15];
     if (blocks == 0) {
         DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG>, 128, smem));
+        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG>, SW_PASS_THREADS, smem));
         if (per_sm < 1) per_sm = 1;
-        if (MULTI && per_sm * 4 > SW_MULTI_MAX_WARPS_PER_SM) per_sm = SW_MULTI_MAX_WARPS_PER_SM / 4;
+        if (MULTI && per_sm * (SW_PASS_THREADS / 32) > SW_MULTI_MAX_WARPS_PER_SM) per_sm = SW_MULTI_MAX_WARPS_PER_SM / (SW_PASS_THREADS / 32);
         blocks = e->sm_count * per_sm;
     }
-    sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG><<<blocks, 128, smem, st>>>(a);
+    sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG><<<blocks, SW_PASS_THREADS, smem, st>>>(a);
     count_launch(e);
     DB200_CUDA_CHECK(cudaGetLastError());
     return DB200_OK;

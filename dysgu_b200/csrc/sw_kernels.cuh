@@ -27,7 +27,13 @@ constexpr int SW_NEG = -16384;
 constexpr int SW_NCFG = 12;          // kernel configurations (K, G)
 constexpr int SW_LBINS = 512;        // length bins per (config, colmax) segment, 32 rows each
 constexpr int SW_NSEG = SW_NCFG * 2; // (config, needs column maxima)
-constexpr int SW_MULTI_MAX_WARPS_PER_SM = 8; // bounds the per-warp boundary scratch of the column-tiled kernel
+constexpr int SW_MULTI_MAX_WARPS_PER_SM = 8;
+#ifndef SW_PASS_THREADS
+#define SW_PASS_THREADS 128       // four warps per block (two-warp blocks with nine blocks per SM measured the same)
+#endif
+#ifndef SW_PASS_MIN_BLOCKS
+#define SW_PASS_MIN_BLOCKS 4
+#endif // bounds the per-warp boundary scratch of the column-tiled kernel
 
 struct PairMeta {      // one alignment problem on packed sequences
     uint32_t q_unit;   // offset of the streamed sequence in the nibble pool, in 16-byte units (32 bases)
@@ -87,7 +93,7 @@ __device__ __forceinline__ int pool_code(const uint4 *pool, uint32_t unit, int i
 // TAG: scores are pre-scaled by 2^TAGB (host side) and the column index inside the virtual lane rides in the low
 // bits of the running maximum, so the best cell's column and row are exact without per-column maxima.
 template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG>
-__global__ void __launch_bounds__(128) sw_pass_kernel(PassArgs a)
+__global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS_MIN_BLOCKS : 1) sw_pass_kernel(PassArgs a)
 {
     constexpr int V = 2 * G;          // virtual lanes per group
     constexpr int C = V * K;          // columns per pass
