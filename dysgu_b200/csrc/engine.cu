@@ -450,6 +450,61 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     DB200_CUDA_CHECK(cudaStreamSynchronize(cs[0]));
     DB200_CUDA_CHECK(cudaStreamSynchronize(cs[1]));
     if (cigar_off) cigar_off[npairs] = cig_written;
+    // Pairs whose traceback did not fit the scratch pools of a large chunk are re-run in small groups (each group
+    // then has the whole pool to itself); their cigars are appended and cigar_off is rebuilt in pair order.
+    static thread_local bool in_retry = false;
+    if (status && cigar_buf && cigar_off && !in_retry) {
+        std::vector<int64_t> redo;
+        for (int64_t i = 0; i < npairs; ++i) if (status[i] == DB200_PAIR_NOSCRATCH) redo.push_back(i);
+        if (!redo.empty()) {
+            if (getenv("DB200_DEBUG")) fprintf(stderr, "[db200] retrying %zu scratch-starved pairs\n", redo.size());
+            std::vector<std::vector<uint32_t>> extra(redo.size());
+            const size_t GROUP = 32;
+            for (size_t g0 = 0; g0 < redo.size(); g0 += GROUP) {
+                const size_t g1 = std::min(redo.size(), g0 + GROUP);
+                std::vector<uint8_t> qb, tb;
+                std::vector<int64_t> qo(1, 0), to(1, 0);
+                std::vector<int32_t> ml;
+                for (size_t k = g0; k < g1; ++k) {
+                    const int64_t i = redo[k];
+                    qb.insert(qb.end(), qbuf + qoff[i], qbuf + qoff[i + 1]); qo.push_back((int64_t)qb.size());
+                    tb.insert(tb.end(), tbuf + toff[i], tbuf + toff[i + 1]); to.push_back((int64_t)tb.size());
+                    if (mask_len) ml.push_back(mask_len[i]);
+                }
+                const int64_t gn = (int64_t)(g1 - g0);
+                std::vector<db200_sw_result> r((size_t)gn);
+                std::vector<int32_t> st2((size_t)gn);
+                std::vector<int64_t> co((size_t)gn + 1);
+                std::vector<uint32_t> cg(qb.size() + tb.size() + 2 * (size_t)gn + 16);
+                in_retry = true;
+                const int rc = db200_sw_batch_host(device, params, qb.data(), qo.data(), tb.data(), to.data(), gn, mask_len ? ml.data() : nullptr,
+                                                   r.data(), cg.data(), (int64_t)cg.size(), co.data(), st2.data());
+                in_retry = false;
+                if (getenv("DB200_DEBUG")) { int nb = 0; for (auto v : st2) nb += v != 0; fprintf(stderr, "[db200] retry group of %lld: rc=%d still failing=%d\n", (long long)gn, rc, nb); }
+                if (rc) return rc;
+                for (int64_t k = 0; k < gn; ++k) {
+                    const int64_t i = redo[g0 + (size_t)k];
+                    results[i] = r[(size_t)k];
+                    status[i] = st2[(size_t)k];
+                    extra[g0 + (size_t)k].assign(cg.begin() + co[(size_t)k], cg.begin() + co[(size_t)k + 1]);
+                }
+            }
+            // rebuild the cigar CSR in pair order
+            std::vector<uint32_t> merged;
+            merged.reserve((size_t)cig_written + 1024);
+            std::vector<int64_t> noff((size_t)npairs + 1, 0);
+            size_t rk = 0;
+            for (int64_t i = 0; i < npairs; ++i) {
+                noff[(size_t)i] = (int64_t)merged.size();
+                if (rk < redo.size() && redo[rk] == i) { merged.insert(merged.end(), extra[rk].begin(), extra[rk].end()); ++rk; }
+                else merged.insert(merged.end(), cigar_buf + cigar_off[i], cigar_buf + cigar_off[i + 1]);
+            }
+            noff[(size_t)npairs] = (int64_t)merged.size();
+            if ((int64_t)merged.size() > cigar_cap) { set_error("sw_batch_host: cigar buffer too small"); return DB200_ERR_CAPACITY; }
+            memcpy(cigar_buf, merged.data(), merged.size() * sizeof(uint32_t));
+            memcpy(cigar_off, noff.data(), noff.size() * sizeof(int64_t));
+        }
+    }
     return DB200_OK;
 }
 

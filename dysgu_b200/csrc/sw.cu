@@ -24,7 +24,7 @@ struct PairState {          // per-pair bookkeeping of the pipeline
     int32_t want_rev;       // reverse pass required
     int32_t want_cigar;     // traceback required
     int32_t cigar_len;
-    int32_t pad_;
+    int32_t trace_bw;       // next band half-width the traceback has to try (travels with a pair between levels)
     int64_t cigar_pos;      // position in the cigar pool
 };
 
@@ -639,6 +639,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     ta.sc = sc; ta.scratch = trace; ta.scratch_cursor = trace_cursor; ta.scratch_cap = trace_cap;
     ta.cigar_pool = cigar_pool; ta.cigar_cursor = cigar_cursor; ta.cigar_cap = (unsigned long long)cig_pool_cap;
     ta.overflow_flag = overflow_flag;
+    ta.debug = getenv("DB200_DEBUG") ? 1 : 0;
     ta.slab = slab; ta.slab_total = (unsigned long long)slab_bytes * (unsigned long long)wide_blocks;
     ta.list[0] = narrow_list; ta.list[1] = medium_list; ta.list[2] = wide_list;
     for (int l = 0; l < 3; ++l) { ta.count[l] = counters + 136 + l; ta.counter[l] = counters + 140 + l; }

@@ -33,6 +33,7 @@ struct TraceArgs {
     int32_t *counter[3];           // work counters of the cooperative kernels
     int32_t coop_blocks[3];        // grid size per level (slab = slab_total / blocks)
     unsigned long long slab_total;
+    int32_t debug;
 };
 
 // level 0 (thread per pair) only takes tiny jobs: rows x band width below this many cells per attempt;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(256) sw_trace_classify_kernel(TraceArgs a)
     }
     const int bw = abs(refLen - readLen) + 1;
     const int lvl = trace_level(readLen, refLen, bw);
+    s.trace_bw = bw;
     a.list[lvl][atomicAdd(a.count[lvl], 1)] = (int32_t)p;
 }
 
@@ -143,7 +145,8 @@ __global__ void __launch_bounds__(128) sw_trace_narrow_kernel(TraceArgs a)
         width = min(2 * bw + 1, refLen);
         {
             const int lvl = trace_level(readLen, refLen, bw);
-            if (lvl != 0) { // the band outgrew the scalar kernel: hand the pair to a cooperative kernel
+            if (lvl != 0) { // the band outgrew the scalar kernel: hand the pair (and the band to try next) to a cooperative kernel
+                s.trace_bw = bw;
                 a.list[lvl][atomicAdd(a.count[lvl], 1)] = p;
                 return;
             }
@@ -268,7 +271,10 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
     int16_t *Hs = sm + 1, *Es = sm + (WMAX + 2) + 1, *Fs = sm + 2 * (WMAX + 2) + 1; // index -1 .. XW are valid
     for (int k = threadIdx.x; k < 36; k += T) mat_s[k] = a.sc.mat[k];
     coop_sync<T>();
-    const unsigned long long slab_bytes = (a.slab_total / (unsigned long long)a.coop_blocks[LEVEL]) & ~255ull;
+    // the slab area is divided among the blocks that can have work: few pairs -> few, large slabs
+    const int nslabs = min((int)gridDim.x, max(*a.count[LEVEL], 1));
+    if ((int)blockIdx.x >= nslabs) return;
+    const unsigned long long slab_bytes = (a.slab_total / (unsigned long long)nslabs) & ~255ull;
     uint8_t *slab = a.slab + (unsigned long long)blockIdx.x * slab_bytes;
     const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
 
@@ -302,9 +308,7 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
                 tw = seqs + qwn - tw0;
             }
         }
-        int bw = abs(refLen - readLen) + 1;
-        // a pair escalated from a lower level already failed every band that level accepts: skip those
-        while (trace_level(readLen, refLen, bw) < LEVEL) bw *= 2;
+        int bw = s.trace_bw;   // first band, or the one a lower level could not hold
         int wst = 0;
         bool failed = false, escalate = false;
         while (true) {
@@ -369,11 +373,14 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
             bw *= 2;
         }
         if (escalate) {
-            if (threadIdx.x == 0) a.list[2][atomicAdd(a.count[2], 1)] = p;
+            if (threadIdx.x == 0) { s.trace_bw = bw; a.list[2][atomicAdd(a.count[2], 1)] = p; }
             coop_sync<T>();
             continue;
         }
         if (failed) {
+            if (threadIdx.x == 0 && a.debug)
+                printf("[db200] traceback level %d: pair %d rows %d cols %d band %d does not fit (slab %llu bytes, %d slabs)\n", LEVEL, p,
+                       readLen, refLen, bw, slab_bytes, nslabs);
             if (threadIdx.x == 0) { atomicExch(a.overflow_flag, 2); s.status = DB200_PAIR_NOSCRATCH; }
             coop_sync<T>();
             continue;

@@ -77,3 +77,26 @@ def test_empty_sequences_are_reported():
     res = batch.sw_align_batch([b"", b"ACGT", b"ACGT"], [b"ACGT", b"", b"ACGT"], 2, -3, 5, 2)
     assert list(res.status) == [1, 1, 0]
     assert res.as_tuple(2) == (8, 0, 0, 3, 0, 3, 0, "4M")
+
+
+def test_scratch_starved_pairs_are_retried():
+    # with tiny traceback pools a batch of long, indel-rich contigs cannot hold every direction matrix at once:
+    # the host entry point must re-run the starved pairs in small groups and still return bit-exact cigars
+    import subprocess
+    import sys
+    import os
+    code = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from dysgu_b200 import batch, workloads
+from oracle import oracle as O
+a, b, prm = workloads.contig_pairs(300, seed=17, platform="ont", lo=1500, hi=4000)
+qs, ts = a.tolist(), b.tolist()
+res = batch.sw_align_batch(qs, ts, **prm)
+ref = O.oracle_sw(qs, ts, prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"])
+bad = sum(1 for i in range(len(qs)) if res.status[i] != 0 or res.as_tuple(i) != ref.as_tuple(i))
+print("BAD", bad)
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DB200_TRACE_POOL_MB="16", DB200_TRACE_SLAB_MB="64")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "BAD 0" in out.stdout, out.stdout[-500:] + out.stderr[-1500:]
