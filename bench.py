@@ -196,6 +196,7 @@ def run_ours(args):
     n = len(q)
     q_bytes, t_bytes = int(q.off[-1]), int(t.off[-1])
     max_q = int(q.lengths.max())
+    max_t = int(t.lengths.max())
 
     prm_c = _lib.SwParams()
     prm_c.match, prm_c.mismatch, prm_c.gap_open, prm_c.gap_extend = prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"]
@@ -215,7 +216,7 @@ def run_ours(args):
 
     def device_step():
         rc = L.db200_sw_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
-                                     d_toff.data_ptr(), t_bytes, n, max_q, None, d_res.data_ptr(), d_cig.data_ptr(), cig_cap,
+                                     d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_cig.data_ptr(), cig_cap,
                                      d_coff.data_ptr(), d_status.data_ptr(), None, C.c_void_p(stream.cuda_stream))
         _lib.check(rc, "db200_sw_batch_device")
 

@@ -27,6 +27,21 @@ def default_device() -> int:
     return int(os.environ.get("DB200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
+def pinned_copy(b: SeqBatch) -> SeqBatch:
+    """Copy a batch into page-locked host memory (db200_host_alloc) so that the host entry points copy asynchronously."""
+    L = _lib.lib()
+
+    def pin(a):
+        n = max(int(a.nbytes), 1)
+        ptr = L.db200_host_alloc(n)
+        if not ptr:
+            raise _lib.AlignEngineError("pinned allocation failed")
+        out = np.frombuffer((C.c_uint8 * n).from_address(ptr), dtype=a.dtype, count=a.size)
+        out[:] = a
+        return out
+    return SeqBatch.__new_pinned__(pin(b.buf), pin(b.off))
+
+
 def _as_batch(x) -> SeqBatch:
     return x if isinstance(x, SeqBatch) else SeqBatch.from_list(x)
 

@@ -317,14 +317,14 @@ void db200_host_free(void *p)
 // ---- Smith-Waterman -------------------------------------------------------------------------------
 int db200_sw_batch_device(int device, const db200_sw_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
                           const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs, int32_t max_query_len,
-                          const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
+                          int32_t max_target_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
                           int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, void *stream)
 {
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
     e->arena[0].reset();
     return sw_batch_device_impl(e, e->arena[0], params, d_qbuf, d_qoff, q_bytes, d_tbuf, d_toff, t_bytes, npairs, max_query_len,
-                                d_mask_len, d_results, d_cigar_buf, cigar_cap, d_cigar_off, d_status, cigar_total,
+                                max_target_len, d_mask_len, d_results, d_cigar_buf, cigar_cap, d_cigar_off, d_status, cigar_total,
                                 (cudaStream_t)stream);
 }
 
@@ -380,13 +380,14 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     int iter = 0;
     for (int64_t c0 = 0; c0 < npairs; ++iter) {
         int64_t c1 = c0, bytes = 0;
-        int32_t maxq = 0;
+        int32_t maxq = 0, maxt = 0;
         while (c1 < npairs && c1 - c0 < chunk_pairs) {
             const int64_t ql = qoff[c1 + 1] - qoff[c1], tl = toff[c1 + 1] - toff[c1];
             if (ql < 0 || tl < 0 || ql > 0x7FFFFFF0 || tl > 0x7FFFFFF0) { set_error("sw_batch_host: bad offsets at pair %lld", (long long)c1); return DB200_ERR_ARG; }
             if (c1 > c0 && bytes + ql + tl > MAX_CHUNK_BYTES) break;
             bytes += ql + tl;
             maxq = std::max<int32_t>(maxq, (int32_t)ql);
+            maxt = std::max<int32_t>(maxt, (int32_t)tl);
             ++c1;
         }
         const int slot = iter & 1;
@@ -430,7 +431,7 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
         if (mask_len) DB200_CUDA_CHECK(cudaMemcpyAsync(d_mask, mask_len + c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, cst));
         DB200_CUDA_CHECK(cudaEventRecord(e->ev_copy[slot], cst));
         DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_copy[slot], 0));
-        rc = sw_batch_device_impl(e, e->arena[slot], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, d_mask, d_res, d_cig,
+        rc = sw_batch_device_impl(e, e->arena[slot], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, maxt, d_mask, d_res, d_cig,
                                   cig_bound, d_coff, d_status, nullptr, st);
         if (rc) return rc;
         DB200_CUDA_CHECK(cudaMemcpyAsync(results + c0, d_res, sizeof(db200_sw_result) * (size_t)n, cudaMemcpyDeviceToHost, st));

@@ -92,7 +92,7 @@ inline size_t scan_tmp_count(int64_t n) { return (size_t)((n + 1023) / 1024 + 2)
 
 int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff,
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
-                         int32_t max_query_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
+                         int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
                          int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st);
 
 int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff,

@@ -425,7 +425,8 @@ static int launch_cfg(Engine *e, int cfg, const PassArgs &a, cudaStream_t st)
 
 int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const uint8_t *d_qbuf, const int64_t *d_qoff,
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
-                         int32_t max_query_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf,
+                         int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len, db200_sw_result *d_results,
+                         uint32_t *d_cigar_buf,
                          int64_t cigar_cap, int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st)
 {
     if (npairs < 0 || !prm || !d_results) { set_error("sw_batch: bad arguments"); return DB200_ERR_ARG; }
@@ -493,6 +494,13 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     uint32_t *cigar_pool = ws.alloc<uint32_t>((size_t)cig_pool_cap + 16);
     int32_t *counters = ws.alloc<int32_t>(4096);
     uint32_t *boundary = ws.alloc<uint32_t>(bwarps * (size_t)bstride + 64);
+    // per-pair boundary columns of column-tiled pairs: rows x (passes - 1) words each; bounded by the query bytes
+    // times the largest pass count any target of this batch can need
+    const int64_t max_t = max_target_len > 0 ? max_target_len : 0;
+    const int64_t max_extra_passes = max_t > 2048 ? (max_t + 2047) / 2048 - 1 : 0;
+    const size_t bnd_cap = (size_t)std::min<int64_t>(2 * (q_bytes + 32 * npairs) * max_extra_passes, (int64_t)1 << 30); // forward + reverse
+    uint32_t *bnd_pool = ws.alloc<uint32_t>(bnd_cap + 64);
+    long long *bnd_off = ws.alloc<long long>(2 * (size_t)npairs);
     uint8_t *trace = ws.alloc<uint8_t>(trace_cap);
     const int wide_blocks = std::min(e->sm_count * 4, 1024);
     const size_t slab_bytes = (e->trace_slab_bytes / (size_t)wide_blocks) & ~(size_t)255;
@@ -502,6 +510,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     int32_t *wide_list = ws.alloc<int32_t>(npairs);
     if (!units || !unit_off || !scan_tmp || !pool || !meta || !rmeta || !state || !fwd || !rev || !tasks_f || !tasks_r || !amb_f ||
         !amb_r || !colmax_off || !cig_off_tmp || !lens || !colmax || !bins || !cigar_pool || !counters || !boundary || !trace || !slab ||
+        !bnd_pool || !bnd_off ||
         !narrow_list || !medium_list || !wide_list) {
         set_error("sw_batch: device workspace allocation failed");
         return DB200_ERR_NOMEM;
@@ -551,6 +560,9 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     pa.pool = reinterpret_cast<const uint4 *>(pool);
     pa.colmax = colmax; pa.colmax_off = colmax_off;
     pa.boundary = boundary; pa.boundary_stride = bstride;
+    pa.bnd_pool = bnd_pool; pa.bnd_cap = (unsigned long long)bnd_cap;
+    pa.bnd_cursor = reinterpret_cast<unsigned long long *>(counters + 144);
+    pa.bnd_off = bnd_off;
     pa.k65536 = 65536u;
     pa.sc = sc;
     int counter_idx = 0;
@@ -600,6 +612,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     sw_scatter_kernel<<<gpair, TB, 0, st>>>(rmeta, state, npairs, 1, start_r, fill_r, tasks_r);
     count_launch(e, 4);
     prof_mark(e, st, ST_REVERSE_PREP);
+    pa.bnd_off = bnd_off + npairs;   // the reversed problems keep their own boundary columns
     { const int rc = aux_fork(e, st); if (rc) return rc; }
     for (int cfg = SW_NCFG - 1; cfg >= 0; --cfg) {
         if (cfg == SW_NCFG - 1 && !can_multi) continue;

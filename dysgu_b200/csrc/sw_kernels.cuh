@@ -65,8 +65,12 @@ struct PassArgs {
     PassOut *out;
     int16_t *colmax;           // COLMAX: per-column maxima then last-row values, at colmax_off[pair]
     const int64_t *colmax_off;
-    uint32_t *boundary;        // MULTI: per-warp right-edge column
+    uint32_t *boundary;        // MULTI: per-warp right-edge column (fallback when the per-pair pool is exhausted)
     int32_t boundary_stride;
+    uint32_t *bnd_pool;        // MULTI: per-pair, per-pass right-edge columns, kept so that an ambiguous pair only
+    unsigned long long *bnd_cursor; //        has to re-run the winning pass
+    unsigned long long bnd_cap;
+    long long *bnd_off;        // per pair: offset into bnd_pool (words), -1 if not kept
     int32_t *amb_list;         // pairs whose end_q is ambiguous (appended at seg_begin[amb_base_seg])
     int32_t *amb_count;
     int32_t amb_base_seg;
@@ -150,7 +154,29 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
 
         int run_score = -1, run_slot = 0, run_row = 0, run_amb = 0, run_wrow = -1;
 
-        for (int ps = 0; ps < npass; ++ps) {
+        // column-tiled pairs keep the right-edge column of every pass (rows padded to 32 per pass)
+        int ps_first = 0, ps_last = npass;
+        uint32_t *pbnd = nullptr;          // per-pair boundary storage, pass p at pbnd + p * bstride
+        int bstride = 0;
+        if (MULTI && active && npass > 1) {
+            bstride = (m + 31) & ~31;
+            long long off = -1;
+            if (!WATCH) {
+                if (lane == 0) {
+                    const unsigned long long need = (unsigned long long)bstride * (unsigned long long)(npass - 1);
+                    const unsigned long long o = atomicAdd(a.bnd_cursor, need);
+                    off = (o + need <= a.bnd_cap) ? (long long)o : -1;
+                    a.bnd_off[pair] = off;
+                }
+                off = __shfl_sync(FULL, off, 0);
+            } else {
+                off = a.bnd_off[pair];
+                if (off >= 0) { ps_first = watch_slot / C; ps_last = ps_first + 1; } // only the winning pass is re-run
+            }
+            if (off >= 0) pbnd = a.bnd_pool + off;
+        }
+
+        for (int ps = ps_first; ps < ps_last; ++ps) {
             // ---- profile of this pass's columns -> shared memory -------------------------------
             __syncwarp();
             {
@@ -227,7 +253,10 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
                     sv = __shfl_sync(FULL, OV, lane - 1);
                 }
                 if (MULTI) {
-                    if ((t & 31) == 0) bchunk = (ps > 0 && t + lane < m) ? bnd[t + lane] : 0u;
+                    if ((t & 31) == 0) {
+                        const uint32_t *src = pbnd ? pbnd + (size_t)(ps - 1) * bstride : bnd;
+                        bchunk = (ps > 0 && t + lane < m) ? src[t + lane] : 0u;
+                    }
                     const uint32_t y = __shfl_sync(FULL, bchunk, t & 31);
                     if (lig == 0) { sh = y << 16; sv = y & 0xFFFF0000u; }
                 } else {
@@ -303,7 +332,8 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
                         if (lane == (r & 31)) wchunk = val;
                         if ((r & 31) == 31 || t == steps - 1) {
                             const int r0 = r & ~31;
-                            if (lane <= (r & 31) && r0 + lane < m && ps + 1 < npass) bnd[r0 + lane] = wchunk;
+                            uint32_t *dst = pbnd ? pbnd + (size_t)ps * bstride : bnd;
+                            if (lane <= (r & 31) && r0 + lane < m && ps + 1 < npass && !(WATCH && pbnd)) dst[r0 + lane] = wchunk;
                         }
                     }
                 }

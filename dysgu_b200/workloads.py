@@ -25,6 +25,13 @@ class SeqBatch:
         self.buf = np.ascontiguousarray(buf, dtype=np.uint8)
         self.off = np.ascontiguousarray(off, dtype=np.int64)
 
+    @classmethod
+    def __new_pinned__(cls, buf, off):
+        """Wrap existing arrays without copying (used for page-locked buffers)."""
+        self = cls.__new__(cls)
+        self.buf, self.off = buf, off
+        return self
+
     def __len__(self):
         return len(self.off) - 1
 

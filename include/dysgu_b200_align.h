@@ -115,7 +115,7 @@ int db200_sw_batch_host(int device, const db200_sw_params *params,
 
 /*
  * Same with every buffer resident in device memory.  q_bytes / t_bytes are the total buffer
- * lengths (qoff[npairs], toff[npairs]) and max_query_len an upper bound of the query lengths -
+ * lengths (qoff[npairs], toff[npairs]) and max_query_len / max_target_len upper bounds of the sequence lengths -
  * known to the caller, needed to size the workspace without a device round trip (0 disables
  * the column-tiled kernel, i.e. targets longer than 1024 are then reported as unsupported).
  * Everything is enqueued on `stream`; the call only synchronises when cigar_total is non-NULL
@@ -124,7 +124,7 @@ int db200_sw_batch_host(int device, const db200_sw_params *params,
 int db200_sw_batch_device(int device, const db200_sw_params *params,
                           const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
                           const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
-                          int32_t max_query_len, const int32_t *d_mask_len,
+                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len,
                           db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
                           int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, void *stream);
 

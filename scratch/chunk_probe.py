@@ -14,7 +14,7 @@ for pairs in (65536, 131072, 262144, 524288):
     d_res=torch.zeros((n,8),dtype=torch.int32,device=dev); d_cig=torch.zeros(cap,dtype=torch.int32,device=dev); d_co=torch.zeros(n+1,dtype=torch.int64,device=dev); d_st=torch.zeros(n,dtype=torch.int32,device=dev)
     st=torch.cuda.current_stream(dev)
     def step():
-        rc=L.db200_sw_batch_device(0,C.byref(prm_c),d_q.data_ptr(),d_qo.data_ptr(),qb,d_t.data_ptr(),d_to.data_ptr(),tb,n,int(q.lengths.max()),None,d_res.data_ptr(),d_cig.data_ptr(),cap,d_co.data_ptr(),d_st.data_ptr(),None,C.c_void_p(st.cuda_stream))
+        rc=L.db200_sw_batch_device(0,C.byref(prm_c),d_q.data_ptr(),d_qo.data_ptr(),qb,d_t.data_ptr(),d_to.data_ptr(),tb,n,int(q.lengths.max()),int(t.lengths.max()),None,d_res.data_ptr(),d_cig.data_ptr(),cap,d_co.data_ptr(),d_st.data_ptr(),None,C.c_void_p(st.cuda_stream))
         assert rc==0
     for _ in range(3): step()
     torch.cuda.synchronize()

@@ -58,6 +58,7 @@ def main():
     shapes.append(("4/5 long-read contigs 1-10 kb check_contig_match SSW (2,-3,10,1), cigar", "sw", q, t, p))
     for name, kind, q, t, p in shapes:
         c = cells(q, t)
+        q, t = batch.pinned_copy(q), batch.pinned_copy(t)
         if kind == "sw":
             dt, r = timed(lambda: batch.sw_align_batch(q, t, **p))
         else:
