@@ -37,6 +37,9 @@ UNIT = "GCUPS"
 SW_LANE_OPS_PER_CELL = 3.5
 # measured on this pool's B200s by dysgu_b200/int_peak (profiles/r01_int_peak.json): VIADDMNMX.S16x2 lane-ops/s
 INT_PEAK_FALLBACK = 1.81e13
+# DRAM bytes moved by the forward scoring launches per byte of ASCII input, from the ncu pass in
+# profiles/r01_forward_traffic.txt (563.3 MB for 833.6 MB of input at 524,288 pairs per step)
+FWD_TRAFFIC_PER_INPUT_BYTE = 563.3e6 / 833.55e6
 
 
 def load_measured_peaks():
@@ -316,7 +319,9 @@ def run_ours(args):
         "frac": (achieved / peak) if achieved else None, "peak_source": "measured: dysgu_b200/int_peak on this pool (profiles/r01_int_peak.json)",
         "ops_per_cell": SW_LANE_OPS_PER_CELL, "kernel_ms_per_step": fwd_ms, "kernel_gcups": cells / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None,
         "hbm_algorithmic_gbs": alg_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None, "hbm_peak_gbs": peaks["hbm_gbs"],
-        "hbm_peak_source": peaks["source"], "traffic": None,
+        "hbm_peak_source": peaks["source"],
+        "traffic": (q_bytes + t_bytes) * FWD_TRAFFIC_PER_INPUT_BYTE, "algorithmic_bytes": alg_bytes,
+        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the forward launches of one step (profiles/r01_forward_traffic.txt), scaled by input bytes",
         "stage_ms_per_step": {k: v / args.steps for k, v in zip(
             ["begin", "pack", "bucket", "forward", "forward_rerun", "reverse_prep", "reverse", "reverse_rerun", "finalize",
              "traceback", "cigar"], stage_ms[:11])},
@@ -375,7 +380,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 19, help="pairs per step per GPU")
-    ap.add_argument("--ref-pairs", type=int, default=40000, help="pairs per step of the CPU reference sample")
+    ap.add_argument("--ref-pairs", type=int, default=400000, help="pairs per step of the CPU reference sample (about 1.3 s on 16 cores)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
