@@ -260,6 +260,35 @@ __global__ void __launch_bounds__(128) sw_trace_narrow_kernel(TraceArgs a)
 // are the zeroed guard entries, which is exactly the reference's "cells outside the band read as 0".
 template <int T> __device__ __forceinline__ void coop_sync() { if (T == 32) __syncwarp(); else __syncthreads(); }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) global -> shared, completion on an mbarrier -------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(phase)
+                     : "memory");
+    } while (!done);
+}
+
 // T = 32: level 1 (one warp per pair, __syncwarp between anti-diagonals); T = 128: level 2 (one block per pair)
 template <int T, int LEVEL, int WMAX, int SEQW, int STAGEB>
 __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
@@ -268,8 +297,11 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
     __shared__ int16_t mat_s[36];
     __shared__ int sh_task, sh_best, sh_ncig;
     __shared__ unsigned long long sh_cpos;
+    __shared__ __align__(8) uint64_t tma_bar;   // completion barrier of the bulk copies below
+    uint32_t tma_phase = 0;
     int16_t *Hs = sm + 1, *Es = sm + (WMAX + 2) + 1, *Fs = sm + 2 * (WMAX + 2) + 1; // index -1 .. XW are valid
     for (int k = threadIdx.x; k < 36; k += T) mat_s[k] = a.sc.mat[k];
+    if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
     coop_sync<T>();
     // the slab area is divided among the blocks that can have work: few pairs -> few, large slabs
     const int nslabs = min((int)gridDim.x, max(*a.count[LEVEL], 1));
@@ -297,13 +329,19 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
         // stage the codes of both sub-sequences in shared memory (the large carve-out leaves little L1 for them)
         {
             uint32_t *seqs = reinterpret_cast<uint32_t *>(sm + 3 * (WMAX + 2));
-            const int qw0 = rbeg >> 3, qwn = ((rbeg + readLen - 1) >> 3) - qw0 + 1;
-            const int tw0 = tbeg >> 3, twn = ((tbeg + refLen - 1) >> 3) - tw0 + 1;
+            // 16-byte aligned word ranges covering the two sub-sequences (sequences start on 16-byte units)
+            const int qw0 = (rbeg >> 3) & ~3, qwn = ((((rbeg + readLen - 1) >> 3) - qw0 + 1) + 3) & ~3;
+            const int tw0 = (tbeg >> 3) & ~3, twn = ((((tbeg + refLen - 1) >> 3) - tw0 + 1) + 3) & ~3;
             if (SEQW > 0 && qwn + twn <= SEQW) {
-                coop_sync<T>();
-                for (int k = threadIdx.x; k < qwn; k += T) seqs[k] = qw[qw0 + k];
-                for (int k = threadIdx.x; k < twn; k += T) seqs[qwn + k] = tw[tw0 + k];
-                coop_sync<T>();
+                coop_sync<T>();   // everybody is done with the previous pair's codes
+                if (threadIdx.x == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&tma_bar, (uint32_t)(qwn + twn) * 4u);
+                    tma_bulk_g2s(seqs, qw + qw0, (uint32_t)qwn * 4u, &tma_bar);
+                    tma_bulk_g2s(seqs + qwn, tw + tw0, (uint32_t)twn * 4u, &tma_bar);
+                }
+                mbar_wait(&tma_bar, tma_phase);
+                tma_phase ^= 1u;
                 qw = seqs - qw0;           // same indexing as the global arrays
                 tw = seqs + qwn - tw0;
             }
@@ -399,11 +437,16 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
                 const int i_hi = w_i;
                 if (i_hi <= 0 || w_bad) break;
                 const int i_lo = max(1, i_hi - stage_rows + 1);
-                const uint4 *src = reinterpret_cast<const uint4 *>(slab + (unsigned long long)i_lo * (unsigned long long)wst);
-                uint4 *dst = reinterpret_cast<uint4 *>(stage);
-                const int n16 = (i_hi - i_lo + 1) * (wst >> 4);
-                for (int k = threadIdx.x; k < n16; k += T) dst[k] = src[k];
-                coop_sync<T>();
+                // one bulk copy (TMA) brings the rows of this chunk; the direction bytes were written with ordinary
+                // stores by this block, hence the proxy fence after the block-wide barrier
+                if (threadIdx.x == 0) {
+                    const uint32_t bytes = (uint32_t)(i_hi - i_lo + 1) * (uint32_t)wst;
+                    fence_proxy_async();
+                    mbar_expect_tx(&tma_bar, bytes);
+                    tma_bulk_g2s(stage, slab + (unsigned long long)i_lo * (unsigned long long)wst, bytes, &tma_bar);
+                }
+                mbar_wait(&tma_bar, tma_phase);
+                tma_phase ^= 1u;
                 if (threadIdx.x == 0) {
                     int i = w_i, j = w_j, run = w_run, prev = w_prev, op = w_op, state = w_state, l = w_l;
                     while (i >= i_lo) {

@@ -100,3 +100,24 @@ print("BAD", bad)
     env = dict(os.environ, DB200_TRACE_POOL_MB="16", DB200_TRACE_SLAB_MB="64")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert "BAD 0" in out.stdout, out.stdout[-500:] + out.stderr[-1500:]
+
+
+def test_column_tiled_pairs_with_tied_ends():
+    # targets of more than 2048 columns run the column-tiled kernel; low-complexity tails make several columns of
+    # one virtual lane reach the maximum, which exercises the single-pass re-run from the kept boundary columns
+    import random
+    rng = random.Random(2024)
+    qs, ts = [], []
+    for _ in range(160):
+        core = pairgen.rand_dna(rng, rng.randint(2080, 4300))
+        unit = rng.choice(["A", "AC", "T", "GT", "CAG"])
+        tail_q = (unit * 40)[:rng.randint(0, 30)]
+        tail_t = (unit * 40)[:rng.randint(0, 30)]
+        q = core + tail_q
+        t = pairgen.mutate(rng, core, 0.01, 0.004, 0.004) + tail_t
+        if rng.random() < 0.5:
+            q, t = t, q
+        qs.append(q.encode()); ts.append(t.encode())
+    res = batch.sw_align_batch(qs, ts, 2, -3, 10, 1)
+    ref = O.oracle_sw(qs, ts, 2, -3, 10, 1)
+    compare(qs, ts, res, ref, "tiled ties")
