@@ -93,18 +93,17 @@ Engine *get_engine(int device)
         delete e;
         return nullptr;
     }
-    for (int i = 0; i < Engine::NAUX; ++i) {
-        cudaStreamCreateWithFlags(&e->aux[i], cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
+    for (int k = 0; k < 2; ++k) {
+        for (int i = 0; i < Engine::NAUX; ++i) {
+            cudaStreamCreateWithFlags(&e->aux[k][i], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&e->ev_join[k][i], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&e->ev_fork[k], cudaEventDisableTiming);
     }
-    cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
     }
-    const char *mb = getenv("DB200_TRACE_POOL_MB");
-    e->trace_pool_bytes = (size_t)(mb ? atol(mb) : 1024) << 20;
-    if (e->trace_pool_bytes < ((size_t)16 << 20)) e->trace_pool_bytes = (size_t)16 << 20;
     const char *sb = getenv("DB200_TRACE_SLAB_MB");
     e->trace_slab_bytes = (size_t)(sb ? atol(sb) : 4096) << 20;
     if (e->trace_slab_bytes < ((size_t)64 << 20)) e->trace_slab_bytes = (size_t)64 << 20;
@@ -115,16 +114,18 @@ Engine *get_engine(int device)
 
 int aux_fork(Engine *e, cudaStream_t st)
 {
-    DB200_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
-    for (int i = 0; i < Engine::NAUX; ++i) DB200_CUDA_CHECK(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
+    const int k = e->aux_set;
+    DB200_CUDA_CHECK(cudaEventRecord(e->ev_fork[k], st));
+    for (int i = 0; i < Engine::NAUX; ++i) DB200_CUDA_CHECK(cudaStreamWaitEvent(e->aux[k][i], e->ev_fork[k], 0));
     return DB200_OK;
 }
 
 int aux_join(Engine *e, cudaStream_t st)
 {
+    const int k = e->aux_set;
     for (int i = 0; i < Engine::NAUX; ++i) {
-        DB200_CUDA_CHECK(cudaEventRecord(e->ev_join[i], e->aux[i]));
-        DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join[i], 0));
+        DB200_CUDA_CHECK(cudaEventRecord(e->ev_join[k][i], e->aux[k][i]));
+        DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join[k][i], 0));
     }
     return DB200_OK;
 }
@@ -323,6 +324,7 @@ int db200_sw_batch_device(int device, const db200_sw_params *params, const uint8
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
     e->arena[0].reset();
+    e->aux_set = 0;
     return sw_batch_device_impl(e, e->arena[0], params, d_qbuf, d_qoff, q_bytes, d_tbuf, d_toff, t_bytes, npairs, max_query_len,
                                 max_target_len, d_mask_len, d_results, d_cigar_buf, cigar_cap, d_cigar_off, d_status, cigar_total,
                                 (cudaStream_t)stream);
@@ -371,13 +373,25 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     if (cigar_off) cigar_off[0] = 0;
     cudaStream_t cs[2] = {e->stream, e->stream2}, cst = e->copy_stream;
     const int64_t MAX_CHUNK_BYTES = (int64_t)1 << 30;
-    int64_t chunk_pairs = npairs / 4;
+    // chunk sizes grow geometrically: a small first chunk keeps the exposed first copy short, later (larger) chunks
+    // run the kernels at better efficiency while their copy hides behind the previous chunk's compute
+    int64_t chunk_pairs = npairs / 16;
     if (chunk_pairs < 32768) chunk_pairs = 32768;
-    if (chunk_pairs > 131072) chunk_pairs = 131072;
-    if (const char *cp = getenv("DB200_HOST_CHUNK_PAIRS")) { const int64_t v = atoll(cp); if (v > 0) chunk_pairs = v; }
+    int64_t chunk_cap = 262144;
+    bool fixed_chunks = false;
+    if (const char *cp = getenv("DB200_HOST_CHUNK_PAIRS")) { const int64_t v = atoll(cp); if (v > 0) { chunk_pairs = v; fixed_chunks = true; } }
     int64_t cig_written = 0;
     SwSlot slots[2];
     int iter = 0;
+    // DB200_TIMELINE=1: print when each chunk's copy and compute started / ended on the device (diagnostics only)
+    static thread_local bool tl_inner = false;
+    const bool timeline = getenv("DB200_TIMELINE") != nullptr && !tl_inner;
+    struct TlRec { cudaEvent_t ev[4]; int64_t n; double host_ms; };
+    std::vector<TlRec> tl;
+    cudaEvent_t tl0 = nullptr;
+    auto host_now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double host0 = host_now();
+    if (timeline) { cudaEventCreate(&tl0); cudaEventRecord(tl0, cst); }
     for (int64_t c0 = 0; c0 < npairs; ++iter) {
         int64_t c1 = c0, bytes = 0;
         int32_t maxq = 0, maxt = 0;
@@ -424,6 +438,8 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
             set_error("sw_batch_host: device allocation failed");
             return DB200_ERR_NOMEM;
         }
+        TlRec rec{};
+        if (timeline) { for (auto &ev : rec.ev) cudaEventCreate(&ev); rec.n = n; cudaEventRecord(rec.ev[0], cst); }
         // H2D on the copy stream
         DB200_CUDA_CHECK(cudaMemcpyAsync(d_q, qbuf + qoff[c0], (size_t)qb, cudaMemcpyHostToDevice, cst));
         DB200_CUDA_CHECK(cudaMemcpyAsync(d_t, tbuf + toff[c0], (size_t)tb, cudaMemcpyHostToDevice, cst));
@@ -431,6 +447,8 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
         if (mask_len) DB200_CUDA_CHECK(cudaMemcpyAsync(d_mask, mask_len + c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, cst));
         DB200_CUDA_CHECK(cudaEventRecord(e->ev_copy[slot], cst));
         DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_copy[slot], 0));
+        if (timeline) { cudaEventRecord(rec.ev[1], cst); cudaEventRecord(rec.ev[2], st); }
+        e->aux_set = slot;
         rc = sw_batch_device_impl(e, e->arena[slot], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, maxt, d_mask, d_res, d_cig,
                                   cig_bound, d_coff, d_status, nullptr, st);
         if (rc) return rc;
@@ -439,8 +457,10 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
         if (cigar_off) DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_off + c0, d_coff, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
         DB200_CUDA_CHECK(cudaMemcpyAsync(total_word, d_coff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         DB200_CUDA_CHECK(cudaEventRecord(e->ev_done[slot], st));
+        if (timeline) { cudaEventRecord(rec.ev[3], st); rec.host_ms = host_now() - host0; tl.push_back(rec); }
         sl.c0 = c0; sl.n = n; sl.d_cig = d_cig; sl.cig_bound = cig_bound; sl.busy = true;
         c0 = c1;
+        if (!fixed_chunks) chunk_pairs = std::min<int64_t>(chunk_pairs * 2, chunk_cap);
     }
     // drain in submission order
     for (int k = 0; k < 2; ++k) {
@@ -450,6 +470,16 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     }
     DB200_CUDA_CHECK(cudaStreamSynchronize(cs[0]));
     DB200_CUDA_CHECK(cudaStreamSynchronize(cs[1]));
+    if (timeline) {
+        fprintf(stderr, "[db200] timeline (ms since call): host returned from sync at %.2f\n", host_now() - host0);
+        for (size_t i = 0; i < tl.size(); ++i) {
+            float t[4];
+            for (int k = 0; k < 4; ++k) { cudaEventElapsedTime(&t[k], tl0, tl[i].ev[k]); cudaEventDestroy(tl[i].ev[k]); }
+            fprintf(stderr, "[db200]   chunk %zu n=%lld  h2d %.2f-%.2f  compute %.2f-%.2f  enqueued by host at %.2f\n", i, (long long)tl[i].n,
+                    t[0], t[1], t[2], t[3], tl[i].host_ms);
+        }
+        cudaEventDestroy(tl0);
+    }
     if (cigar_off) cigar_off[npairs] = cig_written;
     // Pairs whose traceback did not fit the scratch pools of a large chunk are re-run in small groups (each group
     // then has the whole pool to itself); their cigars are appended and cigar_off is rebuilt in pair order.

@@ -49,10 +49,11 @@ struct Engine {
     cudaStream_t stream = nullptr;       // used by the *_host entry points
     cudaStream_t stream2 = nullptr;      // second compute stream: consecutive host chunks overlap their stage tails
     cudaStream_t copy_stream = nullptr;  // H2D prefetch of the next chunk
-    static constexpr int NAUX = 8;       // side streams: independent length buckets run concurrently so that the
-    cudaStream_t aux[NAUX] = {};         // drain phase of one bucket overlaps the bulk of the next
-    cudaEvent_t ev_fork = nullptr;
-    cudaEvent_t ev_join[NAUX] = {};
+    static constexpr int NAUX = 24;      // side streams: independent length buckets run concurrently so that the
+    cudaStream_t aux[2][NAUX] = {};      // drain phase of one bucket overlaps the bulk of the next; one set per
+    cudaEvent_t ev_fork[2] = {};         // in-flight host chunk so that two chunks can fill the GPU together
+    cudaEvent_t ev_join[2][NAUX] = {};
+    int aux_set = 0;                     // set used by the batch being enqueued
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
     Arena arena[2];                      // compute workspace (one per in-flight chunk)
@@ -63,14 +64,13 @@ struct Engine {
     size_t pinned_cap = 0;
     void *pinned_out[2] = {nullptr, nullptr};
     size_t pinned_out_cap[2] = {0, 0};
-    size_t trace_pool_bytes = (size_t)1 << 30;  // scratch of the scalar banded traceback (DB200_TRACE_POOL_MB)
     size_t trace_slab_bytes = (size_t)4 << 30;  // per-block slabs of the wide banded traceback (DB200_TRACE_SLAB_MB)
     // optional stage profiling (CUDA events recorded on the launching stream between pipeline stages)
     bool profiling = false;
     struct Mark { int stage; cudaEvent_t ev; };
     std::vector<Mark> marks;
     std::vector<cudaEvent_t> ev_pool;
-    size_t ev_used = 0;  // scratch of the banded traceback (DB200_TRACE_POOL_MB)
+    size_t ev_used = 0;
 };
 
 Engine *get_engine(int device);  // nullptr + error set on failure

@@ -128,31 +128,33 @@ __global__ void sw_init_kernel(InitArgs a, int32_t *hist)
 }
 
 // single block: exclusive scan of the bin histogram, segment ranges
-__global__ void sw_binscan_kernel(const int32_t *hist, int32_t *bin_start, int32_t *seg_begin, int32_t *seg_count)
+// one warp per segment: totals by warp reduction, bin starts by a warp scan over 32 bins at a time
+__global__ void __launch_bounds__(SW_NSEG * 32) sw_binscan_kernel(const int32_t *hist, int32_t *bin_start, int32_t *seg_begin, int32_t *seg_count)
 {
     __shared__ int32_t seg_tot[SW_NSEG];
     __shared__ int32_t seg_off[SW_NSEG + 1];
-    const int tid = threadIdx.x;
-    if (tid < SW_NSEG) {
-        int s = 0;
-        for (int b = 0; b < SW_LBINS; ++b) s += hist[tid * SW_LBINS + b];
-        seg_tot[tid] = s;
-    }
+    const int seg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int32_t *h = hist + seg * SW_LBINS;
+    int s = 0;
+    for (int b = lane; b < SW_LBINS; b += 32) s += h[b];
+    s = __reduce_add_sync(0xFFFFFFFFu, s);
+    if (lane == 0) seg_tot[seg] = s;
     __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         int acc = 0;
-        for (int s = 0; s < SW_NSEG; ++s) { seg_off[s] = acc; acc += seg_tot[s]; }
+        for (int k = 0; k < SW_NSEG; ++k) { seg_off[k] = acc; acc += seg_tot[k]; }
         seg_off[SW_NSEG] = acc;
     }
     __syncthreads();
-    if (tid < SW_NSEG) {
-        seg_begin[tid] = seg_off[tid];
-        seg_count[tid] = seg_tot[tid];
-        int acc = seg_off[tid];
-        for (int b = 0; b < SW_LBINS; ++b) {
-            bin_start[tid * SW_LBINS + b] = acc;
-            acc += hist[tid * SW_LBINS + b];
-        }
+    if (lane == 0) { seg_begin[seg] = seg_off[seg]; seg_count[seg] = seg_tot[seg]; }
+    int acc = seg_off[seg];
+    for (int b0 = 0; b0 < SW_LBINS; b0 += 32) {
+        const int v = h[b0 + lane];
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        bin_start[seg * SW_LBINS + b0 + lane] = acc + inc - v;
+        acc += __shfl_sync(0xFFFFFFFFu, inc, 31);
     }
 }
 
@@ -470,7 +472,6 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     const size_t nb = (size_t)SW_NSEG * SW_LBINS;
     const int bstride = ((max_query_len > 0 ? max_query_len : 0) + 63) & ~31;
     const size_t bwarps = (size_t)e->sm_count * SW_MULTI_MAX_WARPS_PER_SM;
-    const size_t trace_cap = e->trace_pool_bytes;
     const int64_t cig_pool_cap = cigar_cap > 0 ? cigar_cap : (q_bytes + t_bytes + 2 * npairs);
 
     int32_t *units = ws.alloc<int32_t>(nseq + 16);
@@ -501,7 +502,6 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     const size_t bnd_cap = (size_t)std::min<int64_t>(2 * (q_bytes + 32 * npairs) * max_extra_passes, (int64_t)1 << 30); // forward + reverse
     uint32_t *bnd_pool = ws.alloc<uint32_t>(bnd_cap + 64);
     long long *bnd_off = ws.alloc<long long>(2 * (size_t)npairs);
-    uint8_t *trace = ws.alloc<uint8_t>(trace_cap);
     const int wide_blocks = std::min(e->sm_count * 4, 1024);
     const size_t slab_bytes = (e->trace_slab_bytes / (size_t)wide_blocks) & ~(size_t)255;
     uint8_t *slab = ws.alloc<uint8_t>(slab_bytes * (size_t)wide_blocks);
@@ -509,7 +509,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     int32_t *medium_list = ws.alloc<int32_t>(npairs);
     int32_t *wide_list = ws.alloc<int32_t>(npairs);
     if (!units || !unit_off || !scan_tmp || !pool || !meta || !rmeta || !state || !fwd || !rev || !tasks_f || !tasks_r || !amb_f ||
-        !amb_r || !colmax_off || !cig_off_tmp || !lens || !colmax || !bins || !cigar_pool || !counters || !boundary || !trace || !slab ||
+        !amb_r || !colmax_off || !cig_off_tmp || !lens || !colmax || !bins || !cigar_pool || !counters || !boundary || !slab ||
         !bnd_pool || !bnd_off ||
         !narrow_list || !medium_list || !wide_list) {
         set_error("sw_batch: device workspace allocation failed");
@@ -525,7 +525,6 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     DB200_CUDA_CHECK(cudaMemsetAsync(bins, 0, (nb * 6 + 1024) * sizeof(int32_t), st));
     DB200_CUDA_CHECK(cudaMemsetAsync(counters, 0, 4096 * sizeof(int32_t), st));
     uint32_t *unit_cursor = reinterpret_cast<uint32_t *>(counters + 128);
-    unsigned long long *trace_cursor = reinterpret_cast<unsigned long long *>(counters + 130);
     unsigned long long *cigar_cursor = reinterpret_cast<unsigned long long *>(counters + 132);
     int32_t *overflow_flag = counters + 134;
 
@@ -546,7 +545,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     InitArgs ia;
     ia.meta = meta; ia.mask_len = d_mask_len; ia.state = state; ia.npairs = npairs; ia.max_match = max_match; ia.flag = prm->flag;
     sw_init_kernel<<<gpair, TB, 0, st>>>(ia, hist_f);
-    sw_binscan_kernel<<<1, 32, 0, st>>>(hist_f, start_f, seg_begin_f, seg_count_f);
+    sw_binscan_kernel<<<1, SW_NSEG * 32, 0, st>>>(hist_f, start_f, seg_begin_f, seg_count_f);
     sw_scatter_kernel<<<gpair, TB, 0, st>>>(meta, state, npairs, 0, start_f, fill_f, tasks_f);
     sw_colmax_len_kernel<<<gpair, TB, 0, st>>>(meta, state, npairs, lens);
     count_launch(e, 4);
@@ -574,7 +573,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     for (int seg = SW_NSEG - 1; seg >= 0; --seg) {   // widest buckets first: their drain overlaps the narrower ones
         const int cfg = seg >> 1, cmx = seg & 1;
         if (cfg == SW_NCFG - 1 && !can_multi) continue;
-        cudaStream_t ls = e->aux[(aux_i++) % Engine::NAUX];
+        cudaStream_t ls = e->aux[e->aux_set][(aux_i++) % Engine::NAUX];
         pa.meta = meta; pa.tasks = tasks_f; pa.seg_begin = seg_begin_f; pa.seg_count = seg_count_f; pa.seg = seg;
         pa.counter = counters + (counter_idx++);
         pa.out = fwd;
@@ -608,7 +607,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     ma.unit_cursor = unit_cursor; ma.unit_base = (uint32_t)seq_units;
     sw_mid_kernel<<<gpair, TB, 0, st>>>(ma, hist_r);
     sw_reverse_extract_kernel<<<gwarp_pair, TB, 0, st>>>(meta, rmeta, state, fwd, npairs, pool);
-    sw_binscan_kernel<<<1, 32, 0, st>>>(hist_r, start_r, seg_begin_r, seg_count_r);
+    sw_binscan_kernel<<<1, SW_NSEG * 32, 0, st>>>(hist_r, start_r, seg_begin_r, seg_count_r);
     sw_scatter_kernel<<<gpair, TB, 0, st>>>(rmeta, state, npairs, 1, start_r, fill_r, tasks_r);
     count_launch(e, 4);
     prof_mark(e, st, ST_REVERSE_PREP);
@@ -616,7 +615,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     { const int rc = aux_fork(e, st); if (rc) return rc; }
     for (int cfg = SW_NCFG - 1; cfg >= 0; --cfg) {
         if (cfg == SW_NCFG - 1 && !can_multi) continue;
-        cudaStream_t ls = e->aux[(aux_i++) % Engine::NAUX];
+        cudaStream_t ls = e->aux[e->aux_set][(aux_i++) % Engine::NAUX];
         pa.meta = rmeta; pa.tasks = tasks_r; pa.seg_begin = seg_begin_r; pa.seg_count = seg_count_r; pa.seg = 2 * cfg;
         pa.counter = counters + (counter_idx++);
         pa.out = rev;
@@ -649,7 +648,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     prof_mark(e, st, ST_FINALIZE);
     TraceArgs ta;
     ta.pool = reinterpret_cast<const uint4 *>(pool); ta.meta = meta; ta.state = state; ta.results = d_results; ta.npairs = npairs;
-    ta.sc = sc; ta.scratch = trace; ta.scratch_cursor = trace_cursor; ta.scratch_cap = trace_cap;
+    ta.sc = sc;
     ta.cigar_pool = cigar_pool; ta.cigar_cursor = cigar_cursor; ta.cigar_cap = (unsigned long long)cig_pool_cap;
     ta.overflow_flag = overflow_flag;
     ta.debug = getenv("DB200_DEBUG") ? 1 : 0;
@@ -659,7 +658,16 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     const int warp_blocks = e->sm_count * 24;
     ta.coop_blocks[0] = 0; ta.coop_blocks[1] = warp_blocks; ta.coop_blocks[2] = wide_blocks;
     sw_trace_classify_kernel<<<gpair, TB, 0, st>>>(ta);
-    sw_trace_narrow_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, st>>>(ta);
+    {
+        // level 0: one thread per pair, band rows and directions in a shared-memory slice
+        const size_t sm0 = (size_t)TRACE_NARROW_THREADS * TRACE_NARROW_WORDS * sizeof(uint32_t);
+        static bool attr0_done[16] = {false};
+        if (!attr0_done[e->device & 15]) {
+            DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_trace_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+            attr0_done[e->device & 15] = true;
+        }
+        sw_trace_narrow_kernel<<<(unsigned)((npairs + TRACE_NARROW_THREADS - 1) / TRACE_NARROW_THREADS), TRACE_NARROW_THREADS, sm0, st>>>(ta);
+    }
     {
         // level 1: one warp per pair (state for 2*62+1 diagonals, 8 KB of walk staging)
         constexpr int W1 = 254, S1 = 8192;

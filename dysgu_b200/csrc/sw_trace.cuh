@@ -19,9 +19,6 @@ struct TraceArgs {
     db200_sw_result *results;
     int64_t npairs;
     SwScoring sc;
-    uint8_t *scratch;              // narrow kernel: bump-allocated per attempt
-    unsigned long long *scratch_cursor;
-    unsigned long long scratch_cap;
     uint8_t *slab;                 // cooperative kernels: one slab per block (levels run one after the other)
     uint32_t *cigar_pool;
     unsigned long long *cigar_cursor;
@@ -39,11 +36,18 @@ struct TraceArgs {
 // level 0 (thread per pair) only takes tiny jobs: rows x band width below this many cells per attempt;
 // level 1 (warp per pair) takes bands of up to TRACE_WARP_BW columns either side; level 2 (block per pair) the rest
 constexpr int TRACE_NARROW_CELLS = 768;
+constexpr int TRACE_NARROW_WIDTH = 30;   // widest band row the scalar kernel keeps in its shared-memory slice
 constexpr int TRACE_WARP_BW = 62;
+// per-thread slice of the scalar kernel: direction nibbles of TRACE_NARROW_CELLS cells + four rolling int16 rows,
+// padded to an odd word count so that the 32 slices of a warp start in 32 different banks
+constexpr int TRACE_NARROW_DIR_WORDS = TRACE_NARROW_CELLS / 8;
+constexpr int TRACE_NARROW_ROW = TRACE_NARROW_WIDTH + 2;
+constexpr int TRACE_NARROW_WORDS = (TRACE_NARROW_DIR_WORDS + 4 * TRACE_NARROW_ROW / 2) | 1;
+constexpr int TRACE_NARROW_THREADS = 128;
 __device__ __forceinline__ int trace_level(int readLen, int refLen, int bw)
 {
     const int width = min(2 * bw + 1, refLen);
-    if ((long long)readLen * width <= TRACE_NARROW_CELLS) return 0;
+    if (width <= TRACE_NARROW_WIDTH && (long long)readLen * width <= TRACE_NARROW_CELLS) return 0;
     return bw <= TRACE_WARP_BW ? 1 : 2;
 }
 constexpr int TRACE_WMAX = 4094;       // wide kernel: band diagonals held in shared memory (3 x int16 each)
@@ -122,8 +126,9 @@ __device__ __forceinline__ int trace_step_code(int nib, int state)
     return (nib & 8) ? 5 : 4;
 }
 
-__global__ void __launch_bounds__(128) sw_trace_narrow_kernel(TraceArgs a)
+__global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(TraceArgs a)
 {
+    extern __shared__ uint32_t narrow_sm[];
     __shared__ int16_t mat_s[36];
     if (threadIdx.x < 36) mat_s[threadIdx.x] = a.sc.mat[threadIdx.x];
     __syncthreads();
@@ -139,7 +144,8 @@ __global__ void __launch_bounds__(128) sw_trace_narrow_kernel(TraceArgs a)
     const int rbeg = res.read_begin1, tbeg = res.ref_begin1; // local copies: the byte stores below may alias `res`
     const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
     int bw = abs(refLen - readLen) + 1;
-    uint8_t *dir = nullptr;
+    uint32_t *slice = narrow_sm + threadIdx.x * TRACE_NARROW_WORDS;
+    uint8_t *dir = reinterpret_cast<uint8_t *>(slice);
     int width = 0;
     while (true) {
         width = min(2 * bw + 1, refLen);
@@ -151,15 +157,9 @@ __global__ void __launch_bounds__(128) sw_trace_narrow_kernel(TraceArgs a)
                 return;
             }
         }
-        // scratch per attempt: direction nibbles + two rolling rows of (H, E), band-relative
-        const unsigned long long dir_bytes = ((((unsigned long long)readLen * (unsigned long long)width + 1) / 2) + 15) & ~15ull;
-        const unsigned long long row_bytes = (unsigned long long)(width + 2) * 4ull * sizeof(int32_t);
-        const unsigned long long need = dir_bytes + row_bytes;
-        const unsigned long long off = atomicAdd(a.scratch_cursor, need);
-        if (off + need > a.scratch_cap) { atomicExch(a.overflow_flag, 2); s.status = DB200_PAIR_NOSCRATCH; return; }
-        dir = a.scratch + off;
-        int32_t *Hp = reinterpret_cast<int32_t *>(a.scratch + off + dir_bytes);
-        int32_t *Ep = Hp + (width + 2), *Hc = Ep + (width + 2), *Ec = Hc + (width + 2);
+        // this attempt's direction nibbles and the two rolling rows of (H, E), band-relative, live in the thread's slice
+        int16_t *Hp = reinterpret_cast<int16_t *>(slice + TRACE_NARROW_DIR_WORDS);
+        int16_t *Ep = Hp + TRACE_NARROW_ROW, *Hc = Ep + TRACE_NARROW_ROW, *Ec = Hc + TRACE_NARROW_ROW;
         int best = 0;
         int pbeg = 0, pend = -1;
         for (int i = 0; i < readLen; ++i) {
@@ -192,10 +192,10 @@ __global__ void __launch_bounds__(128) sw_trace_narrow_kernel(TraceArgs a)
                 const unsigned long long cell = rowbase + (unsigned long long)(j - beg);
                 uint8_t &byte = dir[cell >> 1];
                 byte = (cell & 1) ? (uint8_t)((byte & 0x0F) | (nib << 4)) : (uint8_t)((byte & 0xF0) | nib);
-                Hc[j - beg] = h; Ec[j - beg] = e;
+                Hc[j - beg] = (int16_t)h; Ec[j - beg] = (int16_t)max(e, -32768);
                 hleft = h;
             }
-            int32_t *t = Hp; Hp = Hc; Hc = t;
+            int16_t *t = Hp; Hp = Hc; Hc = t;
             t = Ep; Ep = Ec; Ec = t;
             pbeg = beg; pend = end;
         }

@@ -26,3 +26,9 @@ if which in ("all","ed"):
     q,t,p = workloads.insertion_linking(20000, seed=3, platform="hifi")
     probe("ed hifi NW 20k", lambda: batch.ed_align_batch(q,t,**p))
     probe("ed hifi HW loc 20k", lambda: batch.ed_align_batch(q,t,mode="HW",task="locations"))
+if which in ("remap",):
+    import os
+    for n in (8192, 32768, 65536, 131072, 524288):
+        q,t,p = workloads.remap_windows(n, seed=1)
+        os.environ["DB200_HOST_CHUNK_PAIRS"] = str(1<<20)
+        probe("remap %d" % n, lambda: batch.sw_align_batch(q,t,**p))

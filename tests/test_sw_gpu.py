@@ -97,7 +97,7 @@ ref = O.oracle_sw(qs, ts, prm["match"], prm["mismatch"], prm["gap_open"], prm["g
 bad = sum(1 for i in range(len(qs)) if res.status[i] != 0 or res.as_tuple(i) != ref.as_tuple(i))
 print("BAD", bad)
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, DB200_TRACE_POOL_MB="16", DB200_TRACE_SLAB_MB="64")
+    env = dict(os.environ, DB200_TRACE_SLAB_MB="64")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert "BAD 0" in out.stdout, out.stdout[-500:] + out.stderr[-1500:]
 
