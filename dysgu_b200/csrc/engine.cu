@@ -87,20 +87,21 @@ Engine *get_engine(int device)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); delete e; return nullptr; }
     e->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete e;
         return nullptr;
     }
-    for (int k = 0; k < 2; ++k) {
+    e->slot_stream[0] = e->stream;
+    for (int k = 1; k < Engine::NSLOT; ++k) cudaStreamCreateWithFlags(&e->slot_stream[k], cudaStreamNonBlocking);
+    for (int k = 0; k < Engine::NSLOT; ++k) {
         for (int i = 0; i < Engine::NAUX; ++i) {
             cudaStreamCreateWithFlags(&e->aux[k][i], cudaStreamNonBlocking);
             cudaEventCreateWithFlags(&e->ev_join[k][i], cudaEventDisableTiming);
         }
         cudaEventCreateWithFlags(&e->ev_fork[k], cudaEventDisableTiming);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Engine::NSLOT; ++i) {
         cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
     }
@@ -241,10 +242,14 @@ void db200_shutdown(void)
         if (!e) continue;
         cudaSetDevice(e->device);
         cudaDeviceSynchronize();
-        for (int i = 0; i < 2; ++i) { e->arena[i].release(); e->io[i].release(); }
-        for (int i = 0; i < 2; ++i) if (e->pinned_out[i]) cudaFreeHost(e->pinned_out[i]);
+        for (int i = 0; i < Engine::NSLOT; ++i) { e->arena[i].release(); e->io[i].release(); }
+        for (int i = 0; i < Engine::NSLOT; ++i) if (e->pinned_out[i]) cudaFreeHost(e->pinned_out[i]);
         if (e->pinned) cudaFreeHost(e->pinned);
-        cudaStreamDestroy(e->stream);
+        for (int k = 0; k < Engine::NSLOT; ++k) {
+            for (int i = 0; i < Engine::NAUX; ++i) { cudaStreamDestroy(e->aux[k][i]); cudaEventDestroy(e->ev_join[k][i]); }
+            cudaEventDestroy(e->ev_fork[k]); cudaEventDestroy(e->ev_copy[k]); cudaEventDestroy(e->ev_done[k]);
+            cudaStreamDestroy(e->slot_stream[k]);   // [0] is e->stream
+        }
         cudaStreamDestroy(e->copy_stream);
         delete e;
         e = nullptr;
@@ -258,7 +263,9 @@ int64_t db200_workspace_bytes(int device)
 {
     Engine *e = get_engine(device);
     if (!e) return -1;
-    return (int64_t)(e->arena[0].total() + e->arena[1].total() + e->io[0].total() + e->io[1].total());
+    size_t total = 0;
+    for (int i = 0; i < Engine::NSLOT; ++i) total += e->arena[i].total() + e->io[i].total();
+    return (int64_t)total;
 }
 
 int64_t db200_kernel_launches(int device, int reset)
@@ -330,7 +337,7 @@ int db200_sw_batch_device(int device, const db200_sw_params *params, const uint8
                                 (cudaStream_t)stream);
 }
 
-// Host entry point.  The batch is cut into chunks that flow through a two-slot pipeline: while chunk i is being
+// Host entry point.  The batch is cut into chunks that flow through a pipeline of Engine::NSLOT slots: while chunk i is being
 // aligned on the compute stream, chunk i+1 is copied to the device on the copy stream (pinned host buffers make
 // the copies asynchronous).  Fixed-size results travel back right behind the kernels; the variable-size cigar
 // block of a chunk is fetched once its length is known, one chunk later, so the pipeline never drains.
@@ -371,17 +378,23 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     if (!e) return DB200_ERR_CUDA;
     if (npairs < 0 || !params || !qoff || !toff || !results) { set_error("sw_batch_host: bad arguments"); return DB200_ERR_ARG; }
     if (cigar_off) cigar_off[0] = 0;
-    cudaStream_t cs[2] = {e->stream, e->stream2}, cst = e->copy_stream;
+    constexpr int NS = Engine::NSLOT;
+    cudaStream_t *cs = e->slot_stream, cst = e->copy_stream;
     const int64_t MAX_CHUNK_BYTES = (int64_t)1 << 30;
-    // chunk sizes grow geometrically: a small first chunk keeps the exposed first copy short, later (larger) chunks
-    // run the kernels at better efficiency while their copy hides behind the previous chunk's compute
-    int64_t chunk_pairs = npairs / 16;
-    if (chunk_pairs < 32768) chunk_pairs = 32768;
-    int64_t chunk_cap = 262144;
+    // chunk sizes grow geometrically up to about a fifth of the batch: a small first chunk keeps the exposed first copy
+    // short, later (larger) chunks run the kernels at better efficiency while their copy hides behind earlier compute,
+    // and the last chunk - whose dependent stage tails nothing can hide - stays moderate
+    int64_t chunk_pairs = std::min<int64_t>(std::max<int64_t>(npairs / 16, 32768), 131072);
+    const int64_t chunk_cap = std::min<int64_t>(std::max<int64_t>(npairs / 5, 65536), 262144);
     bool fixed_chunks = false;
     if (const char *cp = getenv("DB200_HOST_CHUNK_PAIRS")) { const int64_t v = atoll(cp); if (v > 0) { chunk_pairs = v; fixed_chunks = true; } }
+    std::vector<int64_t> schedule;   // DB200_HOST_CHUNK_SCHEDULE=a,b,c: explicit chunk sizes (the last one repeats); tuning aid
+    if (const char *sp = getenv("DB200_HOST_CHUNK_SCHEDULE")) {
+        for (const char *q = sp; *q;) { char *end; const long long v = strtoll(q, &end, 10); if (end == q) break; if (v > 0) schedule.push_back(v); q = (*end == ',') ? end + 1 : end; }
+        if (!schedule.empty()) { fixed_chunks = true; chunk_pairs = schedule[0]; }
+    }
     int64_t cig_written = 0;
-    SwSlot slots[2];
+    SwSlot slots[NS];
     int iter = 0;
     // DB200_TIMELINE=1: print when each chunk's copy and compute started / ended on the device (diagnostics only)
     static thread_local bool tl_inner = false;
@@ -395,7 +408,9 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     for (int64_t c0 = 0; c0 < npairs; ++iter) {
         int64_t c1 = c0, bytes = 0;
         int32_t maxq = 0, maxt = 0;
-        while (c1 < npairs && c1 - c0 < chunk_pairs) {
+        int64_t want = chunk_pairs;
+        if (npairs - (c0 + want) < want / 2) want = npairs - c0;   // no tiny trailing chunk
+        while (c1 < npairs && c1 - c0 < want) {
             const int64_t ql = qoff[c1 + 1] - qoff[c1], tl = toff[c1 + 1] - toff[c1];
             if (ql < 0 || tl < 0 || ql > 0x7FFFFFF0 || tl > 0x7FFFFFF0) { set_error("sw_batch_host: bad offsets at pair %lld", (long long)c1); return DB200_ERR_ARG; }
             if (c1 > c0 && bytes + ql + tl > MAX_CHUNK_BYTES) break;
@@ -404,10 +419,10 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
             maxt = std::max<int32_t>(maxt, (int32_t)tl);
             ++c1;
         }
-        const int slot = iter & 1;
+        const int slot = iter % NS;
         cudaStream_t st = cs[slot];
         SwSlot &sl = slots[slot];
-        int rc = sw_finalize_slot(e, slot, sl, cigar_buf, cigar_cap, cigar_off, cig_written, st); // chunk iter-2
+        int rc = sw_finalize_slot(e, slot, sl, cigar_buf, cigar_cap, cigar_off, cig_written, st); // chunk iter-NS
         if (rc) return rc;
         const int64_t n = c1 - c0;
         const int64_t qb = qoff[c1] - qoff[c0], tb = toff[c1] - toff[c0];
@@ -461,15 +476,15 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
         sl.c0 = c0; sl.n = n; sl.d_cig = d_cig; sl.cig_bound = cig_bound; sl.busy = true;
         c0 = c1;
         if (!fixed_chunks) chunk_pairs = std::min<int64_t>(chunk_pairs * 2, chunk_cap);
+        if (!schedule.empty()) chunk_pairs = schedule[std::min<size_t>((size_t)iter + 1, schedule.size() - 1)];
     }
     // drain in submission order
-    for (int k = 0; k < 2; ++k) {
-        const int slot = (iter + k) & 1;
+    for (int k = 0; k < NS; ++k) {
+        const int slot = (iter + k) % NS;
         const int rc = sw_finalize_slot(e, slot, slots[slot], cigar_buf, cigar_cap, cigar_off, cig_written, cs[slot]);
         if (rc) return rc;
     }
-    DB200_CUDA_CHECK(cudaStreamSynchronize(cs[0]));
-    DB200_CUDA_CHECK(cudaStreamSynchronize(cs[1]));
+    for (int k = 0; k < NS; ++k) DB200_CUDA_CHECK(cudaStreamSynchronize(cs[k]));
     if (timeline) {
         fprintf(stderr, "[db200] timeline (ms since call): host returned from sync at %.2f\n", host_now() - host0);
         for (size_t i = 0; i < tl.size(); ++i) {

@@ -47,23 +47,24 @@ struct Engine {
     int device = -1;
     bool ready = false;
     cudaStream_t stream = nullptr;       // used by the *_host entry points
-    cudaStream_t stream2 = nullptr;      // second compute stream: consecutive host chunks overlap their stage tails
+    static constexpr int NSLOT = 3;      // host chunks in flight: copy of chunk i+2 / compute of chunk i+1 / drain of chunk i
+    cudaStream_t slot_stream[NSLOT] = {}; // compute stream per slot ([0] is `stream`): consecutive chunks overlap their stage tails
     cudaStream_t copy_stream = nullptr;  // H2D prefetch of the next chunk
     static constexpr int NAUX = 24;      // side streams: independent length buckets run concurrently so that the
-    cudaStream_t aux[2][NAUX] = {};      // drain phase of one bucket overlaps the bulk of the next; one set per
-    cudaEvent_t ev_fork[2] = {};         // in-flight host chunk so that two chunks can fill the GPU together
-    cudaEvent_t ev_join[2][NAUX] = {};
+    cudaStream_t aux[NSLOT][NAUX] = {};  // drain phase of one bucket overlaps the bulk of the next; one set per
+    cudaEvent_t ev_fork[NSLOT] = {};     // in-flight host chunk so that two chunks can fill the GPU together
+    cudaEvent_t ev_join[NSLOT][NAUX] = {};
     int aux_set = 0;                     // set used by the batch being enqueued
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
-    cudaEvent_t ev_done[2] = {nullptr, nullptr};
-    Arena arena[2];                      // compute workspace (one per in-flight chunk)
-    Arena io[2];                         // device copies of host inputs / outputs (one per in-flight chunk)
+    cudaEvent_t ev_copy[NSLOT] = {};
+    cudaEvent_t ev_done[NSLOT] = {};
+    Arena arena[NSLOT];                  // compute workspace (one per in-flight chunk)
+    Arena io[NSLOT];                     // device copies of host inputs / outputs (one per in-flight chunk)
     int64_t launches = 0;
     int sm_count = 0;
     void *pinned = nullptr;              // small pinned scratch (counters read back from the device)
     size_t pinned_cap = 0;
-    void *pinned_out[2] = {nullptr, nullptr};
-    size_t pinned_out_cap[2] = {0, 0};
+    void *pinned_out[NSLOT] = {};
+    size_t pinned_out_cap[NSLOT] = {};
     size_t trace_slab_bytes = (size_t)4 << 30;  // per-block slabs of the wide banded traceback (DB200_TRACE_SLAB_MB)
     // optional stage profiling (CUDA events recorded on the launching stream between pipeline stages)
     bool profiling = false;

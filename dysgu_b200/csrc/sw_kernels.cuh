@@ -130,8 +130,13 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
     if (MULTI) bnd = a.boundary + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)a.boundary_stride;
 
     while (true) {
+        // The warp must run every unit converged: ncu's source counters showed the first unit of each warp executing as
+        // two 16-thread fragments (every instruction issued twice) when the result store at the bottom of the loop
+        // was the last statement of the body; the explicit warp barriers here and there pin the reconvergence points.
+        __syncwarp();
         int base = 0;
         if (lane == 0) base = atomicAdd(a.counter, GROUPS);
+        __syncwarp();
         base = __shfl_sync(FULL, base, 0);
         if (base >= seg_count) break;
         const int ti = base + grp;
@@ -418,6 +423,7 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
                 }
             }
         }
+        __syncwarp();
     }
 }
 
