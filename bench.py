@@ -32,9 +32,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "alignment GCUPS (device-timed)"
 UNIT = "GCUPS"
-# lane-instructions of the minimal packed Smith-Waterman cell update: 7 s16x2 instructions per 2 cells
-# (U, H', H'-gapO, H, V, profile merge, running max) - see DESIGN.md "roofline"
-SW_LANE_OPS_PER_CELL = 3.5
+# ALU-pipe lane-instructions of the packed Smith-Waterman cell update: 6 s16x2 DPX instructions per 2 cells
+# (U, H', H'-gapO, H, V, tagged running max); the profile merge is an IMAD on the FMA pipe and is not counted
+# - see DESIGN.md "roofline"
+SW_LANE_OPS_PER_CELL = 3.0
 # measured on this pool's B200s by dysgu_b200/int_peak (profiles/r01_int_peak.json): VIADDMNMX.S16x2 lane-ops/s
 INT_PEAK_FALLBACK = 1.81e13
 # DRAM bytes moved by the forward scoring launches per byte of ASCII input, from the ncu pass in

@@ -87,8 +87,11 @@ __global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
     const int seg_begin = a.seg_begin[a.seg], seg_count = a.seg_count[a.seg];
 
     while (true) {
+        // explicit warp barriers at the loop edges keep every unit running converged (see sw_pass_kernel)
+        __syncwarp();
         int base = 0;
         if (lane == 0) base = atomicAdd(a.counter, GROUPS);
+        __syncwarp();
         base = __shfl_sync(FULL, base, 0);
         if (base >= seg_count) break;
         const int ti = base + grp;
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
             if (REV) a.loc_buf[2 * (int64_t)task] = end - rpos;
             else if (a.mode == DB200_ED_MODE_NW) a.nw_score[pair] = score;
         }
+        __syncwarp();
     }
 }
 
