@@ -104,6 +104,15 @@ Engine *get_engine(int device)
     for (int i = 0; i < Engine::NSLOT; ++i) {
         cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_sub_join[i], cudaEventDisableTiming);
+    }
+    for (int i = 0; i < Engine::NSUB_MAX; ++i) cudaEventCreateWithFlags(&e->ev_sub[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_sub_fork, cudaEventDisableTiming);
+    if (cudaMalloc(&e->d_sub_words, sizeof(int64_t) * (Engine::NSUB_MAX + 1)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc failed");
+        delete e;
+        return nullptr;
     }
     const char *sb = getenv("DB200_TRACE_SLAB_MB");
     e->trace_slab_bytes = (size_t)(sb ? atol(sb) : 4096) << 20;
@@ -248,9 +257,13 @@ void db200_shutdown(void)
         for (int k = 0; k < Engine::NSLOT; ++k) {
             for (int i = 0; i < Engine::NAUX; ++i) { cudaStreamDestroy(e->aux[k][i]); cudaEventDestroy(e->ev_join[k][i]); }
             cudaEventDestroy(e->ev_fork[k]); cudaEventDestroy(e->ev_copy[k]); cudaEventDestroy(e->ev_done[k]);
+            cudaEventDestroy(e->ev_sub_join[k]);
             cudaStreamDestroy(e->slot_stream[k]);   // [0] is e->stream
         }
         cudaStreamDestroy(e->copy_stream);
+        for (int i = 0; i < Engine::NSUB_MAX; ++i) cudaEventDestroy(e->ev_sub[i]);
+        cudaEventDestroy(e->ev_sub_fork);
+        cudaFree(e->d_sub_words);
         delete e;
         e = nullptr;
     }
@@ -330,11 +343,53 @@ int db200_sw_batch_device(int device, const db200_sw_params *params, const uint8
 {
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
-    e->arena[0].reset();
-    e->aux_set = 0;
-    return sw_batch_device_impl(e, e->arena[0], params, d_qbuf, d_qoff, q_bytes, d_tbuf, d_toff, t_bytes, npairs, max_query_len,
-                                max_target_len, d_mask_len, d_results, d_cigar_buf, cigar_cap, d_cigar_off, d_status, cigar_total,
-                                (cudaStream_t)stream);
+    cudaStream_t ust = (cudaStream_t)stream;
+    // DB200_DEVICE_SUBBATCHES=n cuts the batch into n sub-batches on the engine's slot streams (they share the caller's
+    // output arrays; only the placement of the cigars is ordered, SwLink).  Off by default: measured on B200 with the
+    // 524,288-pair step, 1 / 2 / 3 / 4 / 6 / 8 sub-batches take 22.1 / 22.9 / 23.4 / 23.9 / 25.2 / 27.6 ms - the stage
+    // tails that would overlap are shorter than the per-launch drain each extra set of 24 bucket kernels adds.
+    int nsub = 1;
+    if (const char *sp = getenv("DB200_DEVICE_SUBBATCHES")) nsub = atoi(sp);
+    nsub = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(nsub, Engine::NSUB_MAX), npairs / 4096));
+    if (nsub <= 1 || !d_qoff || !d_toff || !d_results) {
+        e->arena[0].reset();
+        e->aux_set = 0;
+        return sw_batch_device_impl(e, e->arena[0], params, d_qbuf, d_qoff, q_bytes, d_tbuf, d_toff, t_bytes, npairs, max_query_len,
+                                    max_target_len, d_mask_len, d_results, d_cigar_buf, cigar_cap, d_cigar_off, d_status, cigar_total, ust);
+    }
+    constexpr int NS = Engine::NSLOT;
+    DB200_CUDA_CHECK(cudaMemsetAsync(e->d_sub_words, 0, sizeof(int64_t), ust));
+    DB200_CUDA_CHECK(cudaEventRecord(e->ev_sub_fork, ust));
+    for (int k = 0; k < NS && k < nsub; ++k) DB200_CUDA_CHECK(cudaStreamWaitEvent(e->slot_stream[k], e->ev_sub_fork, 0));
+    for (int k = 0; k < NS; ++k) e->arena[k].reset();
+    for (int s = 0; s < nsub; ++s) {
+        const int64_t p0 = npairs * s / nsub, p1 = npairs * (s + 1) / nsub, n = p1 - p0;
+        const int slot = s % NS;
+        // the byte split is only known on the device: bound the slice by its pair count (sizes the workspace only)
+        const int64_t qb = max_query_len > 0 ? std::min<int64_t>(q_bytes, n * (int64_t)max_query_len) : q_bytes;
+        const int64_t tb = max_target_len > 0 ? std::min<int64_t>(t_bytes, n * (int64_t)max_target_len) : t_bytes;
+        SwLink link;
+        link.d_base = e->d_sub_words + s;
+        link.d_end = e->d_sub_words + s + 1;
+        link.wait = s > 0 ? e->ev_sub[s - 1] : nullptr;
+        link.done = e->ev_sub[s];
+        if (s >= NS) e->arena[slot].reset();   // stream order on the slot stream makes the reuse safe
+        e->aux_set = slot;
+        const int rc = sw_batch_device_impl(e, e->arena[slot], params, d_qbuf, d_qoff + p0, qb, d_tbuf, d_toff + p0, tb, n, max_query_len,
+                                            max_target_len, d_mask_len ? d_mask_len + p0 : nullptr, d_results + p0, d_cigar_buf, cigar_cap,
+                                            d_cigar_off ? d_cigar_off + p0 : nullptr, d_status ? d_status + p0 : nullptr, nullptr,
+                                            e->slot_stream[slot], &link);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < NS && k < nsub; ++k) {
+        DB200_CUDA_CHECK(cudaEventRecord(e->ev_sub_join[k], e->slot_stream[k]));
+        DB200_CUDA_CHECK(cudaStreamWaitEvent(ust, e->ev_sub_join[k], 0));
+    }
+    if (cigar_total) {
+        DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_total, e->d_sub_words + nsub, sizeof(int64_t), cudaMemcpyDeviceToHost, ust));
+        DB200_CUDA_CHECK(cudaStreamSynchronize(ust));
+    }
+    return DB200_OK;
 }
 
 // Host entry point.  The batch is cut into chunks that flow through a pipeline of Engine::NSLOT slots: while chunk i is being

@@ -55,6 +55,10 @@ struct Engine {
     cudaEvent_t ev_fork[NSLOT] = {};     // in-flight host chunk so that two chunks can fill the GPU together
     cudaEvent_t ev_join[NSLOT][NAUX] = {};
     int aux_set = 0;                     // set used by the batch being enqueued
+    static constexpr int NSUB_MAX = 16;  // sub-batches of one device call (db200_sw_batch_device)
+    cudaEvent_t ev_sub[NSUB_MAX] = {};   // cigar placement of sub-batch i done
+    cudaEvent_t ev_sub_fork = nullptr, ev_sub_join[NSLOT] = {};
+    int64_t *d_sub_words = nullptr;      // [NSUB_MAX + 1] cigar cursor between sub-batches
     cudaEvent_t ev_copy[NSLOT] = {};
     cudaEvent_t ev_done[NSLOT] = {};
     Arena arena[NSLOT];                  // compute workspace (one per in-flight chunk)
@@ -91,10 +95,19 @@ int aux_join(Engine *e, cudaStream_t st);
 void exclusive_scan_i32_i64(Engine *e, const int32_t *in, int64_t *out, int64_t n, int64_t *tmp, cudaStream_t st);
 inline size_t scan_tmp_count(int64_t n) { return (size_t)((n + 1023) / 1024 + 2); }
 
+// Chaining of the sub-batches of one device call: they run on different streams and share one cigar CSR, so the
+// only ordered step is the placement of the cigars (each sub-batch starts where its predecessor ended).
+struct SwLink {
+    const int64_t *d_base;   // device scalar: first cigar slot of this sub-batch (nullptr: 0)
+    int64_t *d_end;          // device scalar: receives d_base + the cigar ops of this sub-batch
+    cudaEvent_t wait;        // recorded by the predecessor after it wrote its d_end (nullptr: none)
+    cudaEvent_t done;        // recorded after d_end is written (nullptr: not needed)
+};
+
 int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff,
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
-                         int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st);
+                         int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st, const SwLink *link = nullptr);
 
 int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff,
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,

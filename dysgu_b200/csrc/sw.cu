@@ -52,9 +52,31 @@ __device__ __forceinline__ uint32_t nt_code(uint8_t ch)
     }
 }
 
-// one warp per sequence; each lane packs 8 bases into one 32-bit word per iteration
-__global__ void sw_pack_kernel(const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf, const int64_t *toff,
-                               int64_t npairs, const int64_t *unit_off, uint32_t *pool, PairMeta *meta)
+// Four ASCII bytes -> four code bytes (0..4), branch-free.  Folding bit 5 maps lower to upper case; the low three bits
+// of the five letters are distinct (A=1 C=3 G=7 T=4 U=5), so two byte permutes look up the letter each index stands
+// for and its code; a byte whose folded value differs from that letter is not a nucleotide and becomes 4 (N).
+__device__ __forceinline__ uint32_t nibbles_of_bytes(uint32_t v)   // four bytes (each < 16) -> 16 bits of nibbles
+{
+    v = (v | (v >> 4)) & 0x00FF00FFu;
+    return (v | (v >> 8)) & 0xFFFFu;
+}
+
+__device__ __forceinline__ uint32_t nt_codes4(uint32_t x)
+{
+    const uint32_t u = x & 0xDFDFDFDFu;
+    const uint32_t sel = nibbles_of_bytes(u & 0x07070707u);
+    const uint32_t expect = __byte_perm(0x43FF41FFu, 0x47FF5554u, sel);   // idx: -, A, -, C | T, U, -, G  (0xFF never matches: bit 5 set)
+    const uint32_t code = __byte_perm(0x01040004u, 0x02040003u, sel);     // idx: 4, 0, 4, 1 | 3, 0, 4, 2
+    const uint32_t y = expect ^ u;
+    const uint32_t nz = (((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u;   // high bit where the byte differs
+    const uint32_t bad = nz >> 7;                                         // 0x01 per non-nucleotide byte
+    return (code & ~(bad * 0xFFu)) | (bad << 2);
+}
+
+// one warp per sequence; each lane turns 8 bases into one 32-bit word per iteration.  The bytes arrive through two
+// aligned 64-bit loads and a funnel shift (sequences start at arbitrary byte offsets of the CSR buffer).
+__global__ void __launch_bounds__(256) sw_pack_kernel(const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf, const int64_t *toff,
+                                                      int64_t npairs, const int64_t *unit_off, uint32_t *pool, PairMeta *meta)
 {
     const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -66,14 +88,28 @@ __global__ void sw_pack_kernel(const uint8_t *qbuf, const int64_t *qoff, const u
     const int64_t len = off[p + 1] - off[p];
     const int64_t u0 = unit_off[wid];
     const int64_t nwords = ((len + 31) >> 5) << 2;
+    const int64_t fullw = (len + 7) >> 3;          // words holding at least one base
     uint32_t *dst = pool + u0 * 4;
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(src) & 7u);
+    const uint8_t *abase = src - mis;
+    const uint8_t *aend = src + len;               // first byte that must not be the start of an aligned load
+    const unsigned sh = mis * 8u;
     for (int64_t w = lane; w < nwords; w += 32) {
-        uint32_t x = 0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int64_t i = w * 8 + e;
-            const uint32_t c = i < len ? nt_code(src[i]) : (uint32_t)SW_PAD_CODE;
-            x |= c << (4 * e);
+        uint32_t x = 0x55555555u;                  // padding code in every nibble
+        if (w < fullw) {
+            const uint8_t *a = abase + w * 8;
+            const uint2 lo = *reinterpret_cast<const uint2 *>(a);
+            uint2 hi = make_uint2(0u, 0u);
+            if (mis != 0 && a + 8 < aend) hi = *reinterpret_cast<const uint2 *>(a + 8);
+            uint32_t b0, b1;
+            if (sh >= 32u) { b0 = __funnelshift_r(lo.y, hi.x, sh - 32u); b1 = __funnelshift_r(hi.x, hi.y, sh - 32u); }
+            else { b0 = __funnelshift_r(lo.x, lo.y, sh); b1 = __funnelshift_r(lo.y, hi.x, sh); }
+            x = nibbles_of_bytes(nt_codes4(b0)) | (nibbles_of_bytes(nt_codes4(b1)) << 16);
+            const int64_t rem = len - w * 8;       // bases in this word
+            if (rem < 8) {
+                const uint32_t keep = (1u << (4 * (int)rem)) - 1u;
+                x = (x & keep) | (0x55555555u & ~keep);
+            }
         }
         dst[w] = x;
     }
@@ -365,17 +401,27 @@ __global__ void sw_cigar_len_kernel(const PairState *state, int64_t npairs, int3
     lens[p] = state[p].cigar_len;
 }
 
+// `off` are the exclusive cigar offsets of this (sub-)batch.  A sub-batch of a larger device call is linked to its
+// predecessor: *base is the first cigar slot it may use (the predecessor's end), the rebased offsets go to out_off
+// and the sub-batch's own end to *end_word.
 __global__ void sw_cigar_gather_kernel(const PairState *state, int64_t npairs, const int64_t *off, const uint32_t *pool,
-                                       uint32_t *out, int64_t out_cap, int32_t *status_out, int32_t *overflow_flag)
+                                       uint32_t *out, int64_t out_cap, int32_t *status_out, int32_t *overflow_flag,
+                                       const int64_t *base, int64_t *out_off, int64_t *end_word)
 {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= npairs) return;
+    const int64_t b = base ? *base : 0;
+    if (out_off) {
+        out_off[p] = b + off[p];
+        if (p == npairs - 1) out_off[npairs] = b + off[npairs];
+    }
+    if (end_word && p == npairs - 1) *end_word = b + off[npairs];
     if (status_out) status_out[p] = state[p].status;
     const int len = state[p].cigar_len;
     if (len <= 0 || !out) return;
-    if (off[p] + len > out_cap) { atomicExch(overflow_flag, 3); return; }
+    if (b + off[p] + len > out_cap) { atomicExch(overflow_flag, 3); return; }
     const uint32_t *src = pool + state[p].cigar_pos;
-    uint32_t *dst = out + off[p];
+    uint32_t *dst = out + b + off[p];
     for (int i = 0; i < len; ++i) dst[i] = src[i];
 }
 
@@ -429,7 +475,8 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len, db200_sw_result *d_results,
                          uint32_t *d_cigar_buf,
-                         int64_t cigar_cap, int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st)
+                         int64_t cigar_cap, int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st,
+                         const SwLink *link)
 {
     if (npairs < 0 || !prm || !d_results) { set_error("sw_batch: bad arguments"); return DB200_ERR_ARG; }
     if (prm->gap_open <= 0 || prm->gap_extend <= 0 || prm->gap_open > 255 || prm->gap_extend > 255) {
@@ -687,14 +734,25 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     prof_mark(e, st, ST_TRACEBACK);
     sw_cigar_len_kernel<<<gpair, TB, 0, st>>>(state, npairs, lens);
     count_launch(e, 3);
-    int64_t *off_out = d_cigar_off ? d_cigar_off : cig_off_tmp;
-    exclusive_scan_i32_i64(e, lens, off_out, npairs, scan_tmp, st);
-    sw_cigar_gather_kernel<<<gpair, TB, 0, st>>>(state, npairs, off_out, cigar_pool, d_cigar_buf, cigar_cap, d_status, overflow_flag);
+    if (!link) {
+        int64_t *off_out = d_cigar_off ? d_cigar_off : cig_off_tmp;
+        exclusive_scan_i32_i64(e, lens, off_out, npairs, scan_tmp, st);
+        sw_cigar_gather_kernel<<<gpair, TB, 0, st>>>(state, npairs, off_out, cigar_pool, d_cigar_buf, cigar_cap, d_status, overflow_flag,
+                                                     nullptr, nullptr, nullptr);
+    } else {
+        // sub-batch of a larger call: local offsets, then wait for the predecessor's end before placing the cigars
+        exclusive_scan_i32_i64(e, lens, cig_off_tmp, npairs, scan_tmp, st);
+        if (link->wait) DB200_CUDA_CHECK(cudaStreamWaitEvent(st, link->wait, 0));
+        sw_cigar_gather_kernel<<<gpair, TB, 0, st>>>(state, npairs, cig_off_tmp, cigar_pool, d_cigar_buf, cigar_cap, d_status, overflow_flag,
+                                                     link->d_base, d_cigar_off, link->d_end);
+        if (link->done) DB200_CUDA_CHECK(cudaEventRecord(link->done, st));
+    }
     count_launch(e);
     prof_mark(e, st, ST_CIGAR);
     DB200_CUDA_CHECK(cudaGetLastError());
     if (cigar_total) {
-        DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_total, off_out + npairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        const int64_t *total_src = link ? link->d_end : (d_cigar_off ? d_cigar_off : cig_off_tmp) + npairs;
+        DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_total, total_src, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         DB200_CUDA_CHECK(cudaStreamSynchronize(st));
     }
     return DB200_OK;
