@@ -755,6 +755,30 @@ db200_EdlibAlignConfig db200_edlibNewAlignConfig(int k, int mode, int task, cons
     return c;
 }
 
+// edlibAlignmentToCigar (edlib.h:257-271, edlib.cpp:298-347): run-length text of an edit-operation array
+// (0 match, 1 insertion, 2 deletion, 3 mismatch); format 0 = standard (M/I/D), 1 = extended (=/I/D/X).
+// Host-only formatting; the caller frees the string.  NULL for an unknown format or an operation > 3.
+char *db200_edlibAlignmentToCigar(const unsigned char *alignment, int alignmentLength, int cigarFormat)
+{
+    if (cigarFormat != 0 && cigarFormat != 1) return nullptr;
+    if (alignmentLength < 0 || (alignmentLength > 0 && !alignment)) return nullptr;
+    const char *letters = cigarFormat == 0 ? "MIDM" : "=IDX";
+    std::string out;
+    for (int i = 0; i < alignmentLength;) {
+        if (alignment[i] > 3) return nullptr;
+        const char c = letters[alignment[i]];
+        int j = i;
+        while (j < alignmentLength && alignment[j] <= 3 && letters[alignment[j]] == c) ++j;
+        out += std::to_string(j - i);
+        out += c;
+        i = j;
+    }
+    char *r = (char *)malloc(out.size() + 1);
+    if (!r) return nullptr;
+    memcpy(r, out.c_str(), out.size() + 1);
+    return r;
+}
+
 db200_EdlibAlignConfig db200_edlibDefaultAlignConfig(void) { return db200_edlibNewAlignConfig(-1, DB200_ED_MODE_NW, DB200_ED_TASK_DISTANCE, nullptr, 0); }
 
 db200_EdlibAlignResult db200_edlibAlign(const char *query, int queryLength, const char *target, int targetLength,

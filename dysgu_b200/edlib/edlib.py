@@ -4,6 +4,7 @@ from __future__ import annotations
 import re
 
 from .. import batch as _batch
+from .. import queue as _queue
 
 
 def _to_bytes(query, target, additional_equalities):
@@ -43,6 +44,9 @@ def align(query, target, mode="NW", task="distance", k=-1, additionalEqualities=
     if eqs is not None:
         eqs = [((a.encode("utf-8")[0] if isinstance(a, str) else int(a)), (b.encode("utf-8")[0] if isinstance(b, str) else int(b)))
                for a, b in eqs]
+    q = _queue.active_queue()
+    if q is not None:   # deferred mode (dysgu_b200.deferred()): submit now, resolve on first use
+        return _queue.LazyEdlibResult(q, q.submit_ed(qb, tb, mode=mode, task=task, k=-1 if k is None else k, additional_equalities=eqs))
     res = _batch.ed_align_batch([qb], [tb], mode=mode, task=task, k=-1 if k is None else k, additional_equalities=eqs)
     d = res.as_dict(0)
     if d["status"] == 1:

@@ -10,6 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import batch as _batch
+from .. import queue as _queue
 
 _NT_ORDER = "ACGTN"
 
@@ -127,6 +128,32 @@ class AlignmentStructure:
         return [(int(c) >> 4, "MID"[int(c) & 0xF]) for c in self._cigar_ops]
 
 
+class LazyAlignmentStructure(AlignmentStructure):
+    """AlignmentStructure of a pair submitted in deferred mode (dysgu_b200.deferred()): the integer fields and the
+    cigar are fetched from the queue on first use; everything else is the parent class."""
+
+    _LAZY = ("_score1", "_score2", "_ref_begin1", "_ref_end1", "_read_begin1", "_read_end1", "_ref_end2", "_cigar_ops")
+
+    def __init__(self, queue, ticket, read_sequence, reference_sequence, index_starts_at):
+        self._queue, self._ticket = queue, ticket
+        self.read_sequence = read_sequence
+        self.reference_sequence = reference_sequence
+        self.index_starts_at = index_starts_at
+        self._cigar_string = None
+
+    def __getattr__(self, name):   # only reached while the lazy fields are still missing
+        if name in LazyAlignmentStructure._LAZY:
+            fields, ops, status = self._queue.fetch_sw(self._ticket)
+            if status != 0:
+                raise RuntimeError("alignment failed: %s" % _batch.PAIR_STATUS.get(status, status))
+            (self._score1, self._score2, self._ref_begin1, self._ref_end1, self._read_begin1, self._read_end1,
+             self._ref_end2) = (int(x) for x in fields[:7])
+            self._cigar_ops = ops
+            self._queue = None
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+
 class StripedSmithWaterman:
     """Same constructor and call surface as the reference class (_ssw_wrapper.pyx:397-709)."""
 
@@ -207,7 +234,20 @@ class StripedSmithWaterman:
         return out
 
     def __call__(self, target_sequence):
-        return self._run([target_sequence])[0]
+        q = _queue.active_queue()
+        if q is None:
+            return self._run([target_sequence])[0]
+        # deferred mode: submit now, resolve on first use
+        for ch in target_sequence:
+            if ord(ch) > 127:
+                raise IndexError("index %d is out of bounds for axis 0 with size 128" % ord(ch))
+        ticket = q.submit_sw(self._query_bytes, target_sequence.encode("ascii"), match=self.match_score, mismatch=self.mismatch_score,
+                             gap_open=self.gap_open_penalty, gap_extend=self.gap_extend_penalty, score_size=self.score_size,
+                             flag=self.bit_flag, filters=self.score_filter, filterd=self.distance_filter, mask_len=self.mask_length,
+                             matrix=self.matrix)
+        if self.suppress_sequences:
+            return LazyAlignmentStructure(q, ticket, "", "", self.index_starts_at)
+        return LazyAlignmentStructure(q, ticket, self.read_sequence, target_sequence, self.index_starts_at)
 
     def align_many(self, target_sequences):
         """One profile, many targets in a single device batch (e.g. clip and revcomp(clip), post_call.py:53-76)."""

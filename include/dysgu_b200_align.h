@@ -226,6 +226,37 @@ db200_EdlibAlignConfig db200_edlibDefaultAlignConfig(void);
 db200_EdlibAlignResult db200_edlibAlign(const char *query, int queryLength, const char *target, int targetLength,
                                         const db200_EdlibAlignConfig config);
 void db200_edlibFreeAlignResult(db200_EdlibAlignResult result);
+/* edlibAlignmentToCigar (edlib.h:257-271, edlib.cpp:298-347): 0 = EDLIB_CIGAR_STANDARD, 1 = EDLIB_CIGAR_EXTENDED.
+ * Host-side formatting of an edit-operation array; the caller frees the returned string. */
+char *db200_edlibAlignmentToCigar(const unsigned char *alignment, int alignmentLength, int cigarFormat);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Ticket queue: submit / flush / fetch (SURVEY 8b "new batched ABI").                          */
+/* The reference's call sites are synchronous per pair - StripedSmithWaterman(q)(t)             */
+/* (_ssw_wrapper.pyx:613-652) and edlib.align (edlib.pyx:57-156).  A caller that collects its   */
+/* candidates first submits them here; pairs with identical parameters form one device batch.   */
+/* fetch flushes implicitly when its ticket is still pending, so submit + fetch of one pair     */
+/* behaves like the legacy call.  Sequences are copied at submit time.  Pointers returned by    */
+/* fetch stay valid until the next flush, reset or destroy.  Not thread-safe: one queue per      */
+/* thread.                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct db200_queue db200_queue;
+db200_queue *db200_queue_create(int device);      /* NULL without a CUDA device */
+void db200_queue_destroy(db200_queue *q);
+/* mask_len < 0: the wrapper's automatic rule max(len(query)/2, 15).  Returns a ticket >= 0 or DB200_ERR_*. */
+int64_t db200_queue_submit_sw(db200_queue *q, const db200_sw_params *params, const uint8_t *query, int32_t qlen,
+                              const uint8_t *target, int32_t tlen, int32_t mask_len);
+/* params->k applies to this pair. */
+int64_t db200_queue_submit_ed(db200_queue *q, const db200_ed_params *params, const uint8_t *query, int32_t qlen,
+                              const uint8_t *target, int32_t tlen);
+int64_t db200_queue_pending(const db200_queue *q);
+int db200_queue_flush(db200_queue *q);
+/* cigar: result->cigar_len BAM-encoded ops (NULL if none); status: DB200_PAIR_* */
+int db200_queue_fetch_sw(db200_queue *q, int64_t ticket, db200_sw_result *result, const uint32_t **cigar, int32_t *status);
+/* locations: result->num_locations (start, end) int32 pairs (NULL if none) */
+int db200_queue_fetch_ed(db200_queue *q, int64_t ticket, db200_ed_result *result, const int32_t **locations);
+/* Forget every ticket and result (pending pairs are dropped). */
+int db200_queue_reset(db200_queue *q);
 
 #ifdef __cplusplus
 }

@@ -47,3 +47,40 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.SwParams) == 48
     assert C.sizeof(_lib.EdParams) == 32
     assert batch.SW_FIELDS == ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len")
+
+
+def test_alignment_to_cigar_is_host_side_formatting():
+    # edlibAlignmentToCigar (edlib.cpp:298-347): run-length text; standard folds match and mismatch into M
+    L = _lib.lib()
+    L.db200_edlibAlignmentToCigar.restype = C.c_void_p
+    L.db200_edlibAlignmentToCigar.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+
+    def cigar(ops, fmt):
+        p = L.db200_edlibAlignmentToCigar(bytes(ops), len(ops), fmt)
+        if not p:
+            return None
+        s = C.string_at(p).decode()
+        libc.free(p)
+        return s
+
+    ops = [0, 0, 0, 0, 3, 0, 0, 0]                       # the SURVEY 8c vector: "4=1X3="
+    assert cigar(ops, 1) == "4=1X3="
+    assert cigar(ops, 0) == "8M"
+    assert cigar([1, 1, 0, 3, 3, 2, 2, 2, 0], 1) == "2I1=2X3D1="
+    assert cigar([1, 1, 0, 3, 3, 2, 2, 2, 0], 0) == "2I3M3D1M"
+    assert cigar([0] * 1234, 1) == "1234="
+    assert cigar([], 1) == ""
+    assert cigar([0, 4], 1) is None and cigar([0], 2) is None
+
+
+@pytest.mark.skipif(_lib.device_count() > 0, reason="a GPU is present")
+def test_queue_needs_a_device():
+    from dysgu_b200.queue import AlignQueue
+    with pytest.raises(_lib.AlignEngineError, match="no CUDA device"):
+        AlignQueue(0)
+    import dysgu_b200
+    with pytest.raises(_lib.AlignEngineError):
+        with dysgu_b200.deferred():
+            pass
