@@ -9,6 +9,14 @@ StripedSmithWaterman(query = 1000/1500/2000 bp reference window, 2,-8,6,1)(targe
 score + begin/end coordinates + cigar for every pair (flag = 1, what dysgu's wrapper always passes).
 One step = one pass of the whole pipeline over one batch of pairs (per GPU).
 
+Other BASELINE.json shapes run through the same code with --workload (parity-test shapes, reported in
+profiles/; the driver's bench line is the default workload):
+    pe_contigs     SSW (2,-3,10,1) paired-end contigs 100-500 bp           consensus.pyx:977-1018
+    long_contigs   SSW (2,-3,10,1) long-read contigs 1-10 kb (configs 4/5) merge_svs.pyx:355-382
+    remap_chain    edlib HW/locations clip vs 1000 bp window (config 2a)   re_map.py:209
+    hifi_nw/ont_nw edlib NW/distance insertion sequences 50 bp-10 kb (configs 3/4)
+    hifi_hw        edlib HW/locations on the same sequences
+
 Metric: alignment GCUPS = sum(len(query) * len(target)) / time, forward matrix counted once.
   value : device-timed (CUDA events on the launching stream), inputs resident in HBM
   e2e   : the same metric through the host C-ABI call (db200_sw_batch_host) with pinned host buffers,
@@ -122,11 +130,41 @@ def pinned_array(L, shape, dtype):
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
-def make_workload(pairs: int, seed: int):
+# Myers block step = 22 64-bit operations per 64-cell word step = 44 int32-equivalent lane-ops
+ED_LANE_OPS_PER_WORD_STEP = 44.0
+
+# name -> (kind, generator, default pairs per step per GPU, CPU reference sample, description)
+WORKLOADS = {
+    "remap_windows": ("sw", lambda W, n, s: W.remap_windows(n, seed=s), 1 << 19, 400000,
+                      "remap_windows: SSW(window 1000/1500/2000 bp; 2,-8,6,1)(soft clip 15-300 bp), score+coords+cigar"),
+    "pe_contigs": ("sw", lambda W, n, s: W.pe_contig_pairs(n, seed=s), 1 << 18, 100000,
+                   "pe_contigs: check_contig_match SSW (2,-3,10,1), paired-end contigs 100-500 bp, score+coords+cigar"),
+    "long_contigs": ("sw", lambda W, n, s: W.contig_pairs(n, seed=s, platform="ont"), 1 << 14, 1600,
+                     "long_contigs: check_contig_match SSW (2,-3,10,1), long-read contigs 1-10 kb (ONT error), score+coords+cigar"),
+    "remap_chain": ("ed", lambda W, n, s: W.remap_chain(n, seed=s), 1 << 19, 200000,
+                    "remap_chain: edlib HW/locations, clip 15-300 bp vs 1000 bp window"),
+    "hifi_nw": ("ed", lambda W, n, s: W.insertion_linking(n, seed=s, platform="hifi"), 200000, 20000,
+                "hifi_nw: edlib NW/distance k=-1, insertion sequences 50 bp-10 kb, HiFi error, 20 % unrelated"),
+    "ont_nw": ("ed", lambda W, n, s: W.insertion_linking(n, seed=s, platform="ont"), 200000, 20000,
+               "ont_nw: edlib NW/distance k=-1, insertion sequences 50 bp-10 kb, ONT r10 error, 20 % unrelated"),
+    "hifi_hw": ("ed", lambda W, n, s: W.insertion_linking(n, seed=s, platform="hifi")[:2] + (dict(mode="HW", task="locations"),), 20000, 2000,
+                "hifi_hw: edlib HW/locations, insertion sequences 50 bp-10 kb, HiFi error, 20 % unrelated"),
+}
+
+
+def make_workload(pairs: int, seed: int, name: str = "remap_windows"):
     from dysgu_b200 import workloads
-    q, t, prm = workloads.remap_windows(pairs, seed=seed)
+    q, t, prm = WORKLOADS[name][1](workloads, pairs, seed)
     cells = float((q.lengths.astype(np.float64) * t.lengths.astype(np.float64)).sum())
     return q, t, prm, cells
+
+
+def cpu_reference(O, name, q, t, prm, cores):
+    """The reference's compiled cores (oracle/_ref) over a CSR batch on `cores` host threads -> result with .seconds / .fixed"""
+    if WORKLOADS[name][0] == "sw":
+        return O.ref_sw((q.buf, q.off), (t.buf, t.off), prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"],
+                        nthreads=cores, csr=True)
+    return O.ref_ed((q.buf, q.off), (t.buf, t.off), prm["mode"], prm["task"], nthreads=cores, csr=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -143,13 +181,12 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not loadable: %s" % str(exc)[:120]}))
         return 0
     cores = os.cpu_count() or 1
-    sample = args.ref_pairs
-    q, t, prm, cells = make_workload(sample, seed=20261021)
-    qcsr, tcsr = (q.buf, q.off), (t.buf, t.off)
+    kind = WORKLOADS[args.workload][0]
+    sample = args.ref_pairs or WORKLOADS[args.workload][3]
+    q, t, prm, cells = make_workload(sample, 20261021, args.workload)
 
     def step():
-        r = O.ref_sw(qcsr, tcsr, prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"], nthreads=cores, csr=True)
-        return r.seconds
+        return cpu_reference(O, args.workload, q, t, prm, cores).seconds
 
     for _ in range(args.warmup):
         step()
@@ -162,11 +199,11 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * inner / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": "remap_windows: SSW(window 1000/1500/2000 bp; 2,-8,6,1)(soft clip 15-300 bp), score+coords+cigar",
-                   "pairs_per_step": sample, "cells_per_step": cells},
+        "vs_baseline": None, "dtype": "int16" if kind == "sw" else "u64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][4], "pairs_per_step": sample, "cells_per_step": cells},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": "%d pairs per step of the same workload, ssw_init+ssw_align per pair (C level, ssw.c compiled -O2)" % sample},
+                         "sample": "%d pairs per step of the same workload, %s per pair at C level" % (
+                             sample, "ssw_init+ssw_align (ssw.c -O2)" if kind == "sw" else "edlibAlign (edlib.cpp -O3)")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
@@ -178,6 +215,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     from dysgu_b200 import _lib
+    from dysgu_b200 import batch as B
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,36 +231,51 @@ def run_ours(args):
         dist.init_process_group(backend="nccl", device_id=dev)
     L = _lib.lib()
     _lib.check(L.db200_init(local_rank), "db200_init")
+    name = args.workload
+    kind = WORKLOADS[name][0]
 
     # ---- per-rank shard of the workload (pairs are independent: weak scaling, no collective on the data path)
-    pairs = args.pairs
-    q, t, prm, cells = make_workload(pairs, seed=20261021 + rank)
+    pairs = args.pairs or WORKLOADS[name][2]
+    q, t, prm, cells = make_workload(pairs, 20261021 + rank, name)
     n = len(q)
     q_bytes, t_bytes = int(q.off[-1]), int(t.off[-1])
     max_q = int(q.lengths.max())
     max_t = int(t.lengths.max())
 
-    prm_c = _lib.SwParams()
-    prm_c.match, prm_c.mismatch, prm_c.gap_open, prm_c.gap_extend = prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"]
-    prm_c.score_size, prm_c.flag = 2, 1
+    if kind == "sw":
+        prm_c = _lib.SwParams()
+        prm_c.match, prm_c.mismatch, prm_c.gap_open, prm_c.gap_extend = prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"]
+        prm_c.score_size, prm_c.flag = 2, 1
+        var_cap = int(4 * n + 1024) if name == "remap_windows" else int(q_bytes + t_bytes + 2 * n + 16)   # cigar words
+        var_dtype, var_np, res_cols = torch.int32, np.uint32, 8
+    else:
+        prm_c = _lib.EdParams()
+        prm_c.mode, prm_c.task, prm_c.k = B.ED_MODES[prm["mode"]], B.ED_TASKS[prm["task"]], -1
+        var_cap = int(t_bytes + 2 * n + 16) if prm["mode"] != "NW" else int(n + 16)                                       # locations
+        var_dtype, var_np, res_cols = torch.int32, np.int32, 4
+    var_words = var_cap * (1 if kind == "sw" else 2)
 
     # ---- device-resident arm --------------------------------------------------------------------------
     d_q = torch.from_numpy(q.buf).to(dev)
     d_t = torch.from_numpy(t.buf).to(dev)
     d_qoff = torch.from_numpy(q.off).to(dev)
     d_toff = torch.from_numpy(t.off).to(dev)
-    cig_cap = int(4 * n + 1024)
-    d_res = torch.zeros((n, 8), dtype=torch.int32, device=dev)
-    d_cig = torch.zeros(cig_cap, dtype=torch.int32, device=dev)
-    d_coff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_res = torch.zeros((n, res_cols), dtype=torch.int32, device=dev)
+    d_var = torch.zeros(var_words, dtype=var_dtype, device=dev)
+    d_voff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     d_status = torch.zeros(n, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def device_step():
-        rc = L.db200_sw_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
-                                     d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_cig.data_ptr(), cig_cap,
-                                     d_coff.data_ptr(), d_status.data_ptr(), None, C.c_void_p(stream.cuda_stream))
-        _lib.check(rc, "db200_sw_batch_device")
+        if kind == "sw":
+            rc = L.db200_sw_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
+                                         d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_var.data_ptr(), var_cap,
+                                         d_voff.data_ptr(), d_status.data_ptr(), None, C.c_void_p(stream.cuda_stream))
+        else:
+            rc = L.db200_ed_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
+                                         d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_var.data_ptr(), var_cap,
+                                         d_voff.data_ptr(), None, C.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "db200_%s_batch_device" % kind)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -233,13 +286,14 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         device_step()
     barrier()
-    bad = int((d_status != 0).sum().item())
+    bad = int((d_status != 0).sum().item()) if kind == "sw" else int((d_res[:, 0] != 0).sum().item())
     if bad:
         raise SystemExit("bench.py: %d pairs reported a non-zero status" % bad)
-    checksum = int(d_res[:, 0].sum().item())
+    checksum = int(d_res[:, 0 if kind == "sw" else 1].sum().item())
 
     L.db200_profile_enable(local_rank, 1)
     L.db200_kernel_launches(local_rank, 1)
+    L.db200_ed_word_steps(local_rank, 1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -253,6 +307,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = int(L.db200_kernel_launches(local_rank, 1))
+    word_steps = int(L.db200_ed_word_steps(local_rank, 1)) / args.steps
     stage_ms = (C.c_float * 16)()
     L.db200_profile_collect(local_rank, stage_ms, 16)
     L.db200_profile_enable(local_rank, 0)
@@ -273,15 +328,19 @@ def run_ours(args):
     ht = pinned_array(L, (t_bytes,), np.uint8); ht[:] = t.buf
     hqo = pinned_array(L, (n + 1,), np.int64); hqo[:] = q.off
     hto = pinned_array(L, (n + 1,), np.int64); hto[:] = t.off
-    hres = pinned_array(L, (n, 8), np.int32)
-    hcig = pinned_array(L, (cig_cap,), np.uint32)
-    hcoff = pinned_array(L, (n + 1,), np.int64)
+    hres = pinned_array(L, (n, res_cols), np.int32)
+    hvar = pinned_array(L, (var_words,), var_np)
+    hvoff = pinned_array(L, (n + 1,), np.int64)
     hstat = pinned_array(L, (n,), np.int32)
 
     def host_step():
-        rc = L.db200_sw_batch_host(local_rank, C.byref(prm_c), hq.ctypes.data, hqo.ctypes.data, ht.ctypes.data, hto.ctypes.data, n,
-                                   None, hres.ctypes.data, hcig.ctypes.data, cig_cap, hcoff.ctypes.data, hstat.ctypes.data)
-        _lib.check(rc, "db200_sw_batch_host")
+        if kind == "sw":
+            rc = L.db200_sw_batch_host(local_rank, C.byref(prm_c), hq.ctypes.data, hqo.ctypes.data, ht.ctypes.data, hto.ctypes.data, n,
+                                       None, hres.ctypes.data, hvar.ctypes.data, var_cap, hvoff.ctypes.data, hstat.ctypes.data)
+        else:
+            rc = L.db200_ed_batch_host(local_rank, C.byref(prm_c), hq.ctypes.data, hqo.ctypes.data, ht.ctypes.data, hto.ctypes.data, n,
+                                       None, hres.ctypes.data, hvar.ctypes.data, var_cap, hvoff.ctypes.data)
+        _lib.check(rc, "db200_%s_batch_host" % kind)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(2):
@@ -296,37 +355,56 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
     e2e_value = total_cells * e2e_steps / float(tdt.item()) / 1e9
-    if int(hres[:, 0].astype(np.int64).sum()) != checksum:
+    if int(hres[:, 0 if kind == "sw" else 1].astype(np.int64).sum()) != checksum:
         raise SystemExit("bench.py: host and device arms disagree")
-    ncig = int(hcoff[n])
+    nvar = int(hvoff[n])
     h2d = q_bytes + t_bytes + 2 * 8 * (n + 1)
-    d2h = 32 * n + 4 * n + 8 * (n + 1) + 4 * ncig
+    d2h = 4 * res_cols * n + 8 * (n + 1) + (4 * n + 4 * nvar if kind == "sw" else 8 * nvar)
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (forward scoring pass) ---------------------------------------------
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------
     peaks = load_measured_peaks()
-    fwd_ms = stage_ms[3] / args.steps          # forward sw_pass_kernel launches of one step (this rank)
-    fwd_lane_ops = cells * SW_LANE_OPS_PER_CELL
-    achieved = fwd_lane_ops / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None
     peak = peaks["int_lane_ops"] / 1e12
-    alg_bytes = (q_bytes + t_bytes) / 2.0 + 16.0 * n   # packed 4-bit codes in, one PassOut record out
-    roofline = {
-        "bound": "int_alu", "kernel": "sw_pass_kernel (forward scoring pass, all length buckets)",
-        "achieved": achieved, "peak": peak, "unit": "Tlaneop/s (s16x2 DPX lane-instructions)",
-        "frac": (achieved / peak) if achieved else None, "peak_source": "measured: dysgu_b200/int_peak on this pool (profiles/r01_int_peak.json)",
-        "ops_per_cell": SW_LANE_OPS_PER_CELL, "kernel_ms_per_step": fwd_ms, "kernel_gcups": cells / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None,
-        "hbm_algorithmic_gbs": alg_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None, "hbm_peak_gbs": peaks["hbm_gbs"],
-        "hbm_peak_source": peaks["source"],
-        "traffic": (q_bytes + t_bytes) * FWD_TRAFFIC_PER_INPUT_BYTE, "algorithmic_bytes": alg_bytes,
-        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the forward launches of one step (profiles/r01_forward_traffic.txt), scaled by input bytes",
-        "stage_ms_per_step": {k: v / args.steps for k, v in zip(
-            ["begin", "pack", "bucket", "forward", "forward_rerun", "reverse_prep", "reverse", "reverse_rerun", "finalize",
-             "traceback", "cigar"], stage_ms[:11])},
-    }
+    stage_names = ["begin", "pack", "bucket", "forward", "forward_rerun", "reverse_prep", "reverse", "reverse_rerun", "finalize",
+                   "traceback", "cigar", "ed_prep", "ed_forward", "ed_starts", "ed_output"]
+    stages = {k: v / args.steps for k, v in zip(stage_names, stage_ms[:15]) if v > 0 or k == "begin"}
+    if kind == "sw":
+        k_ms = stage_ms[3] / args.steps          # forward sw_pass_kernel launches of one step (this rank)
+        lane_ops = cells * SW_LANE_OPS_PER_CELL
+        achieved = lane_ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
+        alg_bytes = (q_bytes + t_bytes) / 2.0 + 16.0 * n   # packed 4-bit codes in, one PassOut record out
+        roofline = {
+            "bound": "int_alu", "kernel": "sw_pass_kernel (forward scoring pass, all length buckets)",
+            "achieved": achieved, "peak": peak, "unit": "Tlaneop/s (s16x2 DPX lane-instructions)",
+            "frac": (achieved / peak) if achieved else None, "peak_source": "measured: dysgu_b200/int_peak on this pool (profiles/r01_int_peak.json)",
+            "ops_per_cell": SW_LANE_OPS_PER_CELL, "kernel_ms_per_step": k_ms, "kernel_gcups": cells / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None,
+            "hbm_algorithmic_gbs": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None, "hbm_peak_gbs": peaks["hbm_gbs"],
+            "hbm_peak_source": peaks["source"],
+            "traffic": (q_bytes + t_bytes) * FWD_TRAFFIC_PER_INPUT_BYTE if name == "remap_windows" else None, "algorithmic_bytes": alg_bytes,
+            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the forward launches of one step (profiles/r01_forward_traffic.txt), scaled by input bytes",
+            "stage_ms_per_step": stages,
+        }
+    else:
+        k_ms = stage_ms[12] / args.steps         # banded rounds + ed_myers_kernel forward launches of one step
+        lane_ops = word_steps * ED_LANE_OPS_PER_WORD_STEP
+        achieved = lane_ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
+        alg_bytes = float(q_bytes + t_bytes) + 16.0 * n
+        roofline = {
+            "bound": "int_alu", "kernel": "ed_banded_nw_kernel + ed_myers_kernel (forward pass, all configurations)" if prm["mode"] == "NW"
+            else "ed_myers_kernel (forward pass, all configurations)",
+            "achieved": achieved, "peak": peak, "unit": "Tlaneop/s (int32-equivalent ALU lane-ops, 44 per 64-row Myers word step)",
+            "frac": (achieved / peak) if achieved else None, "peak_source": "measured: dysgu_b200/int_peak on this pool (profiles/r01_int_peak.json)",
+            "ops_per_word_step": ED_LANE_OPS_PER_WORD_STEP, "word_steps_per_step": word_steps,
+            "word_steps_full_matrix": float(((q.lengths + 63) // 64 * t.lengths).sum()),
+            "kernel_ms_per_step": k_ms, "kernel_gcups": cells / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None,
+            "hbm_algorithmic_gbs": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None, "hbm_peak_gbs": peaks["hbm_gbs"],
+            "hbm_peak_source": peaks["source"], "traffic": None, "algorithmic_bytes": alg_bytes,
+            "stage_ms_per_step": stages,
+        }
 
     # ---- CPU baseline (rank 0, N = 1 only): the reference cores on all host threads, bounded sample ------------
     cpu_baseline = None
@@ -334,26 +412,26 @@ def run_ours(args):
         try:
             from oracle import oracle as O
             cores = os.cpu_count() or 1
-            sample = min(n, args.ref_pairs)
+            sample = min(n, args.ref_pairs or WORKLOADS[name][3])
             qs, ts = q.take(np.arange(sample)), t.take(np.arange(sample))
             scell = float((qs.lengths.astype(np.float64) * ts.lengths.astype(np.float64)).sum())
-            O.ref_sw((qs.buf, qs.off), (ts.buf, ts.off), prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"],
-                     nthreads=cores, csr=True)  # warm
-            r = O.ref_sw((qs.buf, qs.off), (ts.buf, ts.off), prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"],
-                         nthreads=cores, csr=True)
+            cpu_reference(O, name, qs, ts, prm, cores)  # warm
+            r = cpu_reference(O, name, qs, ts, prm, cores)
             cpu_baseline = {"value": scell / r.seconds / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
-                            "sample": "first %d pairs of the step's batch, ssw_init+ssw_align per pair at C level (ssw.c -O2), %.1f s" % (sample, r.seconds)}
+                            "sample": "first %d pairs of the step's batch, %s per pair at C level, %.1f s" % (
+                                sample, "ssw_init+ssw_align (ssw.c -O2)" if kind == "sw" else "edlibAlign (edlib.cpp -O3)", r.seconds)}
             # spot parity on the sample against the reference itself
-            mism = int((r.fixed[:, :7] != hres[:sample, :7]).any(axis=1).sum())
+            ncmp = 7 if kind == "sw" else 4
+            mism = int((r.fixed[:, :ncmp] != hres[:sample, :ncmp]).any(axis=1).sum())
             cpu_baseline["parity_mismatches_on_sample"] = mism
         except Exception as exc:
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % str(exc)[:100]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
-        "data": "synthetic",
-        "config": {"workload": "remap_windows: SSW(window 1000/1500/2000 bp; 2,-8,6,1)(soft clip 15-300 bp), score+coords+cigar",
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16" if kind == "sw" else "u64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[name][4],
                    "pairs_per_step_per_gpu": n, "cells_per_step_per_gpu": cells, "input_bytes_per_step_per_gpu": q_bytes + t_bytes,
                    "l2": "inputs larger than L2 (%.0f MB per step)" % ((q_bytes + t_bytes) / 1e6), "sharding": "pairs by rank, no collective"},
         "clocks": clocks,
@@ -362,7 +440,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "checksum_score1": checksum,
+        "checksum_%s" % ("score1" if kind == "sw" else "edit_distance"): checksum,
     }
     print(json.dumps(line))
     if dist is not None:
@@ -380,8 +458,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=1 << 19, help="pairs per step per GPU")
-    ap.add_argument("--ref-pairs", type=int, default=400000, help="pairs per step of the CPU reference sample (about 1.3 s on 16 cores)")
+    ap.add_argument("--workload", default="remap_windows", choices=sorted(WORKLOADS), help="default: the headline (BASELINE configs[1])")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per step per GPU (0: the workload's default)")
+    ap.add_argument("--ref-pairs", type=int, default=0, help="pairs per step of the CPU reference sample (0: the workload's default)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -7,9 +7,12 @@
 
 namespace db200 {
 
-static const int ED_CFG_WL[ED_NCFG] = {1, 2, 4, 4, 4, 4, 4, 4, 8, 16, 32};
-static const int ED_CFG_G[ED_NCFG] = {1, 1, 1, 2, 4, 8, 16, 32, 32, 32, 32};
-__device__ __constant__ int d_ed_cfg_words[ED_NCFG] = {1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024};
+// configuration -> (words per thread, threads per pair); capacity in 64-bit words of the query = WL * G.  Steps of at
+// most 1.33x above 32 words (one pair per warp), so a 10 kb query (157 words) runs in the 160-word configuration
+// instead of a 256-word one with 39 % idle lanes.
+static const int ED_CFG_WL[ED_NCFG] = {1, 2, 4, 4, 4, 4, 4, 4, 4, 3, 4, 3, 4, 5, 6, 8, 16, 32};
+static const int ED_CFG_G[ED_NCFG] = {1, 1, 1, 2, 3, 4, 6, 8, 10, 16, 16, 32, 32, 32, 32, 32, 32, 32};
+__device__ __constant__ int d_ed_cfg_words[ED_NCFG] = {1, 2, 4, 8, 12, 16, 24, 32, 40, 48, 64, 96, 128, 160, 192, 256, 512, 1024};
 
 __device__ __forceinline__ int ed_cfg_for(int W)
 {
@@ -30,6 +33,10 @@ struct EdPrepArgs {
     int32_t *hlog_words;
     int32_t *hist;         // [ED_NCFG * ED_LBINS]
     db200_ed_result *results;
+    int32_t band;          // NW: route pairs through the banded rounds (segments = rounds instead of configurations)
+    int32_t *fb_tasks;     // NW + band: pairs that go straight to the full-column kernel, per configuration
+    int32_t *fb_count;
+    int64_t fb_stride;
 };
 
 // one warp per pair: symbol sets, sizes, special cases (edlib.cpp:153-179)
@@ -81,7 +88,17 @@ __global__ void ed_prep_kernel(EdPrepArgs a)
         pw = at * pr.W * (need_rev ? 2 : 1);
         hw = (a.mode != DB200_ED_MODE_NW) ? ((n + 15) >> 4) : 0;
         const int lb = min(n >> 6, ED_LBINS - 1);
-        atomicAdd(&a.hist[pr.cfg * ED_LBINS + (ED_LBINS - 1 - lb)], 1);
+        pr.band_round = -1;
+        if (a.band) {
+            // first banded round whose cost bound 64 * (words - 1) is not already excluded by the length difference
+            const int absd = abs(n - m);
+            for (int r = 0; r < ED_BAND_ROUNDS; ++r)
+                if (pr.W <= ed_band_words(r) || 64 * (ed_band_words(r) - 1) >= absd) { pr.band_round = r; break; }
+            if (pr.band_round >= 0) atomicAdd(&a.hist[pr.band_round * ED_LBINS + (ED_LBINS - 1 - lb)], 1);
+            else a.fb_tasks[(int64_t)pr.cfg * a.fb_stride + atomicAdd(&a.fb_count[pr.cfg], 1)] = (int32_t)p;
+        } else {
+            atomicAdd(&a.hist[pr.cfg * ED_LBINS + (ED_LBINS - 1 - lb)], 1);
+        }
     }
     a.pairs[p] = pr;
     a.peq_words[p] = pw;
@@ -102,6 +119,7 @@ struct EdBuildArgs {
     const int32_t *bin_start;
     int32_t *bin_fill;
     int32_t *tasks;
+    int32_t band;
 };
 
 // one warp per pair: target symbols -> dense row ids, re-coded target, match vectors of the query
@@ -162,9 +180,12 @@ __global__ void ed_build_kernel(EdBuildArgs a)
     if (lane == 0) {
         a.pairs[p] = pr;
         const int lb = min(pr.n >> 6, ED_LBINS - 1);
-        const int key = pr.cfg * ED_LBINS + (ED_LBINS - 1 - lb);
-        const int pos = a.bin_start[key] + atomicAdd(&a.bin_fill[key], 1);
-        a.tasks[pos] = (int32_t)p;
+        const int seg = a.band ? pr.band_round : pr.cfg;   // banded NW: segments are rounds; round -1 sits in the fallback lists already
+        if (seg >= 0) {
+            const int key = seg * ED_LBINS + (ED_LBINS - 1 - lb);
+            const int pos = a.bin_start[key] + atomicAdd(&a.bin_fill[key], 1);
+            a.tasks[pos] = (int32_t)p;
+        }
     }
 }
 
@@ -326,14 +347,31 @@ static int launch_ed_cfg(Engine *e, int cfg, const EdArgs &a, cudaStream_t st)
         case 1: return launch_myers<2, 1, REV>(e, a, st);
         case 2: return launch_myers<4, 1, REV>(e, a, st);
         case 3: return launch_myers<4, 2, REV>(e, a, st);
-        case 4: return launch_myers<4, 4, REV>(e, a, st);
-        case 5: return launch_myers<4, 8, REV>(e, a, st);
-        case 6: return launch_myers<4, 16, REV>(e, a, st);
-        case 7: return launch_myers<4, 32, REV>(e, a, st);
-        case 8: return launch_myers<8, 32, REV>(e, a, st);
-        case 9: return launch_myers<16, 32, REV>(e, a, st);
+        case 4: return launch_myers<4, 3, REV>(e, a, st);
+        case 5: return launch_myers<4, 4, REV>(e, a, st);
+        case 6: return launch_myers<4, 6, REV>(e, a, st);
+        case 7: return launch_myers<4, 8, REV>(e, a, st);
+        case 8: return launch_myers<4, 10, REV>(e, a, st);
+        case 9: return launch_myers<3, 16, REV>(e, a, st);
+        case 10: return launch_myers<4, 16, REV>(e, a, st);
+        case 11: return launch_myers<3, 32, REV>(e, a, st);
+        case 12: return launch_myers<4, 32, REV>(e, a, st);
+        case 13: return launch_myers<5, 32, REV>(e, a, st);
+        case 14: return launch_myers<6, 32, REV>(e, a, st);
+        case 15: return launch_myers<8, 32, REV>(e, a, st);
+        case 16: return launch_myers<16, 32, REV>(e, a, st);
         default: return launch_myers<32, 32, REV>(e, a, st);
     }
+}
+
+template <int R>
+static int launch_banded(Engine *e, const EdBandArgs &a, int64_t npairs, cudaStream_t st)
+{
+    const unsigned blocks = (unsigned)((npairs + 127) / 128);   // upper bound: the lists live on the device
+    ed_banded_nw_kernel<ed_band_words(R), R == ED_BAND_ROUNDS - 1><<<blocks, 128, 0, st>>>(a);
+    count_launch(e);
+    DB200_CUDA_CHECK(cudaGetLastError());
+    return DB200_OK;
 }
 
 int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const uint8_t *d_qbuf, const int64_t *d_qoff,
@@ -365,7 +403,7 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     int64_t *peq_off = ws.alloc<int64_t>(npairs + 1);
     int64_t *hlog_off = ws.alloc<int64_t>(npairs + 1);
     int64_t *scan_tmp = ws.alloc<int64_t>(scan_tmp_count(npairs) * 2);
-    int32_t *bins = ws.alloc<int32_t>(nbins * 3 + 256);
+    int32_t *bins = ws.alloc<int32_t>(nbins * 3 + 512);
     int32_t *tasks = ws.alloc<int32_t>(npairs);
     uint8_t *tcodes = ws.alloc<uint8_t>((size_t)t_bytes + 64);
     uint32_t *hlog = ws.alloc<uint32_t>((size_t)(t_bytes / 16 + npairs + 64));
@@ -374,6 +412,12 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     int32_t *loc_pair = ws.alloc<int32_t>((size_t)std::max<int64_t>(loc_cap, 1));
     int32_t *rev_tasks = ws.alloc<int32_t>((size_t)std::max<int64_t>(loc_cap, 1));
     uint8_t *eq_dev = ws.alloc<uint8_t>(2 * (size_t)std::max(prm->n_eq_pairs, 1));
+    // NW runs the banded rounds first (DB200_ED_BANDED=0: full columns only, the measurement baseline)
+    const char *band_env = getenv("DB200_ED_BANDED");
+    const bool band = prm->mode == DB200_ED_MODE_NW && !(band_env && atoi(band_env) == 0) && npairs * ED_NCFG < ((int64_t)1 << 31);
+    int32_t *carry = band ? ws.alloc<int32_t>((size_t)npairs * ED_BAND_ROUNDS) : nullptr;
+    int32_t *fb_tasks = band ? ws.alloc<int32_t>((size_t)npairs * ED_NCFG) : nullptr;
+    if (band && (!carry || !fb_tasks)) { set_error("ed_batch: device workspace allocation failed"); return DB200_ERR_NOMEM; }
     if (!pairs || !peq_words || !hlog_words || !peq_off || !hlog_off || !scan_tmp || !bins || !tasks || !tcodes || !hlog ||
         !nw_score || !nloc || !loc_pair || !rev_tasks || !eq_dev) {
         set_error("ed_batch: device workspace allocation failed");
@@ -381,10 +425,14 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     }
     int32_t *hist = bins, *bin_start = bins + nbins, *bin_fill = bins + 2 * nbins;
     int32_t *small = bins + 3 * nbins;
-    int32_t *seg_begin = small, *seg_count = small + 16, *rev_count = small + 32, *rev_begin = small + 48, *rev_fill = small + 64;
-    int32_t *counters = small + 96; // 32 work counters
-    int32_t *overflow = small + 160;
-    DB200_CUDA_CHECK(cudaMemsetAsync(bins, 0, (nbins * 3 + 256) * sizeof(int32_t), st));
+    static_assert(ED_NCFG <= 32, "the small arrays below hold 32 entries each");
+    int32_t *seg_begin = small, *seg_count = small + 32, *rev_count = small + 64, *rev_begin = small + 96, *rev_fill = small + 128;
+    int32_t *counters = small + 160; // 64 work counters
+    int32_t *overflow = small + 224;
+    int32_t *carry_count = small + 232;   // [ED_BAND_ROUNDS]
+    int32_t *fb_count = small + 256;      // [ED_NCFG]
+    int32_t *fb_begin = small + 288;      // [ED_NCFG] = cfg * npairs
+    DB200_CUDA_CHECK(cudaMemsetAsync(bins, 0, (nbins * 3 + 512) * sizeof(int32_t), st));
     if (prm->n_eq_pairs > 0)
         DB200_CUDA_CHECK(cudaMemcpyAsync(eq_dev, prm->eq_pairs, 2 * (size_t)prm->n_eq_pairs, cudaMemcpyHostToDevice, st));
 
@@ -396,6 +444,7 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     pa.qbuf = d_qbuf; pa.tbuf = d_tbuf; pa.qoff = d_qoff; pa.toff = d_toff; pa.k = d_k; pa.k_default = prm->k;
     pa.mode = prm->mode; pa.task = prm->task; pa.npairs = npairs; pa.pairs = pairs; pa.peq_words = peq_words;
     pa.hlog_words = hlog_words; pa.hist = hist; pa.results = d_results;
+    pa.band = band ? 1 : 0; pa.fb_tasks = fb_tasks; pa.fb_count = fb_count; pa.fb_stride = npairs;
     ed_prep_kernel<<<gwarp, TB, 0, st>>>(pa);
     count_launch(e);
     exclusive_scan_i32_i64(e, peq_words, peq_off, npairs, scan_tmp, st);
@@ -414,7 +463,7 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     EdBuildArgs ba;
     ba.qbuf = d_qbuf; ba.tbuf = d_tbuf; ba.pairs = pairs; ba.peq_off = peq_off; ba.hlog_off = hlog_off; ba.npairs = npairs;
     ba.peq = peq; ba.tcodes = tcodes; ba.mode = prm->mode; ba.task = prm->task; ba.eq_pairs = eq_dev; ba.n_eq_pairs = prm->n_eq_pairs;
-    ba.bin_start = bin_start; ba.bin_fill = bin_fill; ba.tasks = tasks;
+    ba.bin_start = bin_start; ba.bin_fill = bin_fill; ba.tasks = tasks; ba.band = band ? 1 : 0;
     ed_build_kernel<<<gwarp, TB, 0, st>>>(ba);
     count_launch(e);
     prof_mark(e, st, ST_ED_PREP);
@@ -423,11 +472,44 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     memset(&ea, 0, sizeof(ea));
     ea.pairs = pairs; ea.peq = peq; ea.tcodes = tcodes; ea.hlog = hlog; ea.mode = prm->mode; ea.nw_score = nw_score;
     ea.loc_pair = loc_pair; ea.loc_buf = d_loc_buf;
+    ea.wsteps = reinterpret_cast<unsigned long long *>(e->d_sub_words + Engine::NSUB_MAX + 1);
     int ci = 0;
-    for (int cfg = 0; cfg < ED_NCFG; ++cfg) {
-        ea.tasks = tasks; ea.seg_begin = seg_begin; ea.seg_count = seg_count; ea.seg = cfg; ea.counter = counters + (ci++);
-        const int rc = launch_ed_cfg<false>(e, cfg, ea, st);
-        if (rc) return rc;
+    if (band) {
+        EdBandArgs bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.pairs = pairs; bd.peq = peq; bd.tcodes = tcodes; bd.tasks = tasks; bd.seg_begin = seg_begin; bd.seg_count = seg_count;
+        bd.fb_tasks = fb_tasks; bd.fb_count = fb_count; bd.fb_stride = npairs; bd.nw_score = nw_score; bd.wsteps = ea.wsteps;
+        for (int r = 0; r < ED_BAND_ROUNDS; ++r) {
+            bd.round = r;
+            bd.carry = r > 0 ? carry + (size_t)npairs * r : nullptr;
+            bd.carry_count = r > 0 ? carry_count + r : nullptr;
+            bd.next = carry + (size_t)npairs * (r + 1 < ED_BAND_ROUNDS ? r + 1 : 0);
+            bd.next_count = carry_count + (r + 1 < ED_BAND_ROUNDS ? r + 1 : 0);
+            int rc;
+            switch (r) {
+                case 0: rc = launch_banded<0>(e, bd, npairs, st); break;
+                case 1: rc = launch_banded<1>(e, bd, npairs, st); break;
+                case 2: rc = launch_banded<2>(e, bd, npairs, st); break;
+                case 3: rc = launch_banded<3>(e, bd, npairs, st); break;
+                default: rc = launch_banded<4>(e, bd, npairs, st); break;
+            }
+            if (rc) return rc;
+        }
+        // what no band resolved: the full-column kernels, one list per configuration
+        int32_t fb_begin_h[ED_NCFG];
+        for (int cfg = 0; cfg < ED_NCFG; ++cfg) fb_begin_h[cfg] = (int32_t)(npairs * cfg);
+        DB200_CUDA_CHECK(cudaMemcpyAsync(fb_begin, fb_begin_h, sizeof(fb_begin_h), cudaMemcpyHostToDevice, st));
+        for (int cfg = 0; cfg < ED_NCFG; ++cfg) {
+            ea.tasks = fb_tasks; ea.seg_begin = fb_begin; ea.seg_count = fb_count; ea.seg = cfg; ea.counter = counters + (ci++);
+            const int rc = launch_ed_cfg<false>(e, cfg, ea, st);
+            if (rc) return rc;
+        }
+    } else {
+        for (int cfg = 0; cfg < ED_NCFG; ++cfg) {
+            ea.tasks = tasks; ea.seg_begin = seg_begin; ea.seg_count = seg_count; ea.seg = cfg; ea.counter = counters + (ci++);
+            const int rc = launch_ed_cfg<false>(e, cfg, ea, st);
+            if (rc) return rc;
+        }
     }
     prof_mark(e, st, ST_ED_FORWARD);
 

@@ -16,7 +16,7 @@
 
 namespace db200 {
 
-constexpr int ED_NCFG = 11;
+constexpr int ED_NCFG = 18;
 constexpr int ED_LBINS = 256;   // target-length bins (64 columns each) per config, longest first
 
 struct EdPair {
@@ -33,6 +33,8 @@ struct EdPair {
     int64_t loc_off;
     int32_t special;        // 1: handled without DP (an empty sequence)
     int32_t cfg;
+    int32_t band_round;     // NW: first round of the banded kernel this pair enters (-1: full-column kernel only)
+    int32_t pad_;
 };
 
 struct EdArgs {
@@ -50,6 +52,7 @@ struct EdArgs {
     // reverse (start locations)
     const int32_t *loc_pair;     // location index -> pair
     int32_t *loc_buf;            // (start, end) pairs
+    unsigned long long *wsteps;  // word steps evaluated (statistics)
 };
 
 // One Myers column step on a 64-bit word.  hin/hout are (plus, minus) bit pairs.
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
         base = __shfl_sync(FULL, base, 0);
         if (base >= seg_count) break;
         const int ti = base + grp;
-        const bool active = ti < seg_count;
+        const bool active = grp < GROUPS && ti < seg_count;
         int task = active ? a.tasks[seg_begin + ti] : -1;
         int pair = -1, end = 0, ncols = 0;
         EdPair pr;
@@ -168,27 +171,38 @@ __global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
             }
             const int c_fwd = (int)((tcur >> ((t & 3) * 8)) & 0xFFu);
             uint32_t cin = carry;
-            if (G > 1) cin = __shfl_up_sync(FULL, carry, 1, G);
+            if (G > 1) cin = __shfl_up_sync(FULL, carry, 1);   // G need not divide 32: lanes past the last whole group idle
             if (lig == 0) cin = hin0;
             if (valid) {
                 const int c = REV ? tc[end - j] : c_fwd;
                 const uint64_t *row = peq + (int64_t)c * W;
                 const unsigned long long *srow = peq_s + (c * WL) * 32 + lane;
                 uint32_t hp = cin & 1u, hm = (cin >> 1) & 1u;
-                uint64_t Ph_l = 0, Mh_l = 0;
+                // Every thread that owns at least one word steps all WL of them: the words past the end of the query hold
+                // zero match vectors (or whatever follows in the pool) and feed nothing - only the last thread of a pair
+                // has them and its carry goes nowhere.  No per-word predicate, no per-word select of the last row's word.
+                uint64_t Phr[WL], Mhr[WL];
+                if (SMEM_PEQ && use_smem) {
 #pragma unroll
-                for (int w = 0; w < WL; ++w) {
-                    if (w < nw) {
+                    for (int w = 0; w < WL; ++w) {
                         uint32_t op, om;
-                        uint64_t Phr, Mhr;
-                        const uint64_t eq = (SMEM_PEQ && use_smem) ? srow[w * 32] : __ldg(row + w);
-                        myers_word(Pv[w], Mv[w], eq, hp, hm, op, om, Phr, Mhr);
+                        myers_word(Pv[w], Mv[w], srow[w * 32], hp, hm, op, om, Phr[w], Mhr[w]);
                         hp = op; hm = om;
-                        if (w == last_w) { Ph_l = Phr; Mh_l = Mhr; }
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < WL; ++w) {
+                        uint32_t op, om;
+                        myers_word(Pv[w], Mv[w], __ldg(row + w), hp, hm, op, om, Phr[w], Mhr[w]);
+                        hp = op; hm = om;
                     }
                 }
                 carry = hp | (hm << 1);
-                if (has_last) {
+                if (has_last) {   // one lane per pair: the horizontal delta of the query's last row
+                    uint64_t Ph_l = Phr[0], Mh_l = Mhr[0];
+#pragma unroll
+                    for (int w = 1; w < WL; ++w)
+                        if (w == last_w) { Ph_l = Phr[w]; Mh_l = Mhr[w]; }
                     const int dp = (int)((Ph_l >> last_bit) & 1ull), dm = (int)((Mh_l >> last_bit) & 1ull);
                     score += dp - dm;
                     if (REV) {
@@ -203,8 +217,121 @@ __global__ void __launch_bounds__(128) ed_myers_kernel(EdArgs a)
         if (has_last) {
             if (REV) a.loc_buf[2 * (int64_t)task] = end - rpos;
             else if (a.mode == DB200_ED_MODE_NW) a.nw_score[pair] = score;
+            if (!REV) atomicAdd(a.wsteps, (unsigned long long)ncols * (unsigned long long)W);   // forward passes only
         }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Banded global (NW) edit distance: one thread per pair, a window of WB 64-row words in registers that slides
+// down the diagonal.  Same results as the reference's Ukkonen-banded block algorithm (edlib.cpp:735-944), by a
+// different argument: cells outside the window are replaced by upper bounds (a new bottom word starts with all
+// vertical deltas +1, the row above the window advances by +1 per column), so every computed value is >= the
+// true one and exact on every alignment path that stays inside the window.  A path of cost <= c from corner to
+// corner visits only diagonals j - i in [-(c - D) / 2, (c + D) / 2] (D = n - m); the window placed at
+// 64 * floor((j - (c + D) / 2) / 64) covers them for c = 64 * (WB - 1).  Hence: banded distance <= c  =>  it is
+// the edit distance; banded distance > c  =>  the edit distance is > c and the pair moves to the next, wider
+// round (2, 3, 5, 9, 17 words, then the full-column kernel) - the same doubling edlib applies to k (edlib.cpp:199-214).
+// ------------------------------------------------------------------------------------------------
+constexpr int ED_BAND_ROUNDS = 5;
+__host__ __device__ constexpr int ed_band_words(int r) { return r == 0 ? 2 : (r == 1 ? 3 : (r == 2 ? 5 : (r == 3 ? 9 : 17))); }
+
+struct EdBandArgs {
+    const EdPair *pairs;
+    const uint64_t *peq;
+    const uint8_t *tcodes;
+    const int32_t *tasks;        // pairs entering at this round, longest targets first (segment `round` of the bucket list)
+    const int32_t *seg_begin;
+    const int32_t *seg_count;
+    const int32_t *carry;        // pairs handed on by the previous round
+    const int32_t *carry_count;
+    int32_t *next;               // where this round hands its failures: the next round's carry list ...
+    int32_t *next_count;
+    int32_t *fb_tasks;           // ... or, after the last round, the full-column kernel's task list of the pair's configuration
+    int32_t *fb_count;           // [ED_NCFG]
+    int64_t fb_stride;
+    int32_t round;
+    int32_t *nw_score;
+    unsigned long long *wsteps;  // word steps evaluated (statistics)
+};
+
+template <int WB, bool LAST>
+__global__ void __launch_bounds__(128) ed_banded_nw_kernel(EdBandArgs a)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_first = a.seg_count[a.round];
+    const int n_carry = a.carry_count ? *a.carry_count : 0;
+    if (idx >= n_first + n_carry) return;
+    const int pair = idx < n_first ? a.tasks[a.seg_begin[a.round] + idx] : a.carry[idx - n_first];
+    const EdPair pr = a.pairs[pair];
+    const int m = pr.m, n = pr.n, W = pr.W;
+    const int nwin = min(WB, W);
+    const bool full = W <= WB;                    // the window is the whole column: exact whatever the distance
+    const int c = 64 * (WB - 1);
+    const int H = (c + (n - m)) >> 1;             // rows above the diagonal a cost-c path can reach (routing guarantees c >= |n - m|)
+    const uint64_t *peq = a.peq + pr.peq_off;
+    const uint8_t *tc = a.tcodes + pr.t_off;
+
+    uint64_t Pv[WB], Mv[WB];
+#pragma unroll
+    for (int w = 0; w < WB; ++w) { Pv[w] = ~0ull; Mv[w] = 0ull; }
+    int wb0 = 0;
+    int score = min(64 * nwin, m);                // value of the window's bottom row in column -1
+    const int wb_max = W - nwin;
+    bool failed = false;
+    int jdone = n;
+    for (int j = 0; j < n; ++j) {
+        if (!full) {
+            const int want = min(max(j - H, 0) >> 6, wb_max);
+            if (want > wb0) {                     // the window moves down by one word
+                const int old_b = 64 * (wb0 + nwin) - 1;
+#pragma unroll
+                for (int w = 0; w + 1 < WB; ++w) { Pv[w] = Pv[w + 1]; Mv[w] = Mv[w + 1]; }
+                Pv[WB - 1] = ~0ull; Mv[WB - 1] = 0ull;
+                ++wb0;
+                score += min(64 * (wb0 + nwin), m) - 1 - old_b;
+            }
+        }
+        const int sym = tc[j];
+        const uint64_t *row = peq + (int64_t)sym * W + wb0;
+        uint32_t hp = 1u, hm = 0u;
+        uint64_t Ph_l = 0, Mh_l = 0;
+#pragma unroll
+        for (int w = 0; w < WB; ++w) {
+            if (w < nwin) {
+                uint32_t op, om;
+                myers_word(Pv[w], Mv[w], __ldg(row + w), hp, hm, op, om, Ph_l, Mh_l);
+                hp = op; hm = om;
+            }
+        }
+        const int bit = (wb0 + nwin == W) ? ((m - 1) & 63) : 63;
+        score += (int)((Ph_l >> bit) & 1ull) - (int)((Mh_l >> bit) & 1ull);
+        // Ukkonen cut-off, once per 64 columns: every path through column j costs at least the value on the corner's
+        // diagonal (row j - (n - m)): vertical neighbours differ by at most 1 and a detour of r rows costs r again on
+        // the way back.  Once that value exceeds c the round cannot succeed.
+        if (!full && (j & 63) == 63) {
+            const int i0 = j - (n - m);
+            if (i0 >= 0) {
+                int v = score;
+#pragma unroll
+                for (int w = 0; w < WB; ++w) {
+                    const int lo = i0 + 1 - 64 * (wb0 + w);          // rows of this word above the diagonal row are excluded
+                    uint64_t mask = lo <= 0 ? ~0ull : (lo >= 64 ? 0ull : (~0ull << lo));
+                    if (w == WB - 1 && bit != 63) mask &= (2ull << bit) - 1ull;
+                    v -= __popcll(Pv[w] & mask) - __popcll(Mv[w] & mask);
+                }
+                if (v > c) { score = v; failed = true; jdone = j + 1; break; }
+            }
+        }
+    }
+    atomicAdd(a.wsteps, (unsigned long long)jdone * (unsigned long long)nwin);
+    if (full || (!failed && score <= c) || (pr.k >= 0 && c >= pr.k)) {
+        a.nw_score[pair] = score;                 // exact, or known to exceed k (ed_count_kernel turns that into -1)
+    } else if (!LAST) {
+        a.next[atomicAdd(a.next_count, 1)] = pair;
+    } else {
+        a.fb_tasks[(int64_t)pr.cfg * a.fb_stride + atomicAdd(&a.fb_count[pr.cfg], 1)] = pair;
     }
 }
 

@@ -108,12 +108,13 @@ Engine *get_engine(int device)
     }
     for (int i = 0; i < Engine::NSUB_MAX; ++i) cudaEventCreateWithFlags(&e->ev_sub[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_sub_fork, cudaEventDisableTiming);
-    if (cudaMalloc(&e->d_sub_words, sizeof(int64_t) * (Engine::NSUB_MAX + 1)) != cudaSuccess) {
+    if (cudaMalloc(&e->d_sub_words, sizeof(int64_t) * (Engine::NSUB_MAX + 2)) != cudaSuccess) {
         cudaGetLastError();
         set_error("cudaMalloc failed");
         delete e;
         return nullptr;
     }
+    cudaMemset(e->d_sub_words, 0, sizeof(int64_t) * (Engine::NSUB_MAX + 2));
     const char *sb = getenv("DB200_TRACE_SLAB_MB");
     e->trace_slab_bytes = (size_t)(sb ? atol(sb) : 4096) << 20;
     if (e->trace_slab_bytes < ((size_t)64 << 20)) e->trace_slab_bytes = (size_t)64 << 20;
@@ -288,6 +289,22 @@ int64_t db200_kernel_launches(int device, int reset)
     const int64_t n = e->launches;
     if (reset) e->launches = 0;
     return n;
+}
+
+// 64-row word steps (one Myers block update) the edit-distance kernels evaluated on `device` since the last reset:
+// the work actually done, next to the full-matrix cell count GCUPS is quoted on.  Synchronises the device.
+int64_t db200_ed_word_steps(int device, int reset)
+{
+    Engine *e = get_engine(device);
+    if (!e) return -1;
+    int64_t v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(&v, e->d_sub_words + Engine::NSUB_MAX + 1, sizeof(int64_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    if (reset) cudaMemset(e->d_sub_words + Engine::NSUB_MAX + 1, 0, sizeof(int64_t));
+    return v;
 }
 
 int db200_profile_enable(int device, int on)

@@ -58,7 +58,7 @@ struct Engine {
     static constexpr int NSUB_MAX = 16;  // sub-batches of one device call (db200_sw_batch_device)
     cudaEvent_t ev_sub[NSUB_MAX] = {};   // cigar placement of sub-batch i done
     cudaEvent_t ev_sub_fork = nullptr, ev_sub_join[NSLOT] = {};
-    int64_t *d_sub_words = nullptr;      // [NSUB_MAX + 1] cigar cursor between sub-batches
+    int64_t *d_sub_words = nullptr;      // [NSUB_MAX + 1] cigar cursor between sub-batches; [NSUB_MAX + 1] Myers word steps evaluated
     cudaEvent_t ev_copy[NSLOT] = {};
     cudaEvent_t ev_done[NSLOT] = {};
     Arena arena[NSLOT];                  // compute workspace (one per in-flight chunk)

@@ -60,6 +60,8 @@ int64_t db200_kernel_launches(int device, int reset);
  * the device and returns the accumulated milliseconds per stage (see enum Stage in csrc/engine.cuh:
  * 1 pack, 2 bucket, 3 forward pass, 4 forward re-run, 5 reverse prep, 6 reverse pass, 7 reverse re-run,
  * 8 finalize, 9 traceback, 10 cigar, 11 ed prep, 12 ed forward, 13 ed starts, 14 ed output). */
+/* Myers word steps (one 64-row block update) the edit-distance kernels evaluated since the last reset; synchronises. */
+int64_t db200_ed_word_steps(int device, int reset);
 int db200_profile_enable(int device, int on);
 int db200_profile_collect(int device, float *ms, int nstages);
 /* Page-locked host memory for the *_host entry points (plain malloc'd buffers work too, slower). */
