@@ -76,6 +76,24 @@ class SwResults:
     def as_tuple(self, i):
         return tuple(int(x) for x in self.fixed[i, :7]) + (self.cigar_str(i),)
 
+    def cigar_stats(self):
+        """Per pair, straight from the BAM-encoded cigar arrays (no string round trip): int64 [n, 3] =
+        (bases in M runs, bases in I/D runs, longest I/D run) - the quantities merge_svs.matches_with_max_gap
+        parses out of the cigar string (merge_svs.pyx:196-222).  Vectorised over the whole batch."""
+        n = len(self)
+        out = np.zeros((n, 3), dtype=np.int64)
+        if self.cigar.size == 0:
+            return out
+        lens = (self.cigar >> 4).astype(np.int64)
+        is_m = (self.cigar & 0xF) == 0
+        starts = self.cigar_off[:-1]
+        nonempty = self.cigar_off[1:] > starts
+        idx = starts[nonempty]
+        out[nonempty, 0] = np.add.reduceat(np.where(is_m, lens, 0), idx)
+        out[nonempty, 1] = np.add.reduceat(np.where(is_m, 0, lens), idx)
+        out[nonempty, 2] = np.maximum.reduceat(np.where(is_m, 0, lens), idx)
+        return out
+
 
 def sw_align_batch(queries, targets, match=2, mismatch=-3, gap_open=5, gap_extend=2, score_size=2, flag=1, filters=0,
                    filterd=0, mask_len=None, matrix=None, device=None, want_cigar=True) -> SwResults:

@@ -10,6 +10,7 @@ candidates speculatively and replaying control flow afterwards cannot change a V
     badclip_scores_batch       the two alignments per contig in post_call.get_badclip_metric   post_call.py:50-79
     clip_align_matches_batch   filter_normals.clip_align_matches                         filter_normals.py:657-697
     remap_clip_batch           the edlib -> edlib -> SSW chain of re_map.process_contig   re_map.py:142-153, 208-223
+    matches_with_max_gap_batch merge_svs.matches_with_max_gap on the cigar arrays of a batch    merge_svs.pyx:196-222
 """
 from __future__ import annotations
 
@@ -86,6 +87,16 @@ def check_contig_match_batch(pairs: Sequence[Tuple[str, str]], diffs=8, ol_lengt
         else:
             out.append(0)
     return out
+
+
+def matches_with_max_gap_batch(results, max_gap: int, gaps_tol: float) -> np.ndarray:
+    """merge_svs.matches_with_max_gap for every pair of a batch (merge_svs.pyx:196-222): the matched bases, or 0 when
+    an I/D run is longer than max_gap or gaps / matches exceeds gaps_tol (float32 division as in the reference)."""
+    st = results.cigar_stats()
+    matches, gaps, longest = st[:, 0], st[:, 1], st[:, 2]
+    ratio = np.divide(gaps.astype(np.float32), matches.astype(np.float32), out=np.zeros(len(st), np.float32), where=matches > 0)
+    bad = (longest > max_gap) | ((matches > 0) & (ratio > np.float32(gaps_tol)))
+    return np.where(bad, 0, matches)
 
 
 # ---------------------------------------------------------------------------------------------------------------

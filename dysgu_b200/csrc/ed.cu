@@ -39,22 +39,43 @@ struct EdPrepArgs {
     int64_t fb_stride;
 };
 
+// 256-bit symbol set of a byte range, accumulated per lane in registers (no atomics: DNA has four symbols, every lane
+// would hit the same shared-memory word) and OR-reduced over the warp; lane l < 8 returns word l of the set.
+__device__ __forceinline__ uint32_t symbol_set_word(const uint8_t *s, int len, int lane)
+{
+    uint64_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    for (int i = lane; i < len; i += 32) {
+        const uint32_t c = s[i];
+        const uint64_t bit = 1ull << (c & 63u);
+        const uint32_t hi = c >> 6;
+        b0 |= hi == 0 ? bit : 0ull;
+        b1 |= hi == 1 ? bit : 0ull;
+        b2 |= hi == 2 ? bit : 0ull;
+        b3 |= hi == 3 ? bit : 0ull;
+    }
+    uint32_t w[8] = {(uint32_t)b0, (uint32_t)(b0 >> 32), (uint32_t)b1, (uint32_t)(b1 >> 32),
+                     (uint32_t)b2, (uint32_t)(b2 >> 32), (uint32_t)b3, (uint32_t)(b3 >> 32)};
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t r = __reduce_or_sync(0xFFFFFFFFu, w[k]);
+        if (lane == k) mine = r;
+    }
+    return mine;
+}
+
 // one warp per pair: symbol sets, sizes, special cases (edlib.cpp:153-179)
 __global__ void ed_prep_kernel(EdPrepArgs a)
 {
-    __shared__ uint32_t bm[8][16]; // per warp: 8 words query set, 8 words target set
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (p >= a.npairs) return;
-    if (lane < 16) bm[warp][lane] = 0;
-    __syncwarp();
     const int64_t q0 = a.qoff[p], t0 = a.toff[p];
     const int m = (int)(a.qoff[p + 1] - q0), n = (int)(a.toff[p + 1] - t0);
-    for (int i = lane; i < m; i += 32) { const uint8_t c = a.qbuf[q0 + i]; atomicOr(&bm[warp][c >> 5], 1u << (c & 31)); }
-    for (int i = lane; i < n; i += 32) { const uint8_t c = a.tbuf[t0 + i]; atomicOr(&bm[warp][8 + (c >> 5)], 1u << (c & 31)); }
-    __syncwarp();
+    const uint32_t qs = symbol_set_word(a.qbuf + q0, m, lane);
+    const uint32_t ts = symbol_set_word(a.tbuf + t0, n, lane);
     int au = 0, at = 0;
-    if (lane < 8) { au = __popc(bm[warp][lane] | bm[warp][8 + lane]); at = __popc(bm[warp][8 + lane]); }
+    if (lane < 8) { au = __popc(qs | ts); at = __popc(ts); }
     for (int o = 4; o >= 1; o >>= 1) { au += __shfl_xor_sync(0xFFFFFFFFu, au, o); at += __shfl_xor_sync(0xFFFFFFFFu, at, o); }
     au = __shfl_sync(0xFFFFFFFFu, au, 0);
     at = __shfl_sync(0xFFFFFFFFu, at, 0);
@@ -136,9 +157,10 @@ __global__ void ed_build_kernel(EdBuildArgs a)
     pr.peq_off = a.peq_off[p];
     pr.hlog_off = a.hlog_off[p];
     const uint8_t *q = a.qbuf + pr.q_off, *t = a.tbuf + pr.t_off;
-    if (lane < 8) tset[warp][lane] = 0;
-    __syncwarp();
-    for (int i = lane; i < pr.n; i += 32) { const uint8_t c = t[i]; atomicOr(&tset[warp][c >> 5], 1u << (c & 31)); }
+    {
+        const uint32_t ts = symbol_set_word(t, pr.n, lane);
+        if (lane < 8) tset[warp][lane] = ts;
+    }
     __syncwarp();
     // rank of every byte among the target's symbols (0xFF: not a target symbol)
     for (int c = lane; c < 256; c += 32) {
@@ -151,29 +173,45 @@ __global__ void ed_build_kernel(EdBuildArgs a)
         rank_s[warp][c] = (uint8_t)r;
     }
     __syncwarp();
+    // re-coded target: four symbols per word where source and destination (same offset) are word-aligned
     uint8_t *tc = a.tcodes + pr.t_off;
-    for (int i = lane; i < pr.n; i += 32) tc[i] = rank_s[warp][t[i]];
+    {
+        const int head = min(pr.n, (int)((4u - (unsigned)(reinterpret_cast<uintptr_t>(t) & 3u)) & 3u));
+        const int nw4 = (pr.n - head) >> 2;
+        if (lane < head) tc[lane] = rank_s[warp][t[lane]];
+        const uint32_t *t4 = reinterpret_cast<const uint32_t *>(t + head);
+        uint32_t *tc4 = reinterpret_cast<uint32_t *>(tc + head);
+        for (int i = lane; i < nw4; i += 32) {
+            const uint32_t x = t4[i];
+            tc4[i] = (uint32_t)rank_s[warp][x & 0xFFu] | ((uint32_t)rank_s[warp][(x >> 8) & 0xFFu] << 8) |
+                     ((uint32_t)rank_s[warp][(x >> 16) & 0xFFu] << 16) | ((uint32_t)rank_s[warp][x >> 24] << 24);
+        }
+        const int tail0 = head + 4 * nw4;
+        if (tail0 + lane < pr.n) tc[tail0 + lane] = rank_s[warp][t[tail0 + lane]];
+    }
     const bool need_rev = (a.mode == DB200_ED_MODE_HW && a.task >= DB200_ED_TASK_LOC);
     const int W = pr.W, m = pr.m, At = pr.At;
     uint64_t *peq = a.peq + pr.peq_off;
-    const int total = At * W * (need_rev ? 2 : 1);
-    for (int i = lane; i < total; i += 32) peq[i] = 0ull;
-    __syncwarp();
-    // each lane owns whole words, so no atomics are needed
+    // match vectors: the warp takes one 64-row word at a time (lane l holds rows l and l + 32) and one ballot pair per
+    // target symbol yields that symbol's word - every entry is written exactly once, nothing is read back
     for (int dir = 0; dir < (need_rev ? 2 : 1); ++dir) {
         uint64_t *tab = peq + (int64_t)dir * At * W;
-        for (int w = lane; w < W; w += 32) {
-            for (int b = 0; b < 64; ++b) {
-                const int i = w * 64 + b;
-                if (i >= m) break;
-                const uint8_t c = dir ? q[m - 1 - i] : q[i];
-                const int r = rank_s[warp][c];
-                if (r != 0xFF) tab[(int64_t)r * W + w] |= 1ull << b;
+        for (int w = 0; w < W; ++w) {
+            const int i_lo = w * 64 + lane, i_hi = i_lo + 32;
+            const int c_lo = i_lo < m ? (int)(dir ? q[m - 1 - i_lo] : q[i_lo]) : -1;
+            const int c_hi = i_hi < m ? (int)(dir ? q[m - 1 - i_hi] : q[i_hi]) : -1;
+            const int r_lo = c_lo >= 0 ? (int)rank_s[warp][c_lo] : 0x1FF;
+            const int r_hi = c_hi >= 0 ? (int)rank_s[warp][c_hi] : 0x1FF;
+            for (int r = 0; r < At; ++r) {
+                bool h_lo = r_lo == r, h_hi = r_hi == r;
                 for (int e = 0; e < a.n_eq_pairs; ++e) {   // additionalEqualities: symmetric, not transitive
-                    const uint8_t x = a.eq_pairs[2 * e], y = a.eq_pairs[2 * e + 1];
-                    if (c == x && rank_s[warp][y] != 0xFF) tab[(int64_t)rank_s[warp][y] * W + w] |= 1ull << b;
-                    if (c == y && rank_s[warp][x] != 0xFF) tab[(int64_t)rank_s[warp][x] * W + w] |= 1ull << b;
+                    const int x = a.eq_pairs[2 * e], y = a.eq_pairs[2 * e + 1];
+                    const bool xr = rank_s[warp][x] == r, yr = rank_s[warp][y] == r;
+                    h_lo = h_lo || (c_lo == x && yr) || (c_lo == y && xr);
+                    h_hi = h_hi || (c_hi == x && yr) || (c_hi == y && xr);
                 }
+                const uint32_t lo = __ballot_sync(0xFFFFFFFFu, h_lo), hi = __ballot_sync(0xFFFFFFFFu, h_hi);
+                if (lane == 0) tab[(int64_t)r * W + w] = (uint64_t)lo | ((uint64_t)hi << 32);
             }
         }
     }

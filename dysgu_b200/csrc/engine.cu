@@ -709,15 +709,22 @@ int db200_ed_batch_host(int device, const db200_ed_params *params, const uint8_t
     if (!e) return DB200_ERR_CUDA;
     if (npairs < 0 || !params || !qoff || !toff || !results || !loc_buf || !loc_off) { set_error("ed_batch_host: bad arguments"); return DB200_ERR_ARG; }
     loc_off[0] = 0;
-    cudaStream_t st = e->stream;
-    const int64_t MAX_CHUNK_PAIRS = (int64_t)1 << 20;
-    const int64_t MAX_CHUNK_BYTES = (int64_t)2 << 30;
-    int64_t written = 0;
-    std::vector<int64_t> offs;
+    // Chunks flow through two slots: while chunk i is aligned on its slot's stream, chunk i+1 is copied to the device on the
+    // copy stream (the match-vector pool size is read back inside each chunk, so the host thread follows the compute closely;
+    // the copies are what overlaps).
+    struct Chunk { int64_t c0, c1, qb, tb; int32_t maxq, maxt; };
+    std::vector<Chunk> chunks;
+    const int64_t MAX_CHUNK_BYTES = (int64_t)1 << 30;
+    // at least 131072 pairs per chunk: the banded / long-query kernels are latency-bound per launch (thread or warp per
+    // pair), so cutting a few hundred thousand long pairs into chunks multiplies that latency (200,000 HiFi insertion
+    // pairs: 58 ms in one chunk, 142 ms in four); many short pairs (clip vs window) do profit from the overlapped copies
+    const int64_t want = std::min<int64_t>(std::max<int64_t>(npairs / 4, 131072), (int64_t)1 << 20);
     for (int64_t c0 = 0; c0 < npairs;) {
         int64_t c1 = c0, bytes = 0;
         int32_t maxq = 0, maxt = 0;
-        while (c1 < npairs && c1 - c0 < MAX_CHUNK_PAIRS) {
+        int64_t lim = want;
+        if (npairs - (c0 + lim) < lim / 2) lim = npairs - c0;   // no tiny trailing chunk
+        while (c1 < npairs && c1 - c0 < lim) {
             const int64_t ql = qoff[c1 + 1] - qoff[c1], tl = toff[c1 + 1] - toff[c1];
             if (ql < 0 || tl < 0 || ql > 0x7FFFFFF0 || tl > 0x7FFFFFF0) { set_error("ed_batch_host: bad offsets at pair %lld", (long long)c1); return DB200_ERR_ARG; }
             if (c1 > c0 && bytes + ql + tl > MAX_CHUNK_BYTES) break;
@@ -726,36 +733,68 @@ int db200_ed_batch_host(int device, const db200_ed_params *params, const uint8_t
             maxt = std::max<int32_t>(maxt, (int32_t)tl);
             ++c1;
         }
-        const int64_t n = c1 - c0;
-        const int64_t qb = qoff[c1] - qoff[c0], tb = toff[c1] - toff[c0];
-        offs.resize((size_t)(2 * (n + 1)));
-        for (int64_t i = 0; i <= n; ++i) { offs[(size_t)i] = qoff[c0 + i] - qoff[c0]; offs[(size_t)(n + 1 + i)] = toff[c0 + i] - toff[c0]; }
-        Arena &io = e->io[0];
-        io.reset();
-        e->arena[0].reset();
-        const int64_t cap = std::min<int64_t>(std::max<int64_t>(loc_cap - written, 0), tb + 2 * n + 16);
-        uint8_t *d_q = io.alloc<uint8_t>((size_t)qb + 16), *d_t = io.alloc<uint8_t>((size_t)tb + 16);
-        int64_t *d_off = io.alloc<int64_t>((size_t)(2 * (n + 1)));
-        int32_t *d_k = k ? io.alloc<int32_t>((size_t)n) : nullptr;
-        db200_ed_result *d_res = io.alloc<db200_ed_result>((size_t)n);
-        int64_t *d_loff = io.alloc<int64_t>((size_t)n + 1);
-        int32_t *d_loc = io.alloc<int32_t>((size_t)(2 * cap + 16));
-        if (!d_q || !d_t || !d_off || (k && !d_k) || !d_res || !d_loff || !d_loc) { set_error("ed_batch_host: device allocation failed"); return DB200_ERR_NOMEM; }
-        DB200_CUDA_CHECK(cudaMemcpyAsync(d_q, qbuf + qoff[c0], (size_t)qb, cudaMemcpyHostToDevice, st));
-        DB200_CUDA_CHECK(cudaMemcpyAsync(d_t, tbuf + toff[c0], (size_t)tb, cudaMemcpyHostToDevice, st));
-        DB200_CUDA_CHECK(cudaMemcpyAsync(d_off, offs.data(), sizeof(int64_t) * (size_t)(2 * (n + 1)), cudaMemcpyHostToDevice, st));
-        if (k) DB200_CUDA_CHECK(cudaMemcpyAsync(d_k, k + c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-        int64_t total = 0;
-        int rc = ed_batch_device_impl(e, e->arena[0], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, maxt, d_k, d_res, d_loc, cap,
-                                      d_loff, &total, st);
-        if (rc) return rc;
-        DB200_CUDA_CHECK(cudaMemcpyAsync(results + c0, d_res, sizeof(db200_ed_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
-        DB200_CUDA_CHECK(cudaMemcpyAsync(loc_off + c0, d_loff, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
-        if (total > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(loc_buf + 2 * written, d_loc, sizeof(int32_t) * 2 * (size_t)total, cudaMemcpyDeviceToHost, st));
-        DB200_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (written) for (int64_t i = 0; i <= n; ++i) loc_off[c0 + i] += written;
-        written += total;
+        chunks.push_back(Chunk{c0, c1, qoff[c1] - qoff[c0], toff[c1] - toff[c0], maxq, maxt});
         c0 = c1;
+    }
+    struct Staged { uint8_t *d_q, *d_t; int64_t *d_off; int32_t *d_k; db200_ed_result *d_res; int64_t *d_loff; int32_t *d_loc; int64_t cap; };
+    Staged staged[2] = {};
+    cudaStream_t cst = e->copy_stream;
+    auto stage = [&](size_t ci) -> int {
+        const Chunk &c = chunks[ci];
+        const int slot = (int)(ci & 1);
+        const int64_t n = c.c1 - c.c0;
+        const size_t stage_bytes = sizeof(int64_t) * (size_t)(2 * (n + 1));
+        if (e->pinned_out_cap[slot] < stage_bytes) {
+            if (e->pinned_out[slot]) cudaFreeHost(e->pinned_out[slot]);
+            e->pinned_out[slot] = nullptr;
+            e->pinned_out_cap[slot] = 0;
+            DB200_CUDA_CHECK(cudaHostAlloc(&e->pinned_out[slot], stage_bytes * 2, cudaHostAllocDefault));
+            e->pinned_out_cap[slot] = stage_bytes * 2;
+        }
+        int64_t *offs = reinterpret_cast<int64_t *>(e->pinned_out[slot]);
+        for (int64_t i = 0; i <= n; ++i) { offs[i] = qoff[c.c0 + i] - qoff[c.c0]; offs[n + 1 + i] = toff[c.c0 + i] - toff[c.c0]; }
+        Arena &io = e->io[slot];
+        io.reset();
+        Staged &s = staged[slot];
+        s.cap = c.tb + 2 * n + 16;   // locations of a chunk are bounded by its target bytes
+        s.d_q = io.alloc<uint8_t>((size_t)c.qb + 16);
+        s.d_t = io.alloc<uint8_t>((size_t)c.tb + 16);
+        s.d_off = io.alloc<int64_t>((size_t)(2 * (n + 1)));
+        s.d_k = k ? io.alloc<int32_t>((size_t)n) : nullptr;
+        s.d_res = io.alloc<db200_ed_result>((size_t)n);
+        s.d_loff = io.alloc<int64_t>((size_t)n + 1);
+        s.d_loc = io.alloc<int32_t>((size_t)(2 * s.cap + 16));
+        if (!s.d_q || !s.d_t || !s.d_off || (k && !s.d_k) || !s.d_res || !s.d_loff || !s.d_loc) { set_error("ed_batch_host: device allocation failed"); return DB200_ERR_NOMEM; }
+        DB200_CUDA_CHECK(cudaMemcpyAsync(s.d_q, qbuf + qoff[c.c0], (size_t)c.qb, cudaMemcpyHostToDevice, cst));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(s.d_t, tbuf + toff[c.c0], (size_t)c.tb, cudaMemcpyHostToDevice, cst));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(s.d_off, offs, stage_bytes, cudaMemcpyHostToDevice, cst));
+        if (k) DB200_CUDA_CHECK(cudaMemcpyAsync(s.d_k, k + c.c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, cst));
+        DB200_CUDA_CHECK(cudaEventRecord(e->ev_copy[slot], cst));
+        return DB200_OK;
+    };
+    int64_t written = 0;
+    if (!chunks.empty()) { const int rc = stage(0); if (rc) return rc; }
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk &c = chunks[ci];
+        const int slot = (int)(ci & 1);
+        cudaStream_t st = e->slot_stream[slot];
+        // the other slot's previous chunk was drained at the end of the last iteration: its buffers are free
+        if (ci + 1 < chunks.size()) { const int rc = stage(ci + 1); if (rc) return rc; }
+        const int64_t n = c.c1 - c.c0;
+        Staged &s = staged[slot];
+        DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_copy[slot], 0));
+        e->arena[slot].reset();
+        int64_t total = 0;
+        int rc = ed_batch_device_impl(e, e->arena[slot], params, s.d_q, s.d_off, c.qb, s.d_t, s.d_off + n + 1, c.tb, n, c.maxq, c.maxt, s.d_k,
+                                      s.d_res, s.d_loc, s.cap, s.d_loff, &total, st);
+        if (rc) return rc;
+        if (written + total > loc_cap) { set_error("ed_batch_host: location buffer too small (%lld needed)", (long long)(written + total)); return DB200_ERR_CAPACITY; }
+        DB200_CUDA_CHECK(cudaMemcpyAsync(results + c.c0, s.d_res, sizeof(db200_ed_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(loc_off + c.c0, s.d_loff, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+        if (total > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(loc_buf + 2 * written, s.d_loc, sizeof(int32_t) * 2 * (size_t)total, cudaMemcpyDeviceToHost, st));
+        DB200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (written) for (int64_t i = 0; i <= n; ++i) loc_off[c.c0 + i] += written;
+        written += total;
     }
     loc_off[npairs] = written;
     return DB200_OK;

@@ -75,3 +75,42 @@ def test_shard_bounds_and_merge():
     assert sum((p.tolist() for p in parts), []) == b.tolist()
     off, val = shard.merge_csr([np.array([0, 2, 3]), np.array([0, 1, 1, 4])], [np.array([7, 8, 9]), np.array([1, 2, 3, 4])])
     assert list(off) == [0, 2, 3, 4, 4, 7] and list(val) == [7, 8, 9, 1, 2, 3, 4]
+
+
+def test_cigar_stats_match_a_string_parse():
+    """SwResults.cigar_stats / callers.matches_with_max_gap_batch against the per-string parse the reference does
+    (merge_svs.pyx:196-222), on synthetic cigar arrays incl. empty cigars."""
+    import re
+    import numpy as np
+    from dysgu_b200 import batch, callers
+    rng = np.random.default_rng(5)
+    cigs, off = [], [0]
+    for i in range(300):
+        nops = int(rng.integers(0, 9)) if i % 7 else 0
+        ops = []
+        for j in range(nops):
+            op = 0 if j % 2 == 0 else int(rng.integers(1, 3))
+            ops.append((int(rng.integers(1, 400 if op == 0 else 40)) << 4) | op)
+        cigs += ops
+        off.append(len(cigs))
+    r = batch.SwResults(np.zeros((300, 8), np.int32), np.array(cigs, dtype=np.uint32), np.array(off, dtype=np.int64), np.zeros(300, np.int32))
+    st = r.cigar_stats()
+    for max_gap, tol in ((30, 0.1), (15, 0.02), (1000, 1.0)):
+        got = callers.matches_with_max_gap_batch(r, max_gap, tol)
+        for i in range(300):
+            s = r.cigar_str(i)
+            matches = gaps = 0
+            want = None
+            for num, op in re.findall(r"(\d+)([MID])", s):
+                num = int(num)
+                if op in "DI":
+                    if num > max_gap:
+                        want = 0
+                        break
+                    gaps += num
+                else:
+                    matches += num
+            if want is None:
+                want = 0 if (matches and np.float32(gaps) / np.float32(matches) > np.float32(tol)) else matches
+            assert got[i] == want, (s, max_gap, tol)
+    assert st.shape == (300, 3) and (st[np.diff(off) == 0] == 0).all()
