@@ -121,6 +121,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (before any pinned allocation), so that the
+    page-locked staging buffers of the end-to-end arm are local to the GPU's PCIe root.  Returns a short note."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return "numa: node %d has no CPU in this process's cpuset" % node
+        os.sched_setaffinity(0, allowed)
+        return "numa: node %d, %d cpus" % (node, len(allowed))
+    except Exception as exc:
+        return "numa: not bound (%s)" % str(exc)[:60]
+
+
 def pinned_array(L, shape, dtype):
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     ptr = L.db200_host_alloc(max(n, 1))
@@ -222,6 +246,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the alignment engine has no CPU fallback")
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "numa: not bound (single GPU)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -433,7 +458,8 @@ def run_ours(args):
         "dtype": "int16" if kind == "sw" else "u64", "data": "synthetic",
         "config": {"workload": WORKLOADS[name][4],
                    "pairs_per_step_per_gpu": n, "cells_per_step_per_gpu": cells, "input_bytes_per_step_per_gpu": q_bytes + t_bytes,
-                   "l2": "inputs larger than L2 (%.0f MB per step)" % ((q_bytes + t_bytes) / 1e6), "sharding": "pairs by rank, no collective"},
+                   "l2": "inputs larger than L2 (%.0f MB per step)" % ((q_bytes + t_bytes) / 1e6), "sharding": "pairs by rank, no collective",
+                   "host": numa_note},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": 1e3 * float(tdt.item()) / e2e_steps},

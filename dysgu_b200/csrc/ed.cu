@@ -33,6 +33,7 @@ struct EdPrepArgs {
     int32_t *hlog_words;
     int32_t *hist;         // [ED_NCFG * ED_LBINS]
     db200_ed_result *results;
+    uint32_t *tsets;       // [npairs][8] symbol set of every target (reused by ed_build_kernel)
     int32_t band;          // NW: route pairs through the banded rounds (segments = rounds instead of configurations)
     int32_t *fb_tasks;     // NW + band: pairs that go straight to the full-column kernel, per configuration
     int32_t *fb_count;
@@ -44,15 +45,25 @@ struct EdPrepArgs {
 __device__ __forceinline__ uint32_t symbol_set_word(const uint8_t *s, int len, int lane)
 {
     uint64_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    for (int i = lane; i < len; i += 32) {
-        const uint32_t c = s[i];
+    auto add = [&](uint32_t c) {
         const uint64_t bit = 1ull << (c & 63u);
         const uint32_t hi = c >> 6;
         b0 |= hi == 0 ? bit : 0ull;
         b1 |= hi == 1 ? bit : 0ull;
         b2 |= hi == 2 ? bit : 0ull;
         b3 |= hi == 3 ? bit : 0ull;
+    };
+    // bytes up to the first word boundary, then four symbols per 32-bit load, then the tail
+    const int head = min(len, (int)((4u - (unsigned)(reinterpret_cast<uintptr_t>(s) & 3u)) & 3u));
+    const int nw4 = (len - head) >> 2;
+    if (lane < head) add(s[lane]);
+    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(s + head);
+    for (int i = lane; i < nw4; i += 32) {
+        const uint32_t x = s4[i];
+        add(x & 0xFFu); add((x >> 8) & 0xFFu); add((x >> 16) & 0xFFu); add(x >> 24);
     }
+    const int tail0 = head + 4 * nw4;
+    if (tail0 + lane < len) add(s[tail0 + lane]);
     uint32_t w[8] = {(uint32_t)b0, (uint32_t)(b0 >> 32), (uint32_t)b1, (uint32_t)(b1 >> 32),
                      (uint32_t)b2, (uint32_t)(b2 >> 32), (uint32_t)b3, (uint32_t)(b3 >> 32)};
     uint32_t mine = 0;
@@ -74,6 +85,7 @@ __global__ void ed_prep_kernel(EdPrepArgs a)
     const int m = (int)(a.qoff[p + 1] - q0), n = (int)(a.toff[p + 1] - t0);
     const uint32_t qs = symbol_set_word(a.qbuf + q0, m, lane);
     const uint32_t ts = symbol_set_word(a.tbuf + t0, n, lane);
+    if (lane < 8) a.tsets[p * 8 + lane] = ts;
     int au = 0, at = 0;
     if (lane < 8) { au = __popc(qs | ts); at = __popc(ts); }
     for (int o = 4; o >= 1; o >>= 1) { au += __shfl_xor_sync(0xFFFFFFFFu, au, o); at += __shfl_xor_sync(0xFFFFFFFFu, at, o); }
@@ -141,6 +153,7 @@ struct EdBuildArgs {
     int32_t *bin_fill;
     int32_t *tasks;
     int32_t band;
+    const uint32_t *tsets;
 };
 
 // one warp per pair: target symbols -> dense row ids, re-coded target, match vectors of the query
@@ -157,10 +170,7 @@ __global__ void ed_build_kernel(EdBuildArgs a)
     pr.peq_off = a.peq_off[p];
     pr.hlog_off = a.hlog_off[p];
     const uint8_t *q = a.qbuf + pr.q_off, *t = a.tbuf + pr.t_off;
-    {
-        const uint32_t ts = symbol_set_word(t, pr.n, lane);
-        if (lane < 8) tset[warp][lane] = ts;
-    }
+    if (lane < 8) tset[warp][lane] = a.tsets[p * 8 + lane];
     __syncwarp();
     // rank of every byte among the target's symbols (0xFF: not a target symbol)
     for (int c = lane; c < 256; c += 32) {
@@ -274,8 +284,10 @@ __global__ void ed_count_kernel(EdCountArgs a)
         int score = pr.m;
         int mn = col_m1 ? pr.m : 0x7FFFFFFF;
         int c = col_m1 ? 1 : 0;
+        uint32_t word = 0;
         for (int j = 0; j < pr.n; ++j) {
-            const uint32_t d = (hl[j >> 4] >> ((j & 15) * 2)) & 3u;
+            if ((j & 15) == 0) word = hl[j >> 4];
+            const uint32_t d = (word >> ((j & 15) * 2)) & 3u;
             score += (int)(d & 1u) - (int)(d >> 1);
             if (score < mn) { mn = score; c = 1; }
             else if (score == mn) ++c;
@@ -320,12 +332,45 @@ struct EdEmitArgs {
 __global__ void ed_emit_kernel(EdEmitArgs a)
 {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= a.npairs) return;
-    EdPair &pr = a.pairs[p];
-    const int64_t o = a.loc_off[p];
-    pr.loc_off = o;
-    if (pr.nloc <= 0) return;
-    if (o + pr.nloc > a.loc_cap) { atomicExch(a.overflow, 1); return; }
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const bool want_rev = (a.mode == DB200_ED_MODE_HW && a.task >= DB200_ED_TASK_LOC);
+    // every lane takes part in the reservation below, so nothing returns before it
+    bool live = p < a.npairs;
+    EdPair *prp = live ? &a.pairs[p] : nullptr;
+    int64_t o = 0;
+    if (live) {
+        o = a.loc_off[p];
+        prp->loc_off = o;
+        if (prp->nloc <= 0) live = false;
+        else if (o + prp->nloc > a.loc_cap) { atomicExch(a.overflow, 1); live = false; }
+    }
+    const bool col_m1 = live && !prp->special && (prp->m & 63) != 0 && prp->m == prp->best;   // the -1 end location needs no start search
+    const int ntask = (live && want_rev && !prp->special) ? prp->nloc - (col_m1 ? 1 : 0) : 0;
+    // slots in the start-location task list of the pair's configuration: one atomic per warp and configuration
+    // (a slot per location used to cost one returning atomic each on a handful of addresses)
+    int slot = 0;
+    {
+        const int key = ntask > 0 ? prp->cfg : -1;
+        unsigned todo = __ballot_sync(FULL, key >= 0);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int k = __shfl_sync(FULL, key, leader);
+            const bool mine = key == k;
+            const int v = mine ? ntask : 0;
+            int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
+            const int total = __shfl_sync(FULL, inc, 31);
+            int b = 0;
+            if (lane == leader) b = atomicAdd(&a.rev_fill[k], total);
+            b = __shfl_sync(FULL, b, leader);
+            if (mine) slot = a.rev_begin[k] + b + inc - v;
+            todo &= ~__ballot_sync(FULL, mine);
+        }
+    }
+    if (!live) return;
+    EdPair &pr = *prp;
     int32_t *out = a.loc_buf + 2 * o;
     if (pr.special) {
         out[0] = DB200_ED_NO_START;
@@ -335,12 +380,13 @@ __global__ void ed_emit_kernel(EdEmitArgs a)
     const int start_fixed = (a.task >= DB200_ED_TASK_LOC) ? 0 : DB200_ED_NO_START;
     if (a.mode == DB200_ED_MODE_NW) { out[0] = start_fixed; out[1] = pr.n - 1; return; }
     const uint32_t *hl = a.hlog + pr.hlog_off;
-    const bool want_rev = (a.mode == DB200_ED_MODE_HW && a.task >= DB200_ED_TASK_LOC);
     int w = 0;
     int score = pr.m;
     if ((pr.m & 63) != 0 && score == pr.best) { out[0] = start_fixed; out[1] = -1; ++w; }
+    uint32_t word = 0;
     for (int j = 0; j < pr.n; ++j) {
-        const uint32_t d = (hl[j >> 4] >> ((j & 15) * 2)) & 3u;
+        if ((j & 15) == 0) word = hl[j >> 4];
+        const uint32_t d = (word >> ((j & 15) * 2)) & 3u;
         score += (int)(d & 1u) - (int)(d >> 1);
         if (score == pr.best) {
             out[2 * w] = start_fixed;
@@ -348,8 +394,7 @@ __global__ void ed_emit_kernel(EdEmitArgs a)
             if (want_rev) {
                 const int64_t idx = o + w;
                 a.loc_pair[idx] = (int32_t)p;
-                const int pos = a.rev_begin[pr.cfg] + atomicAdd(&a.rev_fill[pr.cfg], 1);
-                a.rev_tasks[pos] = (int32_t)idx;
+                a.rev_tasks[slot++] = (int32_t)idx;
             }
             ++w;
         }
@@ -443,6 +488,7 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     int64_t *scan_tmp = ws.alloc<int64_t>(scan_tmp_count(npairs) * 2);
     int32_t *bins = ws.alloc<int32_t>(nbins * 3 + 512);
     int32_t *tasks = ws.alloc<int32_t>(npairs);
+    uint32_t *tsets = ws.alloc<uint32_t>((size_t)npairs * 8);
     uint8_t *tcodes = ws.alloc<uint8_t>((size_t)t_bytes + 64);
     uint32_t *hlog = ws.alloc<uint32_t>((size_t)(t_bytes / 16 + npairs + 64));
     int32_t *nw_score = ws.alloc<int32_t>(npairs);
@@ -456,7 +502,7 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     int32_t *carry = band ? ws.alloc<int32_t>((size_t)npairs * ED_BAND_ROUNDS) : nullptr;
     int32_t *fb_tasks = band ? ws.alloc<int32_t>((size_t)npairs * ED_NCFG) : nullptr;
     if (band && (!carry || !fb_tasks)) { set_error("ed_batch: device workspace allocation failed"); return DB200_ERR_NOMEM; }
-    if (!pairs || !peq_words || !hlog_words || !peq_off || !hlog_off || !scan_tmp || !bins || !tasks || !tcodes || !hlog ||
+    if (!pairs || !peq_words || !hlog_words || !peq_off || !hlog_off || !scan_tmp || !bins || !tasks || !tsets || !tcodes || !hlog ||
         !nw_score || !nloc || !loc_pair || !rev_tasks || !eq_dev) {
         set_error("ed_batch: device workspace allocation failed");
         return DB200_ERR_NOMEM;
@@ -482,7 +528,7 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     pa.qbuf = d_qbuf; pa.tbuf = d_tbuf; pa.qoff = d_qoff; pa.toff = d_toff; pa.k = d_k; pa.k_default = prm->k;
     pa.mode = prm->mode; pa.task = prm->task; pa.npairs = npairs; pa.pairs = pairs; pa.peq_words = peq_words;
     pa.hlog_words = hlog_words; pa.hist = hist; pa.results = d_results;
-    pa.band = band ? 1 : 0; pa.fb_tasks = fb_tasks; pa.fb_count = fb_count; pa.fb_stride = npairs;
+    pa.tsets = tsets; pa.band = band ? 1 : 0; pa.fb_tasks = fb_tasks; pa.fb_count = fb_count; pa.fb_stride = npairs;
     ed_prep_kernel<<<gwarp, TB, 0, st>>>(pa);
     count_launch(e);
     exclusive_scan_i32_i64(e, peq_words, peq_off, npairs, scan_tmp, st);
@@ -501,7 +547,7 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     EdBuildArgs ba;
     ba.qbuf = d_qbuf; ba.tbuf = d_tbuf; ba.pairs = pairs; ba.peq_off = peq_off; ba.hlog_off = hlog_off; ba.npairs = npairs;
     ba.peq = peq; ba.tcodes = tcodes; ba.mode = prm->mode; ba.task = prm->task; ba.eq_pairs = eq_dev; ba.n_eq_pairs = prm->n_eq_pairs;
-    ba.bin_start = bin_start; ba.bin_fill = bin_fill; ba.tasks = tasks; ba.band = band ? 1 : 0;
+    ba.bin_start = bin_start; ba.bin_fill = bin_fill; ba.tasks = tasks; ba.band = band ? 1 : 0; ba.tsets = tsets;
     ed_build_kernel<<<gwarp, TB, 0, st>>>(ba);
     count_launch(e);
     prof_mark(e, st, ST_ED_PREP);
