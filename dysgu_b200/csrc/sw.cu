@@ -313,7 +313,21 @@ struct FinalArgs {
     int32_t *status_out;
     int64_t npairs;
     int32_t flag, filters, filterd;
+    const int32_t *pipe_abort;   // set if a pipelined pass gave up waiting for its predecessor (never expected)
+    int32_t tiled_from;          // targets longer than this run in the column-tiled kernel
+    int32_t defer_second_from;   // targets longer than this leave the second-best scan to sw_second_best_kernel (0: never)
 };
+
+// second best over the columns outside the mask window (ssw.c:326-341 / 530-543): the per-column maxima of the query
+// padded with P phantom rows (ssw.c:109 / 364).  Columns lo <= j < hi, stride `step`; first column holding the maximum.
+__device__ __forceinline__ void second_best_scan(const int16_t *cm, const int16_t *lr, int P, int lo, int hi, int step, int &best, int &bref)
+{
+    for (int j = lo; j < hi; j += step) {
+        int x = cm[j];
+        for (int k = 0; k < P && j - 1 - k >= 0; ++k) x = max(x, (int)lr[j - 1 - k]);
+        if (x > best) { best = x; bref = j; }
+    }
+}
 
 __global__ void sw_finalize_kernel(FinalArgs a)
 {
@@ -329,6 +343,13 @@ __global__ void sw_finalize_kernel(FinalArgs a)
         return;
     }
     const PairMeta pm = a.meta[p];
+    if (a.pipe_abort && *a.pipe_abort && pm.n > a.tiled_from) {
+        // not a result: reported like scratch exhaustion so that the host entry point re-runs the pair in a small group
+        s.status = DB200_PAIR_NOSCRATCH;
+        a.results[p] = r;
+        if (a.status_out) a.status_out[p] = s.status;
+        return;
+    }
     const PassOut fw = a.fwd[p], rv = a.rev[p];
     const int score = fw.score;
     r.score1 = score;
@@ -347,21 +368,15 @@ __global__ void sw_finalize_kernel(FinalArgs a)
         const int16_t *lr = cm + pm.n;
         const int L = s.use_word ? 8 : 16;
         const int P = ((pm.m + L - 1) / L) * L - pm.m; // padded profile rows
-        int best = 0, bref = 0;
-        int edge = max(r.ref_end1 - s.mask_len, 0);
-        for (int j = 0; j < edge; ++j) {
-            int x = cm[j];
-            for (int k = 0; k < P && j - 1 - k >= 0; ++k) x = max(x, (int)lr[j - 1 - k]);
-            if (x > best) { best = x; bref = j; }
+        if (a.defer_second_from > 0 && pm.n > a.defer_second_from) {
+            s.need_colmax = 2;   // long target: a warp scans the columns (sw_second_best_kernel)
+        } else {
+            int best = 0, bref = 0;
+            second_best_scan(cm, lr, P, 0, max(r.ref_end1 - s.mask_len, 0), 1, best, bref);
+            second_best_scan(cm, lr, P, min(r.ref_end1 + s.mask_len, pm.n) + (s.use_word ? 0 : 1), pm.n, 1, best, bref);
+            r.score2 = best;
+            r.ref_end2 = bref;
         }
-        edge = min(r.ref_end1 + s.mask_len, pm.n);
-        for (int j = edge + (s.use_word ? 0 : 1); j < pm.n; ++j) {
-            int x = cm[j];
-            for (int k = 0; k < P && j - 1 - k >= 0; ++k) x = max(x, (int)lr[j - 1 - k]);
-            if (x > best) { best = x; bref = j; }
-        }
-        r.score2 = best;
-        r.ref_end2 = bref;
     }
     // ---- begin coordinates ------------------------------------------------------------------------
     const bool want_begin = !(a.flag == 0 || (a.flag == 2 && score < a.filters));
@@ -381,6 +396,36 @@ __global__ void sw_finalize_kernel(FinalArgs a)
     }
     a.results[p] = r;
     if (a.status_out) a.status_out[p] = s.status;
+}
+
+// one warp per pair marked by sw_finalize_kernel: lanes stride over the columns, then (largest value, smallest column)
+__global__ void sw_second_best_kernel(FinalArgs a)
+{
+    const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= a.npairs) return;
+    const PairState &s = a.state[p];
+    if (s.status != DB200_PAIR_OK || s.need_colmax != 2) return;
+    const PairMeta pm = a.meta[p];
+    const int ref_end1 = a.results[p].ref_end1;
+    const int16_t *cm = a.colmax + a.colmax_off[p];
+    const int16_t *lr = cm + pm.n;
+    const int L = s.use_word ? 8 : 16;
+    const int P = ((pm.m + L - 1) / L) * L - pm.m;
+    int best = 0, bref = 0;
+    second_best_scan(cm, lr, P, lane, max(ref_end1 - s.mask_len, 0), 32, best, bref);
+    second_best_scan(cm, lr, P, min(ref_end1 + s.mask_len, pm.n) + (s.use_word ? 0 : 1) + lane, pm.n, 32, best, bref);
+    // value in the high bits, complemented column in the low bits: the maximum is the first column holding the best value
+    unsigned long long key = ((unsigned long long)(unsigned)best << 32) | (unsigned)(0x7FFFFFFF - bref);
+    for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+        key = other > key ? other : key;
+    }
+    if (lane == 0) {
+        const int b = (int)(key >> 32);
+        a.results[p].score2 = b;
+        a.results[p].ref_end2 = b > 0 ? 0x7FFFFFFF - (int)(key & 0xFFFFFFFFu) : 0;
+    }
 }
 
 }  // namespace db200
@@ -426,9 +471,63 @@ __global__ void sw_cigar_gather_kernel(const PairState *state, int64_t npairs, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// pipelined column tiles: the tasks of a column-tiled segment are expanded into (pair, pass) units
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_MULTI_COLS = 2048;   // columns per pass of the column-tiled kernel (K = 32, G = 32)
+
+__global__ void sw_npass_kernel(const int32_t *tasks, const int32_t *seg_begin, const int32_t *seg_count, int seg, const PairMeta *meta,
+                                int64_t npairs, int32_t *lens)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    int v = 0;
+    if (i < seg_count[seg]) v = max(1, (meta[tasks[seg_begin[seg] + i]].n + SW_MULTI_COLS - 1) / SW_MULTI_COLS);
+    lens[i] = v;
+}
+
+struct ExpandArgs {
+    const int32_t *tasks, *seg_begin, *seg_count;
+    int32_t seg;
+    const PairMeta *meta;
+    const int64_t *vt_off;       // exclusive scan of the pass counts, in task order (longest queries first)
+    int32_t *vt_pair, *vt_pass;
+    long long *bnd_off;
+    unsigned long long *bnd_cursor;
+    unsigned long long bnd_cap;
+    int32_t pipe_max_tasks;      // segments with more tasks than this keep one warp per pair
+};
+
+__global__ void sw_expand_kernel(ExpandArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.seg_count[a.seg]) return;
+    const int pair = a.tasks[a.seg_begin[a.seg] + i];
+    const PairMeta pm = a.meta[pair];
+    const int npass = max(1, (pm.n + SW_MULTI_COLS - 1) / SW_MULTI_COLS);
+    const int64_t base = a.vt_off[i];
+    long long off = -1;
+    if (npass > 1) {
+        // right-edge columns of every pass but the last, rows padded to 32 (what sw_pass_kernel indexes)
+        const unsigned long long need = (unsigned long long)((pm.m + 31) & ~31) * (unsigned long long)(npass - 1);
+        const unsigned long long o = atomicAdd(a.bnd_cursor, need);
+        off = (o + need <= a.bnd_cap) ? (long long)o : -1;
+        a.bnd_off[pair] = off;
+    }
+    // Without room for its boundary columns a pair cannot be pipelined: its first unit runs all passes in one warp.
+    // The same holds for every pair of a large segment: with more pairs than the GPU has warps for, one warp per pair
+    // already fills the machine and the hand-over between warps only costs (B200, long-read contigs 1-10 kb, forward
+    // stage: 1,000 pairs 25.5 -> 7.1 ms, 4,000 pairs 27.2 -> 17.0 ms, but 16,000 pairs 52.3 -> 66.7 ms when pipelined).
+    const bool seq = npass > 1 && (off < 0 || a.seg_count[a.seg] > a.pipe_max_tasks);
+    for (int ps = 0; ps < npass; ++ps) {
+        a.vt_pair[base + ps] = pair;
+        a.vt_pass[base + ps] = seq ? (ps == 0 ? -1 : -2) : ps;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
-template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG>
+template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG, bool PIPE = false>
 static int launch_pass(Engine *e, const PassArgs &a, cudaStream_t st)
 {
     constexpr int NCH = K / 8, ROW = 2 * NCH * 32;
@@ -436,15 +535,15 @@ static int launch_pass(Engine *e, const PassArgs &a, cudaStream_t st)
     static int blocks_cached[16] = {0};
     int &blocks = blocks_cached[e->device & 15];
     if (blocks == 0) {
-        DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG>,
+        DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG, PIPE>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG>, SW_PASS_THREADS, smem));
+        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG, PIPE>, SW_PASS_THREADS, smem));
         if (per_sm < 1) per_sm = 1;
         if (MULTI && per_sm * (SW_PASS_THREADS / 32) > SW_MULTI_MAX_WARPS_PER_SM) per_sm = SW_MULTI_MAX_WARPS_PER_SM / (SW_PASS_THREADS / 32);
         blocks = e->sm_count * per_sm;
     }
-    sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG><<<blocks, SW_PASS_THREADS, smem, st>>>(a);
+    sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG, PIPE><<<blocks, SW_PASS_THREADS, smem, st>>>(a);
     count_launch(e);
     DB200_CUDA_CHECK(cudaGetLastError());
     return DB200_OK;
@@ -549,6 +648,34 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     const size_t bnd_cap = (size_t)std::min<int64_t>(2 * (q_bytes + 32 * npairs) * max_extra_passes, (int64_t)1 << 30); // forward + reverse
     uint32_t *bnd_pool = ws.alloc<uint32_t>(bnd_cap + 64);
     long long *bnd_off = ws.alloc<long long>(2 * (size_t)npairs);
+    // Pipelined column tiles (sw_pass_kernel PIPE): only when a target can exceed the widest single-pass configuration and
+    // the batch is small enough for the hand-over between warps to pay.  The pair count of the batch bounds the number of
+    // column-tiled pairs from above; beyond pipe_max_tasks the plain kernel runs (its instantiation is also ~10 % faster
+    // than the PIPE instantiation running one warp per pair: 16,000 long-read contigs 52.5 vs 58.3 ms forward).
+    int pipe_max_tasks = 6144;
+    if (const char *pt = getenv("DB200_SW_PIPE_MAX_TASKS")) pipe_max_tasks = atoi(pt);
+    const bool pipe = max_query_len > 0 && max_target_len > CFG_CAP[SW_NCFG - 2] && npairs <= pipe_max_tasks && !getenv("DB200_SW_NO_PIPE");
+    const size_t vt_cap = pipe ? (size_t)(t_bytes / SW_MULTI_COLS + npairs + 16) : 0;
+    constexpr int NPIPE = 3;   // forward without / with column maxima, reverse
+    int32_t *vt_len = nullptr, *vt_pair = nullptr, *vt_pass = nullptr, *vt_prog = nullptr, *pair_done = nullptr;
+    int64_t *vt_off = nullptr, *vt_scan_tmp = nullptr;
+    PassOut *vt_res = nullptr;
+    if (pipe) {
+        vt_len = ws.alloc<int32_t>((size_t)npairs * NPIPE);
+        vt_off = ws.alloc<int64_t>((size_t)(npairs + 1) * NPIPE);
+        vt_scan_tmp = ws.alloc<int64_t>(scan_tmp_count(npairs) * NPIPE);
+        vt_pair = ws.alloc<int32_t>(vt_cap * NPIPE);
+        vt_pass = ws.alloc<int32_t>(vt_cap * NPIPE);
+        vt_prog = ws.alloc<int32_t>(vt_cap * NPIPE);
+        vt_res = ws.alloc<PassOut>(vt_cap * NPIPE);
+        pair_done = ws.alloc<int32_t>((size_t)npairs * 2);
+        if (!vt_len || !vt_off || !vt_scan_tmp || !vt_pair || !vt_pass || !vt_prog || !vt_res || !pair_done) {
+            set_error("sw_batch: device workspace allocation failed");
+            return DB200_ERR_NOMEM;
+        }
+        DB200_CUDA_CHECK(cudaMemsetAsync(vt_prog, 0, vt_cap * NPIPE * sizeof(int32_t), st));
+        DB200_CUDA_CHECK(cudaMemsetAsync(pair_done, 0, (size_t)npairs * 2 * sizeof(int32_t), st));
+    }
     const int wide_blocks = std::min(e->sm_count * 4, 1024);
     const size_t slab_bytes = (e->trace_slab_bytes / (size_t)wide_blocks) & ~(size_t)255;
     uint8_t *slab = ws.alloc<uint8_t>(slab_bytes * (size_t)wide_blocks);
@@ -614,6 +741,28 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     int counter_idx = 0;
     const bool can_multi = max_query_len > 0;
 
+    // column-tiled segment `seg` of the task list in `pa`, pipelined: expand it into (pair, pass) units, then one warp per unit
+    auto launch_piped = [&](int which, bool colmax, PassArgs pp, cudaStream_t ls) -> int {
+        int32_t *len_w = vt_len + (size_t)npairs * which;
+        int64_t *off_w = vt_off + (size_t)(npairs + 1) * which;
+        sw_npass_kernel<<<gpair, TB, 0, ls>>>(pp.tasks, pp.seg_begin, pp.seg_count, pp.seg, pp.meta, npairs, len_w);
+        count_launch(e);
+        exclusive_scan_i32_i64(e, len_w, off_w, npairs, vt_scan_tmp + scan_tmp_count(npairs) * which, ls);
+        ExpandArgs xa;
+        xa.tasks = pp.tasks; xa.seg_begin = pp.seg_begin; xa.seg_count = pp.seg_count; xa.seg = pp.seg; xa.meta = pp.meta;
+        xa.vt_off = off_w; xa.vt_pair = vt_pair + vt_cap * which; xa.vt_pass = vt_pass + vt_cap * which;
+        xa.bnd_off = pp.bnd_off; xa.bnd_cursor = pp.bnd_cursor; xa.bnd_cap = pp.bnd_cap;
+        xa.pipe_max_tasks = pipe_max_tasks;
+        sw_expand_kernel<<<gpair, TB, 0, ls>>>(xa);
+        count_launch(e);
+        pp.vt_pair = xa.vt_pair; pp.vt_pass = xa.vt_pass; pp.vt_total = off_w + npairs;
+        pp.vt_prog = vt_prog + vt_cap * which; pp.vt_res = vt_res + vt_cap * which;
+        pp.pair_done = pair_done + (which == 2 ? npairs : 0);
+        pp.abort_flag = counters + 148;
+        return colmax ? launch_pass<32, 32, true, true, false, false, true>(e, pp, ls)
+                      : launch_pass<32, 32, false, true, false, false, true>(e, pp, ls);
+    };
+
     // 3. forward pass per segment, then the exact re-run of pairs with an ambiguous end row -----------
     { const int rc = aux_fork(e, st); if (rc) return rc; }
     int aux_i = 0;
@@ -626,7 +775,8 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         pa.out = fwd;
         pa.amb_list = amb_f; pa.amb_count = amb_count_f + 2 * cfg; pa.amb_base_seg = 2 * cfg;
         int rc;
-        if (cmx && tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<true, false, true>(e, cfg, pa, ls); }
+        if (cfg == SW_NCFG - 1 && pipe) { pa.sc = sc; rc = launch_piped(cmx, cmx != 0, pa, ls); }
+        else if (cmx && tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<true, false, true>(e, cfg, pa, ls); }
         else if (cmx) { pa.sc = sc; rc = launch_cfg<true, false, false>(e, cfg, pa, ls); }
         else if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
         else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, ls); }
@@ -668,7 +818,8 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         pa.out = rev;
         pa.amb_list = amb_r; pa.amb_count = amb_count_r + 2 * cfg; pa.amb_base_seg = 2 * cfg;
         int rc;
-        if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
+        if (cfg == SW_NCFG - 1 && pipe) { pa.sc = sc; rc = launch_piped(2, false, pa, ls); }
+        else if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
         else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, ls); }
         if (rc) return rc;
     }
@@ -691,7 +842,10 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     fa.fwd = fwd; fa.rev = rev; fa.meta = meta; fa.state = state; fa.colmax = colmax; fa.colmax_off = colmax_off;
     fa.results = d_results; fa.status_out = nullptr; fa.npairs = npairs;
     fa.flag = prm->flag; fa.filters = prm->filters; fa.filterd = prm->filterd;
+    fa.pipe_abort = pipe ? counters + 148 : nullptr; fa.tiled_from = CFG_CAP[SW_NCFG - 2];
+    fa.defer_second_from = max_target_len > 512 ? 512 : 0;
     sw_finalize_kernel<<<gpair, TB, 0, st>>>(fa);
+    if (fa.defer_second_from > 0) { sw_second_best_kernel<<<gwarp_pair, TB, 0, st>>>(fa); count_launch(e); }
     prof_mark(e, st, ST_FINALIZE);
     TraceArgs ta;
     ta.pool = reinterpret_cast<const uint4 *>(pool); ta.meta = meta; ta.state = state; ta.results = d_results; ta.npairs = npairs;

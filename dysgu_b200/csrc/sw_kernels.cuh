@@ -75,6 +75,14 @@ struct PassArgs {
     int32_t *amb_count;
     int32_t amb_base_seg;
     uint32_t k65536;           // 65536 passed at run time so the score merge stays an IMAD
+    // PIPE (column-tiled pairs, one warp per pass): work units are (pair, pass) entries of an expanded list
+    const int32_t *vt_pair;    // unit -> pair
+    const int32_t *vt_pass;    // unit -> pass; -1: run every pass of the pair in this warp (boundary pool exhausted), -2: nothing to do
+    const int64_t *vt_total;   // number of units
+    int32_t *vt_prog;          // unit -> rows of its right-edge column that are complete (read by the next pass)
+    PassOut *vt_res;           // unit -> candidate of its pass
+    int32_t *pair_done;        // pair -> passes finished; the last one merges the candidates
+    int32_t *abort_flag;       // set when a wait for the producer pass timed out (never expected; avoids a hang)
     SwScoring sc;
 };
 
@@ -96,9 +104,14 @@ __device__ __forceinline__ int pool_code(const uint4 *pool, uint32_t unit, int i
 
 // TAG: scores are pre-scaled by 2^TAGB (host side) and the column index inside the virtual lane rides in the low
 // bits of the running maximum, so the best cell's column and row are exact without per-column maxima.
-template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG>
+// PIPE: the passes (2048-column tiles) of one long pair are work units of their own, taken by different warps.  Pass p
+// consumes the right-edge column of pass p-1 in 32-row chunks as soon as they are complete (a progress word per unit),
+// so the tiles of a 10 kb x 10 kb pair run as a pipeline of five warps instead of one warp after the other.  Units are
+// dispensed in list order and a pass only ever waits for the unit right before it, which a resident warp already holds.
+template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG, bool PIPE = false>
 __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS_MIN_BLOCKS : 1) sw_pass_kernel(PassArgs a)
 {
+    static_assert(!PIPE || (MULTI && !WATCH), "pipelined passes are the column-tiled scoring kernel");
     constexpr int V = 2 * G;          // virtual lanes per group
     constexpr int C = V * K;          // columns per pass
     constexpr int NCH = K / 8;        // 16-byte units per half strip (sizing only)
@@ -138,10 +151,17 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
         if (lane == 0) base = atomicAdd(a.counter, GROUPS);
         __syncwarp();
         base = __shfl_sync(FULL, base, 0);
-        if (base >= seg_count) break;
+        int my_pass = -1;                  // PIPE: the pass this unit stands for (-1: all passes, as without PIPE)
+        if (PIPE) {
+            if ((int64_t)base >= *a.vt_total) break;
+            my_pass = a.vt_pass[base];
+            if (my_pass == -2) continue;
+        } else {
+            if (base >= seg_count) break;
+        }
         const int ti = base + grp;
-        const bool active = grp < GROUPS && ti < seg_count;
-        const int pair = active ? a.tasks[seg_begin + ti] : -1;
+        const bool active = PIPE ? true : (grp < GROUPS && ti < seg_count);
+        const int pair = PIPE ? a.vt_pair[base] : (active ? a.tasks[seg_begin + ti] : -1);
         PairMeta pm;
         pm.q_unit = 0; pm.t_unit = 0; pm.m = 0; pm.n = 0;
         if (active) pm = a.meta[pair];
@@ -166,7 +186,10 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
         if (MULTI && active && npass > 1) {
             bstride = (m + 31) & ~31;
             long long off = -1;
-            if (!WATCH) {
+            if (PIPE) {
+                off = a.bnd_off[pair];     // assigned by sw_expand_kernel
+                if (my_pass >= 0) { ps_first = my_pass; ps_last = my_pass + 1; }
+            } else if (!WATCH) {
                 if (lane == 0) {
                     const unsigned long long need = (unsigned long long)bstride * (unsigned long long)(npass - 1);
                     const unsigned long long o = atomicAdd(a.bnd_cursor, need);
@@ -249,6 +272,35 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
                 cur = __funnelshift_r(prevw, neww, phi4);
                 prevw = neww;
               }
+              if (MULTI && (t8 & 3) == 0) {
+                // every 32 rows, outside the unrolled row loop (which stays the same code with and without PIPE):
+                // publish what this pass has completed, then fetch the next 32 rows of the left neighbour's right edge
+                const int t = t8 * 8;
+                if (PIPE && my_pass >= 0 && ps + 1 < npass && t >= 96) {
+                    // the chunk stored at step t - 2 ends at row t - 65: rows below ((t - 64) & ~31) are complete
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) *(volatile int32_t *)(a.vt_prog + base) = min((t - 64) & ~31, m);
+                }
+                const uint32_t *src = pbnd ? pbnd + (size_t)(ps - 1) * bstride : bnd;
+                if (PIPE && my_pass > 0 && t < m) {
+                    const int need = min(t + 32, m);
+                    if (lane == 0) {
+                        const volatile int32_t *pg = a.vt_prog + (base - 1);
+                        unsigned spins = 0;
+#pragma unroll 1
+                        while (*pg < need && *(volatile int32_t *)a.abort_flag == 0) {
+                            __nanosleep(100);
+                            if (++spins > (1u << 24)) { atomicExch(a.abort_flag, 1); break; }
+                        }
+                    }
+                    __syncwarp();
+                    __threadfence();
+                    bchunk = (t + lane < m) ? __ldcg(src + t + lane) : 0u;
+                } else {
+                    bchunk = (ps > 0 && t + lane < m) ? src[t + lane] : 0u;
+                }
+              }
 #pragma unroll UNR
               for (int b = 0; b < 8; ++b) {
                 const int t = t8 * 8 + b;
@@ -262,10 +314,6 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
                     sv = __shfl_sync(FULL, OV, lane - 1);
                 }
                 if (MULTI) {
-                    if ((t & 31) == 0) {
-                        const uint32_t *src = pbnd ? pbnd + (size_t)(ps - 1) * bstride : bnd;
-                        bchunk = (ps > 0 && t + lane < m) ? src[t + lane] : 0u;
-                    }
                     const uint32_t y = __shfl_sync(FULL, bchunk, t & 31);
                     if (lig == 0) { sh = y << 16; sv = y & 0xFFFF0000u; }
                 } else {
@@ -349,6 +397,11 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
               }
             }
 
+            if (PIPE && my_pass >= 0 && ps + 1 < npass) {   // the whole right edge of this pass is in place
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) *(volatile int32_t *)(a.vt_prog + base) = m;
+            }
             // ---- end of pass: column maxima, lane winners -----------------------------------------
             if (COLMAX && active) {
                 int16_t *cm = a.colmax + a.colmax_off[pair];
@@ -410,7 +463,33 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
             }
         }
 
-        if (active && lig == 0) {
+        if (PIPE && my_pass >= 0 && npass > 1) {
+            // one pass of a pipelined pair: leave the candidate, the pass that finishes last merges them in pass order
+            // (first strictly greater score wins, as the sequential loop above does)
+            if (lane == 0) {
+                PassOut c;
+                c.score = run_score; c.end_t = run_slot; c.end_q = run_row; c.amb = run_amb;
+                a.vt_res[base] = c;
+                __threadfence();
+                const int done = atomicAdd(a.pair_done + pair, 1);
+                if (done == npass - 1) {
+                    __threadfence();
+                    const volatile PassOut *rs = a.vt_res + (base - my_pass);
+                    PassOut o;
+                    o.score = -1; o.end_t = 0; o.end_q = 0; o.amb = 0;
+                    for (int q = 0; q < npass; ++q) {
+                        const int sc_q = rs[q].score;
+                        if (sc_q > o.score) { o.score = sc_q; o.end_t = rs[q].end_t; o.end_q = rs[q].end_q; o.amb = rs[q].amb; }
+                    }
+                    o.amb = (o.amb && o.score > 0) ? 1 : 0;
+                    a.out[pair] = o;
+                    if (o.amb) {
+                        const int pos = atomicAdd(a.amb_count, 1);
+                        a.amb_list[a.seg_begin[a.amb_base_seg] + pos] = pair;
+                    }
+                }
+            }
+        } else if (active && lig == 0) {
             if (WATCH) {
                 a.out[pair].end_q = run_wrow;
                 a.out[pair].amb = run_wrow < 0 ? 2 : 0;

@@ -121,3 +121,32 @@ def test_column_tiled_pairs_with_tied_ends():
     res = batch.sw_align_batch(qs, ts, 2, -3, 10, 1)
     ref = O.oracle_sw(qs, ts, 2, -3, 10, 1)
     compare(qs, ts, res, ref, "tiled ties")
+
+
+def test_pipelined_column_tiles_equal_sequential_tiles():
+    """Targets beyond 2048 columns: the passes of one pair run as a pipeline of warps (sw_pass_kernel PIPE);
+    DB200_SW_NO_PIPE=1 runs them one after the other in one warp.  Both must agree with each other on every field
+    (with and without column maxima, i.e. small and automatic mask lengths) and with the oracle."""
+    import os
+    a, b, prm = workloads.contig_pairs(160, seed=23, platform="ont", lo=1200, hi=9000)
+    qs, ts = a.tolist(), b.tolist()
+    # some pairs swapped so that long targets meet short queries and vice versa, some unrelated
+    for i in range(0, 160, 5):
+        qs[i], ts[i] = ts[i], qs[i]
+    for i in range(3, 160, 16):
+        ts[i] = ts[(i * 7 + 1) % 160]
+    for mask in (None, 15):
+        ml = None if mask is None else np.full(len(qs), mask, np.int32)
+        piped = batch.sw_align_batch(qs, ts, mask_len=ml, **prm)
+        os.environ["DB200_SW_NO_PIPE"] = "1"
+        try:
+            seq = batch.sw_align_batch(qs, ts, mask_len=ml, **prm)
+        finally:
+            del os.environ["DB200_SW_NO_PIPE"]
+        assert (piped.status == 0).all() and (seq.status == 0).all()
+        assert np.array_equal(piped.fixed, seq.fixed), np.nonzero((piped.fixed != seq.fixed).any(axis=1))[0][:10]
+        assert np.array_equal(piped.cigar, seq.cigar) and np.array_equal(piped.cigar_off, seq.cigar_off)
+    sub = list(range(0, 160, 8))
+    res = batch.sw_align_batch([qs[i] for i in sub], [ts[i] for i in sub], **prm)
+    ref = O.oracle_sw([qs[i] for i in sub], [ts[i] for i in sub], prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"])
+    compare([qs[i] for i in sub], [ts[i] for i in sub], res, ref, "pipelined tiles")
