@@ -682,10 +682,11 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     int32_t *narrow_list = ws.alloc<int32_t>(npairs);
     int32_t *medium_list = ws.alloc<int32_t>(npairs);
     int32_t *wide_list = ws.alloc<int32_t>(npairs);
+    int32_t *slab_scalar_list = ws.alloc<int32_t>(npairs);
     if (!units || !unit_off || !scan_tmp || !pool || !meta || !rmeta || !state || !fwd || !rev || !tasks_f || !tasks_r || !amb_f ||
         !amb_r || !colmax_off || !cig_off_tmp || !lens || !colmax || !bins || !cigar_pool || !counters || !boundary || !slab ||
         !bnd_pool || !bnd_off ||
-        !narrow_list || !medium_list || !wide_list) {
+        !narrow_list || !medium_list || !wide_list || !slab_scalar_list) {
         set_error("sw_batch: device workspace allocation failed");
         return DB200_ERR_NOMEM;
     }
@@ -854,8 +855,10 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     ta.overflow_flag = overflow_flag;
     ta.debug = getenv("DB200_DEBUG") ? 1 : 0;
     ta.slab = slab; ta.slab_total = (unsigned long long)slab_bytes * (unsigned long long)wide_blocks;
-    ta.list[0] = narrow_list; ta.list[1] = medium_list; ta.list[2] = wide_list;
+    ta.medium_cursor = reinterpret_cast<unsigned long long *>(counters + 146);
+    ta.list[0] = narrow_list; ta.list[1] = medium_list; ta.list[2] = wide_list; ta.list[3] = slab_scalar_list;
     for (int l = 0; l < 3; ++l) { ta.count[l] = counters + 136 + l; ta.counter[l] = counters + 140 + l; }
+    ta.count[3] = counters + 139;
     const int warp_blocks = e->sm_count * 24;
     ta.coop_blocks[0] = 0; ta.coop_blocks[1] = warp_blocks; ta.coop_blocks[2] = wide_blocks;
     sw_trace_classify_kernel<<<gpair, TB, 0, st>>>(ta);
@@ -867,7 +870,11 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
             DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_trace_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
             attr0_done[e->device & 15] = true;
         }
-        sw_trace_narrow_kernel<<<(unsigned)((npairs + TRACE_NARROW_THREADS - 1) / TRACE_NARROW_THREADS), TRACE_NARROW_THREADS, sm0, st>>>(ta);
+        const unsigned gn = (unsigned)((npairs + TRACE_NARROW_THREADS - 1) / TRACE_NARROW_THREADS);
+        sw_trace_narrow_kernel<<<gn, TRACE_NARROW_THREADS, sm0, st>>>(ta, 0);
+        // the same kernel over the jobs of up to TRACE_MEDIUM_CELLS cells, directions in private regions of the slab
+        sw_trace_narrow_kernel<<<gn, TRACE_NARROW_THREADS, sm0, st>>>(ta, 3);
+        count_launch(e);
     }
     {
         // level 1: one warp per pair (state for 2*62+1 diagonals, 8 KB of walk staging)

@@ -24,18 +24,25 @@ struct TraceArgs {
     unsigned long long *cigar_cursor;
     unsigned long long cigar_cap;
     int32_t *overflow_flag;
-    // work lists per level: 0 = scalar (thread per pair), 1 = one warp per pair, 2 = one block per pair
-    int32_t *list[3];
-    int32_t *count[3];
+    // work lists per level: 0 = scalar (thread per pair, directions in shared memory), 1 = one warp per pair,
+    // 2 = one block per pair, 3 = scalar with the directions in the slab (kept apart from level 0 so that the warps of
+    // either launch hold jobs of similar size)
+    int32_t *list[4];
+    int32_t *count[4];
     int32_t *counter[3];           // work counters of the cooperative kernels
     int32_t coop_blocks[3];        // grid size per level (slab = slab_total / blocks)
     unsigned long long slab_total;
+    unsigned long long *medium_cursor;   // level 0, jobs too large for the shared-memory slice: regions of the slab handed out so far
     int32_t debug;
 };
 
 // level 0 (thread per pair) only takes tiny jobs: rows x band width below this many cells per attempt;
 // level 1 (warp per pair) takes bands of up to TRACE_WARP_BW columns either side; level 2 (block per pair) the rest
 constexpr int TRACE_NARROW_CELLS = 768;
+// ... and up to this many cells with the direction codes in a private region of the slab instead (one byte per cell): a
+// 300-row contig with a band of 3-17 columns is still a job for one thread - the warp-per-pair sweep of level 1 would run
+// it with 3-17 of its 32 lanes and a barrier per anti-diagonal (paired-end contigs: traceback stage 9.5 -> see DESIGN.md)
+constexpr int TRACE_MEDIUM_CELLS = 3072;
 constexpr int TRACE_NARROW_WIDTH = 30;   // widest band row the scalar kernel keeps in its shared-memory slice
 constexpr int TRACE_WARP_BW = 62;
 // per-thread slice of the scalar kernel: direction nibbles of TRACE_NARROW_CELLS cells + four rolling int16 rows,
@@ -48,6 +55,7 @@ __device__ __forceinline__ int trace_level(int readLen, int refLen, int bw)
 {
     const int width = min(2 * bw + 1, refLen);
     if (width <= TRACE_NARROW_WIDTH && (long long)readLen * width <= TRACE_NARROW_CELLS) return 0;
+    if (width <= TRACE_NARROW_WIDTH && (long long)readLen * width <= TRACE_MEDIUM_CELLS) return 3;
     return bw <= TRACE_WARP_BW ? 1 : 2;
 }
 constexpr int TRACE_WMAX = 4094;       // wide kernel: band diagonals held in shared memory (3 x int16 each)
@@ -126,15 +134,16 @@ __device__ __forceinline__ int trace_step_code(int nib, int state)
     return (nib & 8) ? 5 : 4;
 }
 
-__global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(TraceArgs a)
+// self = 0: jobs of list 0, directions in the thread's shared-memory slice; self = 3: jobs of list 3, directions in the slab
+__global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(TraceArgs a, int self)
 {
     extern __shared__ uint32_t narrow_sm[];
     __shared__ int16_t mat_s[36];
     if (threadIdx.x < 36) mat_s[threadIdx.x] = a.sc.mat[threadIdx.x];
     __syncthreads();
     const int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (li >= *a.count[0]) return;
-    const int p = a.list[0][li];
+    if (li >= *a.count[self]) return;
+    const int p = a.list[self][li];
     PairState &s = a.state[p];
     db200_sw_result &res = a.results[p];
     const PairMeta pm = a.meta[p];
@@ -143,20 +152,27 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
     const int score = res.score1;
     const int rbeg = res.read_begin1, tbeg = res.ref_begin1; // local copies: the byte stores below may alias `res`
     const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
-    int bw = abs(refLen - readLen) + 1;
+    int bw = self == 0 ? abs(refLen - readLen) + 1 : s.trace_bw;
     uint32_t *slice = narrow_sm + threadIdx.x * TRACE_NARROW_WORDS;
     uint8_t *dir = reinterpret_cast<uint8_t *>(slice);
+    uint8_t *gdir = nullptr;   // medium jobs: one byte per cell in a private region of the slab
     int width = 0;
     while (true) {
         width = min(2 * bw + 1, refLen);
         {
-            const int lvl = trace_level(readLen, refLen, bw);
-            if (lvl != 0) { // the band outgrew the scalar kernel: hand the pair (and the band to try next) to a cooperative kernel
+            int lvl = trace_level(readLen, refLen, bw);
+            if (lvl == 3 && self == 3 && !gdir) {
+                const unsigned long long region = atomicAdd(a.medium_cursor, 1ull);
+                if ((region + 1ull) * (unsigned long long)TRACE_MEDIUM_CELLS <= a.slab_total) gdir = a.slab + region * (unsigned long long)TRACE_MEDIUM_CELLS;
+                else lvl = bw <= TRACE_WARP_BW ? 1 : 2;   // no room left: a cooperative kernel takes the pair
+            }
+            if (lvl != self) { // the band outgrew this launch: hand the pair (and the band to try next) to a later one
                 s.trace_bw = bw;
                 a.list[lvl][atomicAdd(a.count[lvl], 1)] = p;
                 return;
             }
         }
+        const bool use_g = self == 3;
         // this attempt's direction nibbles and the two rolling rows of (H, E), band-relative, live in the thread's slice
         int16_t *Hp = reinterpret_cast<int16_t *>(slice + TRACE_NARROW_DIR_WORDS);
         int16_t *Ep = Hp + TRACE_NARROW_ROW, *Hc = Ep + TRACE_NARROW_ROW, *Ec = Hc + TRACE_NARROW_ROW;
@@ -190,8 +206,11 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
                 const int src = (g <= d) ? 0 : (e1 > f1 ? 1 : 2);
                 const uint8_t nib = (uint8_t)(src | (e_open << 2) | (f_open << 3));
                 const unsigned long long cell = rowbase + (unsigned long long)(j - beg);
-                uint8_t &byte = dir[cell >> 1];
-                byte = (cell & 1) ? (uint8_t)((byte & 0x0F) | (nib << 4)) : (uint8_t)((byte & 0xF0) | nib);
+                if (use_g) gdir[cell] = nib;
+                else {
+                    uint8_t &byte = dir[cell >> 1];
+                    byte = (cell & 1) ? (uint8_t)((byte & 0x0F) | (nib << 4)) : (uint8_t)((byte & 0xF0) | nib);
+                }
                 Hc[j - beg] = (int16_t)h; Ec[j - beg] = (int16_t)max(e, -32768);
                 hleft = h;
             }
@@ -205,6 +224,7 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
     // ---- walk twice: first count the runs, then write them in final (reversed) order ------------------
     int ncig = 0;
     unsigned long long cpos = 0;
+    const bool walk_g = self == 3;
     for (int phase = 0; phase < 2; ++phase) {
         int i = readLen - 1, j = refLen - 1;
         int run = 0, prev = 0, op = 0, state = 2; // state: 0 = in E, 1 = in F, 2 = in H
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
             const int x = j - beg;
             if (x < 0 || x >= width || j < 0) { bad = true; break; } // the reference would read out of bounds here
             const unsigned long long cell = (unsigned long long)i * (unsigned long long)width + (unsigned long long)x;
-            const int nib = (dir[cell >> 1] >> ((cell & 1) * 4)) & 15;
+            const int nib = walk_g ? (int)gdir[cell] : ((dir[cell >> 1] >> ((cell & 1) * 4)) & 15);
             switch (trace_step_code(nib, state)) {
                 case 1: --i; --j; state = 2; op = 0; break;
                 case 2: --i; state = 0; op = 1; break;
