@@ -725,7 +725,7 @@ int db200_ed_batch_host(int device, const db200_ed_params *params, const uint8_t
         int64_t c1 = c0, bytes = 0;
         int32_t maxq = 0, maxt = 0;
         int64_t lim = want;
-        if (npairs - (c0 + lim) < lim / 2) lim = npairs - c0;   // no tiny trailing chunk
+        if (npairs - (c0 + lim) < lim) lim = npairs - c0;   // no trailing chunk below the minimum
         while (c1 < npairs && c1 - c0 < lim) {
             const int64_t ql = qoff[c1 + 1] - qoff[c1], tl = toff[c1 + 1] - toff[c1];
             if (ql < 0 || tl < 0 || ql > 0x7FFFFFF0 || tl > 0x7FFFFFF0) { set_error("ed_batch_host: bad offsets at pair %lld", (long long)c1); return DB200_ERR_ARG; }

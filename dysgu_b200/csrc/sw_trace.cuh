@@ -43,6 +43,7 @@ constexpr int TRACE_NARROW_CELLS = 768;
 // 300-row contig with a band of 3-17 columns is still a job for one thread - the warp-per-pair sweep of level 1 would run
 // it with 3-17 of its 32 lanes and a barrier per anti-diagonal (paired-end contigs: traceback stage 9.5 -> see DESIGN.md)
 constexpr int TRACE_MEDIUM_CELLS = 3072;
+constexpr int TRACE_MEDIUM_MIN_JOBS = 16384;   // below this many such jobs in a batch the warp-per-pair kernel is quicker
 constexpr int TRACE_NARROW_WIDTH = 30;   // widest band row the scalar kernel keeps in its shared-memory slice
 constexpr int TRACE_WARP_BW = 62;
 // per-thread slice of the scalar kernel: direction nibbles of TRACE_NARROW_CELLS cells + four rolling int16 rows,
@@ -153,6 +154,12 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
     const int rbeg = res.read_begin1, tbeg = res.ref_begin1; // local copies: the byte stores below may alias `res`
     const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
     int bw = self == 0 ? abs(refLen - readLen) + 1 : s.trace_bw;
+    if (self == 3 && *a.count[3] < TRACE_MEDIUM_MIN_JOBS) {
+        // few of these jobs: one thread each would only add its latency (~0.3 ms) to the batch - the warp-per-pair
+        // kernel runs them side by side (what happens to the chunks of the host pipeline on the soft-clip workload)
+        a.list[bw <= TRACE_WARP_BW ? 1 : 2][atomicAdd(a.count[bw <= TRACE_WARP_BW ? 1 : 2], 1)] = p;
+        return;
+    }
     uint32_t *slice = narrow_sm + threadIdx.x * TRACE_NARROW_WORDS;
     uint8_t *dir = reinterpret_cast<uint8_t *>(slice);
     uint8_t *gdir = nullptr;   // medium jobs: one byte per cell in a private region of the slab
