@@ -579,21 +579,26 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
             }
             if (rc) return rc;
         }
-        // what no band resolved: the full-column kernels, one list per configuration
+        // what no band resolved: the full-column kernels, one list per configuration, side by side on the side streams
+        // (every configuration is a launch of its own whose tail - one warp finishing a 10 kb pair - nothing else hides)
         int32_t fb_begin_h[ED_NCFG];
         for (int cfg = 0; cfg < ED_NCFG; ++cfg) fb_begin_h[cfg] = (int32_t)(npairs * cfg);
         DB200_CUDA_CHECK(cudaMemcpyAsync(fb_begin, fb_begin_h, sizeof(fb_begin_h), cudaMemcpyHostToDevice, st));
-        for (int cfg = 0; cfg < ED_NCFG; ++cfg) {
+        { const int rc = aux_fork(e, st); if (rc) return rc; }
+        for (int cfg = ED_NCFG - 1; cfg >= 0; --cfg) {
             ea.tasks = fb_tasks; ea.seg_begin = fb_begin; ea.seg_count = fb_count; ea.seg = cfg; ea.counter = counters + (ci++);
-            const int rc = launch_ed_cfg<false>(e, cfg, ea, st);
+            const int rc = launch_ed_cfg<false>(e, cfg, ea, e->aux[e->aux_set][cfg % Engine::NAUX]);
             if (rc) return rc;
         }
+        { const int rc = aux_join(e, st); if (rc) return rc; }
     } else {
-        for (int cfg = 0; cfg < ED_NCFG; ++cfg) {
+        { const int rc = aux_fork(e, st); if (rc) return rc; }
+        for (int cfg = ED_NCFG - 1; cfg >= 0; --cfg) {   // longest queries first: their drain overlaps the shorter configurations
             ea.tasks = tasks; ea.seg_begin = seg_begin; ea.seg_count = seg_count; ea.seg = cfg; ea.counter = counters + (ci++);
-            const int rc = launch_ed_cfg<false>(e, cfg, ea, st);
+            const int rc = launch_ed_cfg<false>(e, cfg, ea, e->aux[e->aux_set][cfg % Engine::NAUX]);
             if (rc) return rc;
         }
+        { const int rc = aux_join(e, st); if (rc) return rc; }
     }
     prof_mark(e, st, ST_ED_FORWARD);
 
@@ -613,11 +618,13 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     prof_mark(e, st, ST_ED_OUTPUT);
 
     if (need_rev) {
-        for (int cfg = 0; cfg < ED_NCFG; ++cfg) {
+        { const int rc = aux_fork(e, st); if (rc) return rc; }
+        for (int cfg = ED_NCFG - 1; cfg >= 0; --cfg) {
             ea.tasks = rev_tasks; ea.seg_begin = rev_begin; ea.seg_count = rev_count; ea.seg = cfg; ea.counter = counters + (ci++);
-            const int rc = launch_ed_cfg<true>(e, cfg, ea, st);
+            const int rc = launch_ed_cfg<true>(e, cfg, ea, e->aux[e->aux_set][cfg % Engine::NAUX]);
             if (rc) return rc;
         }
+        { const int rc = aux_join(e, st); if (rc) return rc; }
     }
     prof_mark(e, st, ST_ED_STARTS);
     DB200_CUDA_CHECK(cudaGetLastError());

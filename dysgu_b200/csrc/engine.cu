@@ -699,6 +699,7 @@ int db200_ed_batch_device(int device, const db200_ed_params *params, const uint8
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
     e->arena[0].reset();
+    e->aux_set = 0;
     return ed_batch_device_impl(e, e->arena[0], params, d_qbuf, d_qoff, q_bytes, d_tbuf, d_toff, t_bytes, npairs, max_query_len,
                                 max_target_len, d_k, d_results, d_loc_buf, loc_cap, d_loc_off, loc_total, (cudaStream_t)stream);
 }
@@ -786,6 +787,7 @@ int db200_ed_batch_host(int device, const db200_ed_params *params, const uint8_t
         Staged &s = staged[slot];
         DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_copy[slot], 0));
         e->arena[slot].reset();
+        e->aux_set = slot;
         int64_t total = 0;
         int rc = ed_batch_device_impl(e, e->arena[slot], params, s.d_q, s.d_off, c.qb, s.d_t, s.d_off + n + 1, c.tb, n, c.maxq, c.maxt, s.d_k,
                                       s.d_res, s.d_loc, s.cap, s.d_loff, &total, st);
