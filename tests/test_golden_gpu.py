@@ -113,3 +113,21 @@ def test_multi_gpu_threads_match_single_gpu():
     assert np.array_equal(fixed, one.fixed)
     off, cig = shard.merge_csr([p.cigar_off for p in parts], [p.cigar for p in parts])
     assert np.array_equal(off, one.cigar_off) and np.array_equal(cig, one.cigar)
+
+
+def test_additional_equalities_golden():
+    """edlib's additionalEqualities (symmetric, not transitive; edlib.cpp:60-91) against vectors produced by the
+    reference's own wrapper (tests/golden/make_golden_equalities.py): wildcards, IUPAC pairs, case folding, a symbol that
+    only occurs in queries, a non-transitive chain - through the batch call and through edlib.align."""
+    for block in load("ed_equalities.json"):
+        eqs = [tuple(e) for e in block["equalities"]]
+        qs = [c["query"].encode() for c in block["cases"]]
+        ts = [c["target"].encode() for c in block["cases"]]
+        r = batch.ed_align_batch(qs, ts, mode=block["mode"], task=block["task"], k=block["k"], additional_equalities=eqs)
+        for i, c in enumerate(block["cases"]):
+            want = dict(c["result"], status=0)
+            want["locations"] = [tuple(x) for x in want["locations"]]
+            assert r.as_dict(i) == want, (block["name"], block["mode"], block["k"], c["query"][:40], c["target"][:40])
+        c = block["cases"][0]
+        got = align(c["query"], c["target"], block["mode"], block["task"], block["k"], additionalEqualities=eqs)
+        assert got["editDistance"] == c["result"]["editDistance"] and got["locations"] == [tuple(x) for x in c["result"]["locations"]]

@@ -150,3 +150,46 @@ def test_pipelined_column_tiles_equal_sequential_tiles():
     res = batch.sw_align_batch([qs[i] for i in sub], [ts[i] for i in sub], **prm)
     ref = O.oracle_sw([qs[i] for i in sub], [ts[i] for i in sub], prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"])
     compare([qs[i] for i in sub], [ts[i] for i in sub], res, ref, "pipelined tiles")
+
+
+def test_device_entry_point_sub_batches_share_one_cigar_csr():
+    """DB200_DEVICE_SUBBATCHES (off by default) cuts a device-resident batch into sub-batches on the engine's slot streams;
+    the outputs - fixed records, status, and the cigar CSR the sub-batches append to in order - must not change."""
+    import ctypes as C
+    import os
+    import torch
+    from dysgu_b200 import _lib
+    L = _lib.lib()
+    q, t, prm = workloads.remap_windows(30000, seed=3)
+    n, qb, tb = len(q), int(q.off[-1]), int(t.off[-1])
+    p = _lib.SwParams()
+    p.match, p.mismatch, p.gap_open, p.gap_extend, p.score_size, p.flag = prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"], 2, 1
+    dev = torch.device("cuda", 0)
+    dq, dt = torch.from_numpy(q.buf).to(dev), torch.from_numpy(t.buf).to(dev)
+    dqo, dto = torch.from_numpy(q.off).to(dev), torch.from_numpy(t.off).to(dev)
+    cap = 4 * n + 1024
+    outs = {}
+    for nsub in (1, 3, 7):
+        os.environ["DB200_DEVICE_SUBBATCHES"] = str(nsub)
+        try:
+            res = torch.zeros((n, 8), dtype=torch.int32, device=dev)
+            cig = torch.zeros(cap, dtype=torch.int32, device=dev)
+            coff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            st = torch.full((n,), -1, dtype=torch.int32, device=dev)
+            total = C.c_int64(-1)
+            rc = L.db200_sw_batch_device(0, C.byref(p), dq.data_ptr(), dqo.data_ptr(), qb, dt.data_ptr(), dto.data_ptr(), tb, n,
+                                         int(q.lengths.max()), int(t.lengths.max()), None, res.data_ptr(), cig.data_ptr(), cap,
+                                         coff.data_ptr(), st.data_ptr(), C.addressof(total), None)
+            _lib.check(rc, "db200_sw_batch_device")
+            torch.cuda.synchronize()
+            outs[nsub] = (res.cpu(), cig.cpu(), coff.cpu(), st.cpu(), total.value)
+        finally:
+            del os.environ["DB200_DEVICE_SUBBATCHES"]
+    ref = outs[1]
+    assert ref[4] == int(ref[2][-1]) and (ref[3] == 0).all()
+    for nsub in (3, 7):
+        for a, b in zip(ref[:4], outs[nsub][:4]):
+            assert torch.equal(a, b), nsub
+        assert outs[nsub][4] == ref[4]
+    oracle = O.oracle_sw((q.buf, q.off), (t.buf, t.off), prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"], csr=True)
+    assert np.array_equal(ref[0].numpy(), oracle.fixed)
