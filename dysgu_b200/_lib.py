@@ -63,6 +63,16 @@ def lib():
         L.db200_ed_batch_device.argtypes = [C.c_int, C.POINTER(EdParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                             C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    if hasattr(L, "db200_ed_path_batch_host"):
+        L.db200_ed_path_batch_host.restype = C.c_int
+        L.db200_ed_path_batch_host.argtypes = [C.c_int, C.POINTER(EdParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                               C.c_void_p]
+        L.db200_ed_path_batch_device.restype = C.c_int
+        L.db200_ed_path_batch_device.argtypes = [C.c_int, C.POINTER(EdParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                                 C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                                 C.c_void_p]
     _lib = L
     return L
 

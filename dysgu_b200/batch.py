@@ -129,10 +129,13 @@ def sw_align_batch(queries, targets, match=2, mismatch=-3, gap_open=5, gap_exten
 class EdResults:
     """Results of an edit-distance batch (fields follow EdlibAlignResult, edlib.h:162-218)."""
 
-    def __init__(self, fixed, loc, loc_off):
+    def __init__(self, fixed, loc, loc_off, path=None, path_off=None, path_len=None):
         self.fixed = fixed      # int32 [n,4]: status, editDistance, alphabetLength, numLocations
         self.loc = loc          # int32 [total,2]: (start, end); start == ED_NO_START -> None
         self.loc_off = loc_off
+        self.path = path        # task "path": uint8 edit operations (0 match, 1 insertion, 2 deletion, 3 mismatch)
+        self.path_off = path_off
+        self.path_len = path_len
 
     def __len__(self):
         return self.fixed.shape[0]
@@ -141,14 +144,40 @@ class EdResults:
     def edit_distance(self):
         return self.fixed[:, 1]
 
+    def alignment(self, i):
+        """Edit operations of pair i (EdlibAlignResult.alignment), None where the reference returns none."""
+        if self.path is None or self.path_len[i] <= 0:
+            return None
+        return self.path[self.path_off[i]:self.path_off[i] + self.path_len[i]]
+
+    def cigar(self, i, extended=True):
+        """edlibAlignmentToCigar of pair i (edlib.cpp:298-347; the wrapper uses the extended format, edlib.pyx:143-147)."""
+        ops = self.alignment(i)
+        return None if ops is None else ops_to_cigar(ops, extended)
+
     def as_dict(self, i):
         st, ed, al, nl = (int(x) for x in self.fixed[i])
         locs = [(None if int(s) == ED_NO_START else int(s), int(e)) for s, e in self.loc[self.loc_off[i]:self.loc_off[i + 1]]]
-        return {"status": st, "editDistance": ed, "alphabetLength": al, "locations": locs}
+        d = {"status": st, "editDistance": ed, "alphabetLength": al, "locations": locs}
+        if self.path is not None:
+            d["cigar"] = self.cigar(i)
+        return d
+
+
+def ops_to_cigar(ops, extended=True) -> str:
+    """Run-length text of an edit-operation array; standard format merges match and mismatch into M."""
+    ops = np.asarray(ops, dtype=np.uint8)
+    if ops.size == 0:
+        return ""
+    letters = np.frombuffer(b"=IDX" if extended else b"MIDM", dtype=np.uint8)[ops]
+    cut = np.flatnonzero(letters[1:] != letters[:-1]) + 1
+    starts = np.concatenate(([0], cut))
+    ends = np.concatenate((cut, [ops.size]))
+    return "".join("%d%s" % (e - b, chr(letters[b])) for b, e in zip(starts, ends))
 
 
 def ed_align_batch(queries, targets, mode="NW", task="distance", k=-1, additional_equalities=None, device=None) -> EdResults:
-    """edlib.align semantics per pair (edlib.pyx:57-156) for tasks 'distance' and 'locations'."""
+    """edlib.align semantics per pair (edlib.pyx:57-156): tasks 'distance', 'locations' and 'path'."""
     q, t = _as_batch(queries), _as_batch(targets)
     n = len(q)
     if len(t) != n:
@@ -176,6 +205,15 @@ def ed_align_batch(queries, targets, mode="NW", task="distance", k=-1, additiona
     loc = np.zeros((cap, 2), dtype=np.int32)
     qbuf = q.buf if q.buf.size else np.zeros(1, np.uint8)
     tbuf = t.buf if t.buf.size else np.zeros(1, np.uint8)
+    if prm.task == ED_TASKS["path"]:
+        pcap = int(q.off[-1] + t.off[-1]) + 1
+        path = np.zeros(pcap, dtype=np.uint8)
+        plen = np.zeros(max(n, 1), dtype=np.int32)
+        rc = L.db200_ed_path_batch_host(default_device() if device is None else device, C.byref(prm), _ptr(qbuf), _ptr(q.off),
+                                        _ptr(tbuf), _ptr(t.off), n, _ptr(karr), _ptr(fixed), _ptr(loc), cap, _ptr(loff), _ptr(path),
+                                        pcap, _ptr(plen))
+        _lib.check(rc, "db200_ed_path_batch_host")
+        return EdResults(fixed, loc[:loff[n]], loff, path, (q.off + t.off)[:n], plen[:n])
     rc = L.db200_ed_batch_host(default_device() if device is None else device, C.byref(prm), _ptr(qbuf), _ptr(q.off), _ptr(tbuf),
                                _ptr(t.off), n, _ptr(karr), _ptr(fixed), _ptr(loc), cap, _ptr(loff))
     _lib.check(rc, "db200_ed_batch_host")

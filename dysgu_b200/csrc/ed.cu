@@ -4,6 +4,7 @@
 // Reference behaviour being reproduced (dysgu v1.9.0): edlib.pyx:57-156 (wrapper), edlib.cpp:141-296
 // (driver: alphabet, empty sequences, k handling, start locations), 355-381 (Peq), 546-709, 735-944.
 #include "ed_kernels.cuh"
+#include "ed_path.cuh"
 
 namespace db200 {
 
@@ -422,6 +423,54 @@ static int launch_myers(Engine *e, const EdArgs &a, cudaStream_t st)
     return DB200_OK;
 }
 
+// ---- task "path" (edlib.cpp:268-285, 1177-1412) ---------------------------------------------------------------------------
+struct EdPathArgs {
+    const EdPair *pairs;
+    const uint64_t *peq;
+    const uint8_t *tcodes;
+    const db200_ed_result *results;
+    const int64_t *loc_off;
+    const int32_t *loc_buf;
+    uint8_t *path_buf;          // pair p writes at path_buf[q_off + t_off ..), at most m + n operations
+    int32_t *path_len;
+    int64_t npairs;
+    uint8_t *scratch;           // one region of `stride` bytes per thread: leaf columns | Pv | Mv | left | right | tmp
+    int64_t stride;
+    int32_t leaf_bytes, vec_bytes, col_bytes;
+    int32_t *counter;
+};
+
+// Thread per pair, pairs handed out through a counter (their cost spans five orders of magnitude).  The alignment is the
+// global one of the query against target[start .. end] of the pair's first location; pairs without a result (distance
+// above k, an empty sequence: edlib.cpp:161-179 returns before the path step) report length 0.  All of the work is in
+// ed_path.cuh, which the CPU test suite runs against the reference's vectors.
+__global__ void __launch_bounds__(64) ed_path_kernel(EdPathArgs a)
+{
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    uint8_t *base = a.scratch + tid * a.stride;
+    EdPathScratch s;
+    s.dir = reinterpret_cast<uint64_t *>(base);
+    s.Pv = reinterpret_cast<uint64_t *>(base + a.leaf_bytes);
+    s.Mv = reinterpret_cast<uint64_t *>(base + a.leaf_bytes + a.vec_bytes);
+    s.left = reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes);
+    s.right = reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + a.col_bytes);
+    s.tmp = base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + 2 * (int64_t)a.col_bytes;
+    while (true) {
+        const int64_t p = atomicAdd(a.counter, 1);
+        if (p >= a.npairs) break;
+        const EdPair pr = a.pairs[p];
+        const db200_ed_result r = a.results[p];
+        int len = 0;
+        if (!pr.special && r.status == 0 && r.edit_distance >= 0 && r.num_locations > 0) {
+            const int64_t l = a.loc_off[p];
+            const int start = a.loc_buf[2 * l], end = a.loc_buf[2 * l + 1];
+            len = ed_path_pair(a.peq + pr.peq_off, a.tcodes + pr.t_off, pr.W, pr.m, start, end + 1, r.edit_distance, s,
+                               a.path_buf + pr.q_off + pr.t_off);
+        }
+        a.path_len[p] = len;   // -1: no split consistent with the distance was found (an internal error, reported by the host)
+    }
+}
+
 template <bool REV>
 static int launch_ed_cfg(Engine *e, int cfg, const EdArgs &a, cudaStream_t st)
 {
@@ -460,10 +509,19 @@ static int launch_banded(Engine *e, const EdBandArgs &a, int64_t npairs, cudaStr
 int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const uint8_t *d_qbuf, const int64_t *d_qoff,
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_k, db200_ed_result *d_results,
-                         int32_t *d_loc_buf, int64_t loc_cap, int64_t *d_loc_off, int64_t *loc_total, cudaStream_t st)
+                         int32_t *d_loc_buf, int64_t loc_cap, int64_t *d_loc_off, int64_t *loc_total, cudaStream_t st,
+                         uint8_t *d_path_buf, int64_t path_cap, int32_t *d_path_len)
 {
     if (npairs < 0 || !prm || !d_results) { set_error("ed_batch: bad arguments"); return DB200_ERR_ARG; }
-    if (prm->task == DB200_ED_TASK_PATH) { set_error("ed_batch: task 'path' is not provided by the device path"); return DB200_ERR_ARG; }
+    const bool want_path = prm->task == DB200_ED_TASK_PATH;
+    if (want_path && (!d_path_buf || !d_path_len)) {
+        set_error("ed_batch: task 'path' needs the path buffers of db200_ed_path_batch_host / db200_ed_path_batch_device");
+        return DB200_ERR_ARG;
+    }
+    if (want_path && path_cap < q_bytes + t_bytes) {
+        set_error("ed_batch: path buffer too small (%lld bytes needed)", (long long)(q_bytes + t_bytes));
+        return DB200_ERR_CAPACITY;
+    }
     if (prm->task < 0 || prm->task > 2) { set_error("ed_batch: bad task"); return DB200_ERR_ARG; }
     if (npairs == 0) {
         if (d_loc_off) DB200_CUDA_CHECK(cudaMemsetAsync(d_loc_off, 0, sizeof(int64_t), st));
@@ -627,6 +685,26 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
         { const int rc = aux_join(e, st); if (rc) return rc; }
     }
     prof_mark(e, st, ST_ED_STARTS);
+    if (want_path) {
+        // scratch per thread: the reference's 1 MB rule bounds the stored columns of a leaf, the rest follows the longest query
+        const int64_t Wq = Wmax, maxt = std::max(max_target_len, 1);
+        EdPathArgs xa;
+        memset(&xa, 0, sizeof(xa));
+        xa.leaf_bytes = (int32_t)std::min<int64_t>(ED_PATH_LEAF_BYTES, 16 * Wq * maxt);
+        xa.vec_bytes = (int32_t)(8 * Wq);
+        xa.col_bytes = (int32_t)((4 * ((int64_t)std::max(max_query_len, 1) + 1) + 7) & ~7ll);
+        xa.stride = (xa.leaf_bytes + 2 * (int64_t)xa.vec_bytes + 2 * (int64_t)xa.col_bytes + (int64_t)std::max(max_query_len, 0) + maxt + 1 + 15) & ~15ll;
+        const int64_t budget = (int64_t)3 << 29;   // 1.5 GB of scratch at most
+        int64_t threads = std::min<int64_t>(npairs, (int64_t)e->sm_count * 256);
+        threads = std::max<int64_t>(64, std::min(threads, budget / xa.stride) / 64 * 64);
+        xa.scratch = ws.alloc<uint8_t>((size_t)(threads * xa.stride));
+        if (!xa.scratch) { set_error("ed_batch: device workspace allocation failed (path scratch)"); return DB200_ERR_NOMEM; }
+        xa.pairs = pairs; xa.peq = peq; xa.tcodes = tcodes; xa.results = d_results; xa.loc_off = d_loc_off; xa.loc_buf = d_loc_buf;
+        xa.path_buf = d_path_buf; xa.path_len = d_path_len; xa.npairs = npairs; xa.counter = counters + (ci++);
+        ed_path_kernel<<<(unsigned)(threads / 64), 64, 0, st>>>(xa);
+        count_launch(e);
+        prof_mark(e, st, ST_ED_PATH);
+    }
     DB200_CUDA_CHECK(cudaGetLastError());
     if (loc_total) {
         int32_t ovf = 0;

@@ -84,7 +84,7 @@ inline void count_launch(Engine *e, int n = 1) { e->launches += n; }
 
 // stage ids reported by db200_profile_collect (a mark closes the stage named by the PREVIOUS mark)
 enum Stage { ST_BEGIN = 0, ST_PACK, ST_BUCKET, ST_FORWARD, ST_FORWARD_WATCH, ST_REVERSE_PREP, ST_REVERSE, ST_REVERSE_WATCH,
-             ST_FINALIZE, ST_TRACEBACK, ST_CIGAR, ST_ED_PREP, ST_ED_FORWARD, ST_ED_STARTS, ST_ED_OUTPUT, ST_COUNT };
+             ST_FINALIZE, ST_TRACEBACK, ST_CIGAR, ST_ED_PREP, ST_ED_FORWARD, ST_ED_STARTS, ST_ED_OUTPUT, ST_ED_PATH, ST_COUNT };
 void prof_mark(Engine *e, cudaStream_t st, int stage);
 // fork: side streams wait for everything enqueued on `st` so far; join: `st` waits for all side streams
 int aux_fork(Engine *e, cudaStream_t st);
@@ -112,6 +112,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *params, co
 int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff,
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_k, db200_ed_result *d_results, int32_t *d_loc_buf, int64_t loc_cap,
-                         int64_t *d_loc_off, int64_t *loc_total, cudaStream_t st);
+                         int64_t *d_loc_off, int64_t *loc_total, cudaStream_t st,
+                         uint8_t *d_path_buf = nullptr, int64_t path_cap = 0, int32_t *d_path_len = nullptr);
 
 }  // namespace db200

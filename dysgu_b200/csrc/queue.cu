@@ -76,6 +76,9 @@ struct db200_queue {
     std::vector<db200_ed_result> ed_res;
     std::vector<int64_t> ed_loc_off;
     std::vector<int32_t> ed_loc;       // (start, end) pairs
+    std::vector<int64_t> ed_path_off;  // [slot] -> first operation in ed_path (-1: the pair's group had another task)
+    std::vector<int32_t> ed_path_len;
+    std::vector<uint8_t> ed_path;      // edit operations of task "path" groups
     int64_t npending = 0;
     ~db200_queue() { for (auto g : groups) delete g; }
 };
@@ -210,8 +213,23 @@ int db200_queue_flush(db200_queue *q)
             p.eq_pairs = g->eq.empty() ? nullptr : g->eq.data();
             p.n_eq_pairs = (int32_t)(g->eq.size() / 2);
             p.k = -1;
-            rc = db200_ed_batch_host(q->device, &p, g->qbuf.p, g->qoff.p, g->tbuf.p, g->toff.p, n, g->aux.p, q->ed_res.data() + base,
-                                     q->ed_loc.data() + lbase, cap, loff.data());
+            const bool want_path = p.task == DB200_ED_TASK_PATH;
+            const size_t pbase = q->ed_path.size();
+            q->ed_path_off.resize(base + (size_t)n, -1);
+            q->ed_path_len.resize(base + (size_t)n, 0);
+            if (want_path) {
+                const int64_t pcap = (int64_t)(g->qbuf.n + g->tbuf.n);
+                q->ed_path.resize(pbase + (size_t)pcap + 1);
+                rc = db200_ed_path_batch_host(q->device, &p, g->qbuf.p, g->qoff.p, g->tbuf.p, g->toff.p, n, g->aux.p, q->ed_res.data() + base,
+                                              q->ed_loc.data() + lbase, cap, loff.data(), q->ed_path.data() + pbase, pcap + 1,
+                                              q->ed_path_len.data() + base);
+                if (rc == DB200_OK)
+                    for (int64_t i = 0; i < n; ++i) q->ed_path_off[base + (size_t)i] = (int64_t)pbase + g->qoff.p[i] + g->toff.p[i];
+            } else {
+                rc = db200_ed_batch_host(q->device, &p, g->qbuf.p, g->qoff.p, g->tbuf.p, g->toff.p, n, g->aux.p, q->ed_res.data() + base,
+                                         q->ed_loc.data() + lbase, cap, loff.data());
+            }
+            if (rc != DB200_OK) { q->ed_path.resize(pbase); q->ed_path_off.resize(base); q->ed_path_len.resize(base); }
             if (rc == DB200_OK) {
                 q->ed_loc.resize(lbase + 2 * (size_t)loff[(size_t)n]);
                 q->ed_loc_off.resize(base + (size_t)n);
@@ -273,6 +291,18 @@ int db200_queue_fetch_ed(db200_queue *q, int64_t ticket, db200_ed_result *result
     return DB200_OK;
 }
 
+int db200_queue_fetch_ed_path(db200_queue *q, int64_t ticket, const uint8_t **path, int32_t *path_len)
+{
+    const Ticket *t = nullptr;
+    const int rc = resolve(q, ticket, 1, &t);
+    if (rc != DB200_OK) return rc;
+    const size_t s = (size_t)t->slot;
+    const bool has = q->ed_path_off[s] >= 0 && q->ed_path_len[s] > 0;
+    if (path) *path = has ? q->ed_path.data() + q->ed_path_off[s] : nullptr;
+    if (path_len) *path_len = has ? q->ed_path_len[s] : 0;
+    return DB200_OK;
+}
+
 int db200_queue_reset(db200_queue *q)
 {
     if (!q) { set_error("queue_reset: bad arguments"); return DB200_ERR_ARG; }
@@ -283,6 +313,7 @@ int db200_queue_reset(db200_queue *q)
     q->tickets.clear();
     q->sw_res.clear(); q->sw_status.clear(); q->sw_cig_off.clear(); q->sw_cig.clear();
     q->ed_res.clear(); q->ed_loc_off.clear(); q->ed_loc.clear();
+    q->ed_path_off.clear(); q->ed_path_len.clear(); q->ed_path.clear();
     q->npending = 0;
     return DB200_OK;
 }

@@ -39,8 +39,6 @@ def align(query, target, mode="NW", task="distance", k=-1, additionalEqualities=
         mode = "NW"           # unknown strings leave the default config untouched (edlib.pyx:103-105)
     if task not in ("distance", "locations", "path"):
         task = "distance"
-    if task == "path":
-        raise NotImplementedError("task='path' is not provided by the device path (no dysgu caller requests it)")
     if eqs is not None:
         eqs = [((a.encode("utf-8")[0] if isinstance(a, str) else int(a)), (b.encode("utf-8")[0] if isinstance(b, str) else int(b)))
                for a, b in eqs]
@@ -51,7 +49,7 @@ def align(query, target, mode="NW", task="distance", k=-1, additionalEqualities=
     d = res.as_dict(0)
     if d["status"] == 1:
         raise Exception("There was an error.")
-    return {"editDistance": d["editDistance"], "alphabetLength": d["alphabetLength"], "locations": d["locations"], "cigar": None}
+    return {"editDistance": d["editDistance"], "alphabetLength": d["alphabetLength"], "locations": d["locations"], "cigar": d.get("cigar")}
 
 
 def getNiceAlignment(alignResult, query, target, gapSymbol="-"):

@@ -48,6 +48,7 @@ def _bind(L):
     L.db200_queue_reset.argtypes = [C.c_void_p]
     L.db200_queue_fetch_sw.argtypes = [C.c_void_p, C.c_int64, C.POINTER(SwResultC), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_int32)]
     L.db200_queue_fetch_ed.argtypes = [C.c_void_p, C.c_int64, C.POINTER(EdResultC), C.POINTER(C.POINTER(C.c_int32))]
+    L.db200_queue_fetch_ed_path.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int32)]
     L._queue_bound = True
     return L
 
@@ -132,7 +133,13 @@ class AlignQueue:
         if r.num_locations > 0 and loc:
             a = np.ctypeslib.as_array(loc, shape=(2 * r.num_locations,))
             locs = [(None if int(a[2 * i]) == _batch.ED_NO_START else int(a[2 * i]), int(a[2 * i + 1])) for i in range(r.num_locations)]
-        return {"status": int(r.status), "editDistance": int(r.edit_distance), "alphabetLength": int(r.alphabet_length), "locations": locs}
+        ops = C.POINTER(C.c_uint8)()
+        nops = C.c_int32(0)
+        _lib.check(self._L.db200_queue_fetch_ed_path(self._q, ticket, C.byref(ops), C.byref(nops)), "db200_queue_fetch_ed_path")
+        d = {"status": int(r.status), "editDistance": int(r.edit_distance), "alphabetLength": int(r.alphabet_length), "locations": locs}
+        if nops.value > 0 and ops:   # task "path" tickets with an alignment
+            d["cigar"] = _batch.ops_to_cigar(np.ctypeslib.as_array(ops, shape=(nops.value,)))
+        return d
 
 
 # ---- deferred mode of the drop-in classes ---------------------------------------------------------------------------
@@ -169,7 +176,7 @@ class LazyEdlibResult(Mapping):
             d = self._queue.fetch_ed(self._ticket)
             if d["status"] == 1:
                 raise Exception("There was an error.")
-            self._d = {"editDistance": d["editDistance"], "alphabetLength": d["alphabetLength"], "locations": d["locations"], "cigar": None}
+            self._d = {"editDistance": d["editDistance"], "alphabetLength": d["alphabetLength"], "locations": d["locations"], "cigar": d.get("cigar")}
             self._queue = None
         return self._d
 

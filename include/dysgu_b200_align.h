@@ -59,7 +59,7 @@ int64_t db200_kernel_launches(int device, int reset);
 /* Stage profiling: CUDA events between pipeline stages on the launching stream.  `collect` synchronises
  * the device and returns the accumulated milliseconds per stage (see enum Stage in csrc/engine.cuh:
  * 1 pack, 2 bucket, 3 forward pass, 4 forward re-run, 5 reverse prep, 6 reverse pass, 7 reverse re-run,
- * 8 finalize, 9 traceback, 10 cigar, 11 ed prep, 12 ed forward, 13 ed starts, 14 ed output). */
+ * 8 finalize, 9 traceback, 10 cigar, 11 ed prep, 12 ed forward, 13 ed starts, 14 ed output, 15 ed path). */
 /* Myers word steps (one 64-row block update) the edit-distance kernels evaluated since the last reset; synchronises. */
 int64_t db200_ed_word_steps(int device, int reset);
 int db200_profile_enable(int device, int on);
@@ -163,7 +163,7 @@ void db200_align_destroy(db200_s_align *a);
 #define DB200_ED_MODE_HW 2   /* EDLIB_MODE_HW  */
 #define DB200_ED_TASK_DISTANCE 0
 #define DB200_ED_TASK_LOC 1
-#define DB200_ED_TASK_PATH 2 /* not provided by the device path (no dysgu caller requests it) */
+#define DB200_ED_TASK_PATH 2 /* EDLIB_TASK_PATH: through db200_ed_path_batch_* (no dysgu caller requests it) */
 #define DB200_ED_NO_START INT32_MIN /* start location left unset (edlib.pyx:140: None) */
 
 typedef struct {
@@ -201,7 +201,35 @@ int db200_ed_batch_device(int device, const db200_ed_params *params,
                           db200_ed_result *d_results, int32_t *d_loc_buf, int64_t loc_cap,
                           int64_t *d_loc_off, int64_t *loc_total, void *stream);
 
-/* Legacy single-pair entry point with edlib's signature (edlib.h:146-271). */
+/*
+ * task "path" (EDLIB_TASK_PATH; edlib.cpp:268-285 driver, 1177-1229 obtainAlignment, 958-1157 traceback, 1247-1412
+ * Hirschberg): everything db200_ed_batch_* reports for task "locations", plus the edit operations (EDLIB_EDOP_*:
+ * 0 match, 1 insertion, 2 deletion, 3 mismatch) of the global alignment of the query to
+ * target[start .. end] of the pair's FIRST location - the alignment the reference reports, not just one of its cost.
+ * params->task must be DB200_ED_TASK_PATH.  The operations of pair i start at path_buf[(qoff[i] - qoff[0]) +
+ * (toff[i] - toff[0])] and there are path_len[i] of them (at most len(query) + len(target), so path_cap =
+ * total query bytes + total target bytes always suffices and less is refused with DB200_ERR_CAPACITY);
+ * path_len[i] == 0 where the reference returns no alignment (distance above k, an empty sequence: edlib.cpp:161-179).
+ * db200_edlibAlignmentToCigar formats one pair's operations as the cigar string of edlib.pyx:143-147.
+ */
+int db200_ed_path_batch_host(int device, const db200_ed_params *params,
+                             const uint8_t *qbuf, const int64_t *qoff,
+                             const uint8_t *tbuf, const int64_t *toff, int64_t npairs,
+                             const int32_t *k,
+                             db200_ed_result *results, int32_t *loc_buf, int64_t loc_cap, int64_t *loc_off,
+                             uint8_t *path_buf, int64_t path_cap, int32_t *path_len);
+
+/* Device-resident variant; d_path_len[i] < 0 flags an internal error for pair i (never seen; the host variant checks it). */
+int db200_ed_path_batch_device(int device, const db200_ed_params *params,
+                               const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
+                               const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
+                               int32_t max_query_len, int32_t max_target_len, const int32_t *d_k,
+                               db200_ed_result *d_results, int32_t *d_loc_buf, int64_t loc_cap,
+                               int64_t *d_loc_off, int64_t *loc_total,
+                               uint8_t *d_path_buf, int64_t path_cap, int32_t *d_path_len, void *stream);
+
+/* Legacy single-pair entry point with edlib's signature (edlib.h:146-271); task EDLIB_TASK_PATH fills
+ * alignment / alignmentLength like the reference. */
 typedef struct { char first; char second; } db200_EdlibEqualityPair;
 typedef struct {
     int k;
@@ -257,6 +285,8 @@ int db200_queue_flush(db200_queue *q);
 int db200_queue_fetch_sw(db200_queue *q, int64_t ticket, db200_sw_result *result, const uint32_t **cigar, int32_t *status);
 /* locations: result->num_locations (start, end) int32 pairs (NULL if none) */
 int db200_queue_fetch_ed(db200_queue *q, int64_t ticket, db200_ed_result *result, const int32_t **locations);
+/* task "path" tickets: the edit operations (NULL / 0 where the reference returns no alignment or the ticket's task was another) */
+int db200_queue_fetch_ed_path(db200_queue *q, int64_t ticket, const uint8_t **path, int32_t *path_len);
 /* Forget every ticket and result (pending pairs are dropped). */
 int db200_queue_reset(db200_queue *q);
 
