@@ -173,6 +173,11 @@ WORKLOADS = {
                "ont_nw: edlib NW/distance k=-1, insertion sequences 50 bp-10 kb, ONT r10 error, 20 % unrelated"),
     "hifi_hw": ("ed", lambda W, n, s: W.insertion_linking(n, seed=s, platform="hifi")[:2] + (dict(mode="HW", task="locations"),), 20000, 2000,
                 "hifi_hw: edlib HW/locations, insertion sequences 50 bp-10 kb, HiFi error, 20 % unrelated"),
+    # task "path" (no dysgu caller requests it): the locations run plus the alignment of the first location
+    "remap_path": ("ed", lambda W, n, s: W.remap_chain(n, seed=s)[:2] + (dict(mode="HW", task="path"),), 1 << 18, 100000,
+                   "remap_path: edlib HW/path, clip 15-300 bp vs 1000 bp window, distance+locations+edit operations"),
+    "hifi_path": ("ed", lambda W, n, s: W.insertion_linking(n, seed=s, platform="hifi")[:2] + (dict(mode="NW", task="path"),), 20000, 4000,
+                  "hifi_path: edlib NW/path, insertion sequences 50 bp-10 kb, HiFi error, 20 % unrelated, distance+edit operations"),
 }
 
 
@@ -279,6 +284,8 @@ def run_ours(args):
         var_cap = int(t_bytes + 2 * n + 16) if prm["mode"] != "NW" else int(n + 16)                                       # locations
         var_dtype, var_np, res_cols = torch.int32, np.int32, 4
     var_words = var_cap * (1 if kind == "sw" else 2)
+    want_path = kind == "ed" and prm["task"] == "path"
+    path_cap = q_bytes + t_bytes + 16
 
     # ---- device-resident arm --------------------------------------------------------------------------
     d_q = torch.from_numpy(q.buf).to(dev)
@@ -289,6 +296,8 @@ def run_ours(args):
     d_var = torch.zeros(var_words, dtype=var_dtype, device=dev)
     d_voff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_path = torch.zeros(path_cap if want_path else 1, dtype=torch.uint8, device=dev)
+    d_plen = torch.zeros(n if want_path else 1, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def device_step():
@@ -296,6 +305,11 @@ def run_ours(args):
             rc = L.db200_sw_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
                                          d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_var.data_ptr(), var_cap,
                                          d_voff.data_ptr(), d_status.data_ptr(), None, C.c_void_p(stream.cuda_stream))
+        elif want_path:
+            rc = L.db200_ed_path_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
+                                              d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_var.data_ptr(), var_cap,
+                                              d_voff.data_ptr(), None, d_path.data_ptr(), path_cap, d_plen.data_ptr(),
+                                              C.c_void_p(stream.cuda_stream))
         else:
             rc = L.db200_ed_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
                                          d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_var.data_ptr(), var_cap,
@@ -314,6 +328,8 @@ def run_ours(args):
     bad = int((d_status != 0).sum().item()) if kind == "sw" else int((d_res[:, 0] != 0).sum().item())
     if bad:
         raise SystemExit("bench.py: %d pairs reported a non-zero status" % bad)
+    if want_path and int((d_plen < 0).sum().item()):
+        raise SystemExit("bench.py: pairs without an alignment path")
     checksum = int(d_res[:, 0 if kind == "sw" else 1].sum().item())
 
     L.db200_profile_enable(local_rank, 1)
@@ -357,11 +373,17 @@ def run_ours(args):
     hvar = pinned_array(L, (var_words,), var_np)
     hvoff = pinned_array(L, (n + 1,), np.int64)
     hstat = pinned_array(L, (n,), np.int32)
+    hpath = pinned_array(L, (path_cap if want_path else 1,), np.uint8); hpath[:] = 0
+    hplen = pinned_array(L, (n if want_path else 1,), np.int32)
 
     def host_step():
         if kind == "sw":
             rc = L.db200_sw_batch_host(local_rank, C.byref(prm_c), hq.ctypes.data, hqo.ctypes.data, ht.ctypes.data, hto.ctypes.data, n,
                                        None, hres.ctypes.data, hvar.ctypes.data, var_cap, hvoff.ctypes.data, hstat.ctypes.data)
+        elif want_path:
+            rc = L.db200_ed_path_batch_host(local_rank, C.byref(prm_c), hq.ctypes.data, hqo.ctypes.data, ht.ctypes.data, hto.ctypes.data, n,
+                                            None, hres.ctypes.data, hvar.ctypes.data, var_cap, hvoff.ctypes.data, hpath.ctypes.data,
+                                            path_cap, hplen.ctypes.data)
         else:
             rc = L.db200_ed_batch_host(local_rank, C.byref(prm_c), hq.ctypes.data, hqo.ctypes.data, ht.ctypes.data, hto.ctypes.data, n,
                                        None, hres.ctypes.data, hvar.ctypes.data, var_cap, hvoff.ctypes.data)
@@ -384,7 +406,7 @@ def run_ours(args):
         raise SystemExit("bench.py: host and device arms disagree")
     nvar = int(hvoff[n])
     h2d = q_bytes + t_bytes + 2 * 8 * (n + 1)
-    d2h = 4 * res_cols * n + 8 * (n + 1) + (4 * n + 4 * nvar if kind == "sw" else 8 * nvar)
+    d2h = 4 * res_cols * n + 8 * (n + 1) + (4 * n + 4 * nvar if kind == "sw" else 8 * nvar) + (q_bytes + t_bytes + 4 * n if want_path else 0)
 
     if rank != 0:
         if dist is not None:
@@ -395,8 +417,8 @@ def run_ours(args):
     peaks = load_measured_peaks()
     peak = peaks["int_lane_ops"] / 1e12
     stage_names = ["begin", "pack", "bucket", "forward", "forward_rerun", "reverse_prep", "reverse", "reverse_rerun", "finalize",
-                   "traceback", "cigar", "ed_prep", "ed_forward", "ed_starts", "ed_output"]
-    stages = {k: v / args.steps for k, v in zip(stage_names, stage_ms[:15]) if v > 0 or k == "begin"}
+                   "traceback", "cigar", "ed_prep", "ed_forward", "ed_starts", "ed_output", "ed_path"]
+    stages = {k: v / args.steps for k, v in zip(stage_names, stage_ms[:16]) if v > 0 or k == "begin"}
     if kind == "sw":
         k_ms = stage_ms[3] / args.steps          # forward sw_pass_kernel launches of one step (this rank)
         lane_ops = cells * SW_LANE_OPS_PER_CELL
@@ -449,6 +471,11 @@ def run_ours(args):
             ncmp = 7 if kind == "sw" else 4
             mism = int((r.fixed[:, :ncmp] != hres[:sample, :ncmp]).any(axis=1).sum())
             cpu_baseline["parity_mismatches_on_sample"] = mism
+            if want_path:   # the reference's alignment arrays against ours, operation by operation (same slot per pair)
+                ln = r.path_len.astype(np.int64)
+                idx = np.repeat(np.asarray(r.path_off, dtype=np.int64) - (np.cumsum(ln) - ln), ln) + np.arange(int(ln.sum()), dtype=np.int64)
+                cpu_baseline["path_mismatches_on_sample"] = int((r.path_len != hplen[:sample]).sum()) + int((r.path[idx] != hpath[idx]).sum())
+                cpu_baseline["path_operations_on_sample"] = int(ln.sum())
         except Exception as exc:
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % str(exc)[:100]}
 

@@ -68,6 +68,7 @@ def driver_lib():
         _driver = C.CDLL(path)
         _driver.ref_sw_batch_nt.restype = C.c_double
         _driver.ref_ed_batch.restype = C.c_double
+        _driver.ref_ed_path_batch.restype = C.c_double
         rc = _driver.ref_driver_load(os.path.join(REF, "libssw_ref.so").encode(), os.path.join(REF, "libedlib_ref.so").encode())
         if rc != 0:
             raise RuntimeError("ref_driver_load failed: %d" % rc)
@@ -153,11 +154,14 @@ def ref_sw(queries, targets, match=2, mismatch=-3, gap_open=5, gap_extend=2, sco
 
 
 class EdBatchResult:
-    def __init__(self, fixed, loc, loc_off, seconds=None):
+    def __init__(self, fixed, loc, loc_off, seconds=None, path=None, path_off=None, path_len=None):
         self.fixed = fixed      # int32 [n,4]: status, editDistance, alphabetLength, numLocations
         self.loc = loc          # int32 [total,2]: start (INT32_MIN = None), end
         self.loc_off = loc_off
         self.seconds = seconds
+        self.path = path        # task path: uint8 operations, pair i at path_off[i] .. path_off[i] + path_len[i]
+        self.path_off = path_off
+        self.path_len = path_len
 
     def as_dict(self, i):
         st, ed, al, nl = (int(x) for x in self.fixed[i])
@@ -166,7 +170,7 @@ class EdBatchResult:
         return {"status": st, "editDistance": ed, "alphabetLength": al, "locations": locs}
 
 
-def _ed_batch(fn, qcsr, tcsr, mode, task, k, nthreads=None, want_loc=True):
+def _ed_batch(fn, qcsr, tcsr, mode, task, k, nthreads=None, want_loc=True, want_path=False):
     qbuf, qoff = qcsr
     tbuf, toff = tcsr
     n = len(qoff) - 1
@@ -184,10 +188,17 @@ def _ed_batch(fn, qcsr, tcsr, mode, task, k, nthreads=None, want_loc=True):
     if nthreads is not None:
         args.append(C.c_int(nthreads))
     args += [_p(fixed, C.c_int32), _p(loc, C.c_int32) if want_loc else None, C.c_int64(cap), _p(loff, C.c_int64)]
+    path = plen = poff = None
+    if want_path:
+        poff = (np.asarray(qoff) - qoff[0] + np.asarray(toff) - toff[0])[:n]
+        path = np.zeros(int(qoff[n] - qoff[0] + toff[n] - toff[0]) + 1, dtype=np.uint8)
+        plen = np.zeros(max(n, 1), dtype=np.int32)
+        args += [_p(path, C.c_uint8), _p(plen, C.c_int32)]
     rc = fn(*args)
     if rc < 0:
         raise RuntimeError("batch call failed: %r" % rc)
-    return EdBatchResult(fixed, loc[:loff[n]], loff, seconds=float(rc) if nthreads is not None else None)
+    return EdBatchResult(fixed, loc[:loff[n]], loff, seconds=float(rc) if nthreads is not None else None, path=path, path_off=poff,
+                         path_len=None if plen is None else plen[:n])
 
 
 def oracle_ed(queries, targets, mode="NW", task="distance", k=None, csr=False):
@@ -199,4 +210,6 @@ def oracle_ed(queries, targets, mode="NW", task="distance", k=None, csr=False):
 def ref_ed(queries, targets, mode="NW", task="distance", k=None, nthreads=1, csr=False, want_loc=True):
     qcsr = queries if csr else to_csr(queries)
     tcsr = targets if csr else to_csr(targets)
+    if task in ("path", TASKS["path"]):   # the reference's alignment arrays as well (EdlibAlignResult.alignment)
+        return _ed_batch(driver_lib().ref_ed_path_batch, qcsr, tcsr, mode, task, k, nthreads=nthreads, want_loc=want_loc, want_path=True)
     return _ed_batch(driver_lib().ref_ed_batch, qcsr, tcsr, mode, task, k, nthreads=nthreads, want_loc=want_loc)

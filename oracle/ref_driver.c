@@ -216,6 +216,8 @@ typedef struct {
     int32_t *out_fixed;
     int32_t **locs;
     int keep;
+    uint8_t *path_buf;    /* task path: operations of pair p at (qoff[p] - qoff[0]) + (toff[p] - toff[0]) */
+    int32_t *path_len;
 } ed_ctx;
 
 static void ed_one(int64_t p, void *vctx, void **scratch)
@@ -236,15 +238,36 @@ static void ed_one(int64_t p, void *vctx, void **scratch)
             c->locs[p][2 * a + 1] = r.endLocations ? r.endLocations[a] : INT32_MIN;
         }
     }
+    if (c->path_buf) {
+        c->path_len[p] = r.alignment ? r.alignmentLength : 0;
+        if (r.alignment)
+            memcpy(c->path_buf + (c->qoff[p] - c->qoff[0]) + (c->toff[p] - c->toff[0]), r.alignment, (size_t)r.alignmentLength);
+    }
     p_edlib_free(r);
 }
+
+/* EdlibAlignResult.alignment of every pair (task path) next to the fields ref_ed_batch reports; path_buf holds
+ * total query + target bytes, path_len[p] = alignmentLength (0: no alignment). */
+double ref_ed_path_batch(const char *qbuf, const int64_t *qoff, const char *tbuf, const int64_t *toff,
+                         int64_t npairs, int32_t mode, int32_t task, const int32_t *k, int nthreads,
+                         int32_t *out_fixed, int32_t *loc_buf, int64_t loc_cap, int64_t *loc_off,
+                         uint8_t *path_buf, int32_t *path_len);
 
 double ref_ed_batch(const char *qbuf, const int64_t *qoff, const char *tbuf, const int64_t *toff,
                     int64_t npairs, int32_t mode, int32_t task, const int32_t *k, int nthreads,
                     int32_t *out_fixed, int32_t *loc_buf, int64_t loc_cap, int64_t *loc_off)
 {
+    return ref_ed_path_batch(qbuf, qoff, tbuf, toff, npairs, mode, task, k, nthreads, out_fixed, loc_buf, loc_cap, loc_off, NULL, NULL);
+}
+
+double ref_ed_path_batch(const char *qbuf, const int64_t *qoff, const char *tbuf, const int64_t *toff,
+                         int64_t npairs, int32_t mode, int32_t task, const int32_t *k, int nthreads,
+                         int32_t *out_fixed, int32_t *loc_buf, int64_t loc_cap, int64_t *loc_off,
+                         uint8_t *path_buf, int32_t *path_len)
+{
     ed_ctx c;
     memset(&c, 0, sizeof(c));
+    c.path_buf = path_len ? path_buf : NULL; c.path_len = path_len;
     c.qbuf = qbuf; c.tbuf = tbuf; c.qoff = qoff; c.toff = toff; c.mode = mode; c.task = task; c.k = k;
     c.out_fixed = out_fixed;
     c.locs = (int32_t **)calloc((size_t)(npairs > 0 ? npairs : 1), sizeof(int32_t *));
