@@ -424,6 +424,8 @@ static int launch_myers(Engine *e, const EdArgs &a, cudaStream_t st)
 }
 
 // ---- task "path" (edlib.cpp:268-285, 1177-1412) ---------------------------------------------------------------------------
+constexpr int ED_PATH_WARP_MIN_W = 8;     // query words from which a pair goes to the warp kernel
+constexpr int ED_PATH_WARP_MAX_W = 256;   // 8 words per lane
 struct EdPathArgs {
     const EdPair *pairs;
     const uint64_t *peq;
@@ -438,6 +440,7 @@ struct EdPathArgs {
     int64_t stride;
     int32_t leaf_bytes, vec_bytes, col_bytes;
     int32_t *counter;
+    int32_t split;              // 1: pairs of ED_PATH_WARP_MIN_W..MAX_W query words belong to ed_path_warp_kernel
 };
 
 // Thread per pair, pairs handed out through a counter (their cost spans five orders of magnitude).  The alignment is the
@@ -459,6 +462,7 @@ __global__ void __launch_bounds__(64) ed_path_kernel(EdPathArgs a)
         const int64_t p = atomicAdd(a.counter, 1);
         if (p >= a.npairs) break;
         const EdPair pr = a.pairs[p];
+        if (a.split && pr.W >= ED_PATH_WARP_MIN_W && pr.W <= ED_PATH_WARP_MAX_W) continue;   // ed_path_warp_kernel's pairs
         const db200_ed_result r = a.results[p];
         int len = 0;
         if (!pr.special && r.status == 0 && r.edit_distance >= 0 && r.num_locations > 0) {
@@ -468,6 +472,182 @@ __global__ void __launch_bounds__(64) ed_path_kernel(EdPathArgs a)
                                a.path_buf + pr.q_off + pr.t_off);
         }
         a.path_len[p] = len;   // -1: no split consistent with the distance was found (an internal error, reported by the host)
+    }
+}
+
+// ---- long pairs: one warp per pair ---------------------------------------------------------------------------------------
+// The same steps as ed_path_pair, with the two sweeps - score columns of the halving step, stored columns of a leaf - run
+// as a wavefront over the lanes: lane l owns WL consecutive 64-row words in registers and works on column s - l at step s,
+// the horizontal delta of a lane boundary travels with __shfl_up_sync.  The walk back over a leaf is the scalar
+// path_leaf_walk on lane 0.
+
+template <int WL, bool STORE>
+__device__ __noinline__ void path_warp_sweep(const uint64_t *peq, const uint8_t *tcodes, int W, int q0, int q1, int tfirst, int ncol,
+                                             bool reverse, uint64_t *PM, int32_t *out)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int qlen = q1 - q0, Wq = (qlen + 63) >> 6;
+    const int w0 = lane * WL;
+    const int nw = max(0, min(WL, Wq - w0));
+    const int nl = (Wq + WL - 1) / WL;   // lanes that own words
+    uint64_t Pv[WL], Mv[WL];
+#pragma unroll
+    for (int i = 0; i < WL; ++i) { Pv[i] = ~0ull; Mv[i] = 0ull; }
+    uint32_t cp = 0, cm = 0;             // deltas leaving this lane's last word at the previous step
+    const int steps = ncol + nl - 1;
+    for (int s = 0; s < steps; ++s) {
+        uint32_t hp = __shfl_up_sync(FULL, cp, 1), hm = __shfl_up_sync(FULL, cm, 1);
+        if (lane == 0) { hp = 1; hm = 0; }   // the row above the matrix grows by one per column
+        const int c = s - lane;
+        if (nw > 0 && c >= 0 && c < ncol) {
+            const uint64_t *row = peq + (long)tcodes[reverse ? tfirst - c : tfirst + c] * W;
+            uint64_t hin_p = hp, hin_m = hm;
+#pragma unroll
+            for (int i = 0; i < WL; ++i) {
+                if (i < nw) {
+                    const int w = w0 + i;
+                    uint64_t Eq = reverse ? __brevll(path_bits(row, W, (long)q1 - 64L * (w + 1))) : path_bits(row, W, (long)q0 + 64L * w);
+                    const uint64_t pv = Pv[i], mv = Mv[i];
+                    const uint64_t Xv = Eq | mv;
+                    Eq |= hin_m;
+                    const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+                    uint64_t Ph = mv | ~(Xh | pv);
+                    uint64_t Mh = pv & Xh;
+                    const uint64_t op = Ph >> 63, om = Mh >> 63;
+                    Ph = (Ph << 1) | hin_p;
+                    Mh = (Mh << 1) | hin_m;
+                    Pv[i] = Mh | ~(Xv | Ph);
+                    Mv[i] = Ph & Xv;
+                    if (STORE) {
+                        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(PM + ((long)c * Wq + w) * 2);
+                        *dst = make_ulonglong2(Pv[i], Mv[i]);
+                    }
+                    hin_p = op; hin_m = om;
+                }
+            }
+            cp = (uint32_t)hin_p; cm = (uint32_t)hin_m;
+        }
+    }
+    if (!STORE) {
+        // out[r] = ncol + vertical deltas of rows 0..r: totals of the earlier lanes by a warp scan, then bit by bit
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < WL; ++i) if (i < nw) tot += __popcll(Pv[i]) - __popcll(Mv[i]);
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int sc = ncol + incl - tot;
+#pragma unroll
+        for (int i = 0; i < WL; ++i) {
+            if (i < nw) {
+                const int r0 = (w0 + i) * 64;
+                const int nb = min(64, qlen - r0);
+                for (int b = 0; b < nb; ++b) {
+                    sc += (int)((Pv[i] >> b) & 1ull) - (int)((Mv[i] >> b) & 1ull);
+                    out[r0 + b] = sc;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <bool STORE>
+__device__ __forceinline__ void path_warp_sweep_any(const uint64_t *peq, const uint8_t *tcodes, int W, int q0, int q1, int tfirst, int ncol,
+                                                    bool reverse, uint64_t *PM, int32_t *out)
+{
+    const int Wq = (q1 - q0 + 63) >> 6;
+    if (Wq <= 32) path_warp_sweep<1, STORE>(peq, tcodes, W, q0, q1, tfirst, ncol, reverse, PM, out);
+    else if (Wq <= 64) path_warp_sweep<2, STORE>(peq, tcodes, W, q0, q1, tfirst, ncol, reverse, PM, out);
+    else if (Wq <= 128) path_warp_sweep<4, STORE>(peq, tcodes, W, q0, q1, tfirst, ncol, reverse, PM, out);
+    else path_warp_sweep<8, STORE>(peq, tcodes, W, q0, q1, tfirst, ncol, reverse, PM, out);
+}
+
+// ed_path_pair for a whole warp (every lane follows the same control flow; m <= 64 * ED_PATH_WARP_MAX_W)
+__device__ int ed_path_pair_warp(const uint64_t *peq, const uint8_t *tcodes, int W, int m, int t0, int t1, int best, const EdPathScratch &s,
+                                 uint8_t *out)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    int stack[ED_PATH_STACK][5];
+    int sp = 0, n = 0;
+    stack[sp][0] = 0; stack[sp][1] = m; stack[sp][2] = t0; stack[sp][3] = t1; stack[sp][4] = best; ++sp;
+    while (sp > 0) {
+        __syncwarp();
+        --sp;
+        const int q0 = stack[sp][0], q1 = stack[sp][1], a0 = stack[sp][2], a1 = stack[sp][3], score = stack[sp][4];
+        const int qlen = q1 - q0, tlen = a1 - a0;
+        if (qlen == 0 || tlen == 0) {
+            for (int k = lane; k < tlen; k += 32) out[n + k] = 2;
+            for (int k = lane; k < qlen; k += 32) out[n + tlen + k] = 1;
+            n += tlen + qlen;
+            continue;
+        }
+        const long long blocks = (qlen + 63) >> 6;
+        const long long state = (2ll * 8 + 4) * blocks * tlen + 2ll * 4 * tlen;   // the reference's 1 MB rule (edlib.cpp:1204-1206)
+        if (state < 1024 * 1024) {
+            path_warp_sweep_any<true>(peq, tcodes, W, q0, q1, a0, tlen, false, s.dir, nullptr);
+            int k = 0;
+            if (lane == 0) k = path_leaf_walk(s.dir, qlen, tlen, s.tmp, out + n);
+            n += __shfl_sync(FULL, k, 0);
+            continue;
+        }
+        const int lw = tlen / 2, rw = tlen - lw;
+        path_warp_sweep_any<false>(peq, tcodes, W, q0, q1, a0, lw, false, nullptr, s.left);
+        path_warp_sweep_any<false>(peq, tcodes, W, q0, q1, a1 - 1, rw, true, nullptr, s.right);
+        // first query index whose two halves add up to the optimum, then the two boundary cases (edlib.cpp:1330-1372)
+        int idx = -2, ls = 0, rs = 0;
+        for (int base = 0; base <= qlen - 2 && idx == -2; base += 32) {
+            const int qi = base + lane;
+            const bool hit = qi <= qlen - 2 && s.left[qi] + s.right[qlen - 2 - qi] == score;
+            const unsigned b = __ballot_sync(FULL, hit);
+            if (b) idx = base + __ffs(b) - 1;
+        }
+        if (idx >= 0) { ls = s.left[idx]; rs = s.right[qlen - 2 - idx]; }
+        if (idx == -2 && lw + s.right[qlen - 1] == score) { idx = -1; ls = lw; rs = s.right[qlen - 1]; }
+        if (idx == -2 && s.left[qlen - 1] + rw == score) { idx = qlen - 1; ls = s.left[qlen - 1]; rs = rw; }
+        if (idx == -2 || sp + 2 > ED_PATH_STACK) return -1;
+        const int qs = q0 + idx + 1;
+        stack[sp][0] = qs; stack[sp][1] = q1; stack[sp][2] = a0 + lw; stack[sp][3] = a1; stack[sp][4] = rs; ++sp;
+        stack[sp][0] = q0; stack[sp][1] = qs; stack[sp][2] = a0; stack[sp][3] = a0 + lw; stack[sp][4] = ls; ++sp;
+    }
+    __syncwarp();
+    return n;
+}
+
+__global__ void __launch_bounds__(128) ed_path_warp_kernel(EdPathArgs a)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    uint8_t *base = a.scratch + wid * a.stride;
+    EdPathScratch s;
+    s.dir = reinterpret_cast<uint64_t *>(base);
+    s.Pv = nullptr; s.Mv = nullptr;   // the vectors live in registers
+    s.left = reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes);
+    s.right = reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + a.col_bytes);
+    s.tmp = base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + 2 * (int64_t)a.col_bytes;
+    while (true) {
+        __syncwarp();
+        int64_t p = 0;
+        if (lane == 0) p = atomicAdd(a.counter, 1);
+        p = __shfl_sync(FULL, p, 0);
+        if (p >= a.npairs) break;
+        const EdPair pr = a.pairs[p];
+        if (pr.W < ED_PATH_WARP_MIN_W || pr.W > ED_PATH_WARP_MAX_W) continue;   // ed_path_kernel's pairs
+        const db200_ed_result r = a.results[p];
+        int len = 0;
+        if (!pr.special && r.status == 0 && r.edit_distance >= 0 && r.num_locations > 0) {
+            const int64_t l = a.loc_off[p];
+            const int start = a.loc_buf[2 * l], end = a.loc_buf[2 * l + 1];
+            len = ed_path_pair_warp(a.peq + pr.peq_off, a.tcodes + pr.t_off, pr.W, pr.m, start, end + 1, r.edit_distance, s,
+                                    a.path_buf + pr.q_off + pr.t_off);
+        }
+        if (lane == 0) a.path_len[p] = len;
     }
 }
 
@@ -686,23 +866,43 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     }
     prof_mark(e, st, ST_ED_STARTS);
     if (want_path) {
-        // scratch per thread: the reference's 1 MB rule bounds the stored columns of a leaf, the rest follows the longest query
-        const int64_t Wq = Wmax, maxt = std::max(max_target_len, 1);
+        // Pairs of 8..256 query words go to the warp kernel, the rest to the thread kernel.  Scratch per worker: the
+        // reference's 1 MB rule bounds the stored columns of a leaf, the rest follows the longest query it can meet.
+        const int64_t maxt = std::max(max_target_len, 1);
+        const bool split = Wmax >= ED_PATH_WARP_MIN_W;
+        const int64_t budget = (int64_t)3 << 29;   // 1.5 GB of scratch per kernel at most
+        auto layout = [&](EdPathArgs &xa, int64_t qcap) {
+            const int64_t Wq = (qcap + 63) / 64;
+            xa.leaf_bytes = (int32_t)std::min<int64_t>(ED_PATH_LEAF_BYTES, 16 * Wq * maxt);
+            xa.vec_bytes = (int32_t)(8 * Wq);
+            xa.col_bytes = (int32_t)((4 * (qcap + 1) + 7) & ~7ll);
+            xa.stride = (xa.leaf_bytes + 2 * (int64_t)xa.vec_bytes + 2 * (int64_t)xa.col_bytes + qcap + maxt + 1 + 15) & ~15ll;
+        };
         EdPathArgs xa;
         memset(&xa, 0, sizeof(xa));
-        xa.leaf_bytes = (int32_t)std::min<int64_t>(ED_PATH_LEAF_BYTES, 16 * Wq * maxt);
-        xa.vec_bytes = (int32_t)(8 * Wq);
-        xa.col_bytes = (int32_t)((4 * ((int64_t)std::max(max_query_len, 1) + 1) + 7) & ~7ll);
-        xa.stride = (xa.leaf_bytes + 2 * (int64_t)xa.vec_bytes + 2 * (int64_t)xa.col_bytes + (int64_t)std::max(max_query_len, 0) + maxt + 1 + 15) & ~15ll;
-        const int64_t budget = (int64_t)3 << 29;   // 1.5 GB of scratch at most
-        int64_t threads = std::min<int64_t>(npairs, (int64_t)e->sm_count * 256);
-        threads = std::max<int64_t>(64, std::min(threads, budget / xa.stride) / 64 * 64);
-        xa.scratch = ws.alloc<uint8_t>((size_t)(threads * xa.stride));
-        if (!xa.scratch) { set_error("ed_batch: device workspace allocation failed (path scratch)"); return DB200_ERR_NOMEM; }
         xa.pairs = pairs; xa.peq = peq; xa.tcodes = tcodes; xa.results = d_results; xa.loc_off = d_loc_off; xa.loc_buf = d_loc_buf;
-        xa.path_buf = d_path_buf; xa.path_len = d_path_len; xa.npairs = npairs; xa.counter = counters + (ci++);
-        ed_path_kernel<<<(unsigned)(threads / 64), 64, 0, st>>>(xa);
-        count_launch(e);
+        xa.path_buf = d_path_buf; xa.path_len = d_path_len; xa.npairs = npairs; xa.split = split ? 1 : 0;
+        {
+            const int64_t qmax = std::max(max_query_len, 1);
+            layout(xa, (split && Wmax <= ED_PATH_WARP_MAX_W) ? std::min<int64_t>(qmax, 64 * (ED_PATH_WARP_MIN_W - 1)) : qmax);
+            int64_t threads = std::min<int64_t>((npairs + 63) / 64 * 64, (int64_t)e->sm_count * 256);
+            threads = std::max<int64_t>(64, std::min(threads, budget / xa.stride) / 64 * 64);
+            xa.scratch = ws.alloc<uint8_t>((size_t)(threads * xa.stride));
+            if (!xa.scratch) { set_error("ed_batch: device workspace allocation failed (path scratch)"); return DB200_ERR_NOMEM; }
+            xa.counter = counters + (ci++);
+            ed_path_kernel<<<(unsigned)(threads / 64), 64, 0, st>>>(xa);
+            count_launch(e);
+        }
+        if (split) {
+            layout(xa, std::min<int64_t>(std::max(max_query_len, 1), 64 * ED_PATH_WARP_MAX_W));
+            int64_t warps = std::min<int64_t>((npairs + 3) / 4 * 4, (int64_t)e->sm_count * 16);
+            warps = std::max<int64_t>(4, std::min(warps, budget / xa.stride) / 4 * 4);
+            xa.scratch = ws.alloc<uint8_t>((size_t)(warps * xa.stride));
+            if (!xa.scratch) { set_error("ed_batch: device workspace allocation failed (path scratch)"); return DB200_ERR_NOMEM; }
+            xa.counter = counters + (ci++);
+            ed_path_warp_kernel<<<(unsigned)(warps / 4), 128, 0, st>>>(xa);
+            count_launch(e);
+        }
         prof_mark(e, st, ST_ED_PATH);
     }
     DB200_CUDA_CHECK(cudaGetLastError());

@@ -103,6 +103,40 @@ DB200_HD int path_leaf_cell(const uint64_t *pm, int i, int j)
     return s + DB200_POPC64(pm[2 * full] & mask) - DB200_POPC64(pm[2 * full + 1] & mask);
 }
 
+// The walk back over the stored columns of a leaf (edlib.cpp:958-1157): from the bottom-right corner, preferring "up"
+// (insertion), then "left" (deletion), then the diagonal; the rest of the first row / column once it leaves the matrix.
+DB200_HD int path_leaf_walk(const uint64_t *PM, int qlen, int tlen, uint8_t *tmp, uint8_t *out)
+{
+    const int Wq = (qlen + 63) >> 6;
+    int i = qlen - 1, j = tlen - 1, n = 0;
+    int cur = path_leaf_cell(PM + (long)j * Wq * 2, i, j);
+    int left = j > 0 ? path_leaf_cell(PM + (long)(j - 1) * Wq * 2, i, j - 1) : i + 1;   // D[i][j-1]; column -1 holds i + 1
+    while (i >= 0 && j >= 0) {
+        const uint64_t *pc = PM + (long)j * Wq * 2 + 2 * (i >> 6);
+        const int sh = i & 63;
+        const int vc = (int)((pc[0] >> sh) & 1ull) - (int)((pc[1] >> sh) & 1ull);
+        int vl = 1;
+        if (j > 0) {
+            const uint64_t *pl = pc - (long)Wq * 2;
+            vl = (int)((pl[0] >> sh) & 1ull) - (int)((pl[1] >> sh) & 1ull);
+        }
+        const int up = cur - vc, diag = left - vl;
+        const int op = (up + 1 == cur) ? 1 : ((left + 1 == cur) ? 2 : (diag == cur ? 0 : 3));
+        tmp[n++] = (uint8_t)op;
+        if (op == 1) { --i; cur = up; left = diag; }
+        else {
+            cur = (op == 2) ? left : diag;
+            if (op != 2) --i;
+            --j;
+            if (i >= 0 && j >= 0) left = j > 0 ? path_leaf_cell(PM + (long)(j - 1) * Wq * 2, i, j - 1) : i + 1;
+        }
+    }
+    for (; j >= 0; --j) tmp[n++] = 2;                           // the rest of the first row: deletions
+    for (; i >= 0; --i) tmp[n++] = 1;                           // the rest of the first column: insertions
+    for (int k = 0; k < n; ++k) out[k] = tmp[n - 1 - k];
+    return n;
+}
+
 // Traceback of a sub-problem small enough for the reference's direct method (edlib.cpp:1204-1221, 958-1157).  The sweep
 // keeps the vertical delta vectors (Pv, Mv) of every column - 16 bytes per 64 cells, the reference's own 1 MB rule bounds
 // them by ED_PATH_LEAF_BYTES - and the walk rebuilds the three neighbour values from them: up and diagonal from one bit
@@ -135,33 +169,7 @@ DB200_HD int path_leaf(const uint64_t *peq, const uint8_t *tcodes, int W, int q0
             hp = op; hm = om;
         }
     }
-    int i = qlen - 1, j = tlen - 1, n = 0;
-    int cur = path_leaf_cell(PM + (long)j * Wq * 2, i, j);
-    int left = j > 0 ? path_leaf_cell(PM + (long)(j - 1) * Wq * 2, i, j - 1) : i + 1;   // D[i][j-1]; column -1 holds i + 1
-    while (i >= 0 && j >= 0) {
-        const uint64_t *pc = PM + (long)j * Wq * 2 + 2 * (i >> 6);
-        const int sh = i & 63;
-        const int vc = (int)((pc[0] >> sh) & 1ull) - (int)((pc[1] >> sh) & 1ull);
-        int vl = 1;
-        if (j > 0) {
-            const uint64_t *pl = pc - (long)Wq * 2;
-            vl = (int)((pl[0] >> sh) & 1ull) - (int)((pl[1] >> sh) & 1ull);
-        }
-        const int up = cur - vc, diag = left - vl;
-        const int op = (up + 1 == cur) ? 1 : ((left + 1 == cur) ? 2 : (diag == cur ? 0 : 3));
-        s.tmp[n++] = (uint8_t)op;
-        if (op == 1) { --i; cur = up; left = diag; }
-        else {
-            cur = (op == 2) ? left : diag;
-            if (op != 2) --i;
-            --j;
-            if (i >= 0 && j >= 0) left = j > 0 ? path_leaf_cell(PM + (long)(j - 1) * Wq * 2, i, j - 1) : i + 1;
-        }
-    }
-    for (; j >= 0; --j) s.tmp[n++] = 2;                           // the rest of the first row: deletions
-    for (; i >= 0; --i) s.tmp[n++] = 1;                           // the rest of the first column: insertions
-    for (int k = 0; k < n; ++k) out[k] = s.tmp[n - 1 - k];
-    return n;
+    return path_leaf_walk(PM, qlen, tlen, s.tmp, out);
 }
 
 // Operations (0 match, 1 insertion, 2 deletion, 3 mismatch) aligning the whole query of m symbols to target[t0..t1) at
