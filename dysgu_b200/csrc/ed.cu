@@ -481,9 +481,9 @@ __global__ void __launch_bounds__(64) ed_path_kernel(EdPathArgs a)
 // the horizontal delta of a lane boundary travels with __shfl_up_sync.  The walk back over a leaf is the scalar
 // path_leaf_walk on lane 0.
 
-template <int WL, bool STORE>
+template <int WL, bool STORE, bool REV>
 __device__ __noinline__ void path_warp_sweep(const uint64_t *peq, const uint8_t *tcodes, int W, int q0, int q1, int tfirst, int ncol,
-                                             bool reverse, uint64_t *PM, int32_t *out)
+                                             uint64_t *PM, int32_t *out)
 {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -491,9 +491,20 @@ __device__ __noinline__ void path_warp_sweep(const uint64_t *peq, const uint8_t 
     const int w0 = lane * WL;
     const int nw = max(0, min(WL, Wq - w0));
     const int nl = (Wq + WL - 1) / WL;   // lanes that own words
-    uint64_t Pv[WL], Mv[WL];
+    // Match-vector bits of this lane: forward word w covers query positions [q0 + 64 w, + 64), reverse word w covers
+    // [q1 - 64 (w + 1), + 64) read backwards - either way 64 bits at one fixed bit offset into WL + 1 consecutive words of a
+    // Peq row (zero outside the row), loaded once per column.
+    const long pos0 = REV ? (long)q1 - 64L * (w0 + WL) : (long)q0 + 64L * w0;
+    const long wb = pos0 >= 0 ? (pos0 >> 6) : -((-pos0 + 63) >> 6);
+    const int sh = (int)(pos0 - wb * 64);
+    uint32_t vmask = 0;
 #pragma unroll
-    for (int i = 0; i < WL; ++i) { Pv[i] = ~0ull; Mv[i] = 0ull; }
+    for (int k = 0; k <= WL; ++k) vmask |= (wb + k >= 0 && wb + k < W) ? (1u << k) : 0u;
+    uint64_t Pv[WL], Mv[WL];
+    int32_t end[WL];                     // value of each word's last row (column -1: 64 w + 64)
+#pragma unroll
+    for (int i = 0; i < WL; ++i) { Pv[i] = ~0ull; Mv[i] = 0ull; end[i] = 64 * (w0 + i + 1); }
+    int32_t *E = STORE ? reinterpret_cast<int32_t *>(PM + (long)ncol * Wq * 2) : nullptr;
     uint32_t cp = 0, cm = 0;             // deltas leaving this lane's last word at the previous step
     const int steps = ncol + nl - 1;
     for (int s = 0; s < steps; ++s) {
@@ -501,13 +512,17 @@ __device__ __noinline__ void path_warp_sweep(const uint64_t *peq, const uint8_t 
         if (lane == 0) { hp = 1; hm = 0; }   // the row above the matrix grows by one per column
         const int c = s - lane;
         if (nw > 0 && c >= 0 && c < ncol) {
-            const uint64_t *row = peq + (long)tcodes[reverse ? tfirst - c : tfirst + c] * W;
+            const uint64_t *row = peq + (long)tcodes[REV ? tfirst - c : tfirst + c] * W + wb;
+            uint64_t r[WL + 1];
+#pragma unroll
+            for (int k = 0; k <= WL; ++k) r[k] = ((vmask >> k) & 1u) ? row[k] : 0ull;
             uint64_t hin_p = hp, hin_m = hm;
 #pragma unroll
             for (int i = 0; i < WL; ++i) {
                 if (i < nw) {
-                    const int w = w0 + i;
-                    uint64_t Eq = reverse ? __brevll(path_bits(row, W, (long)q1 - 64L * (w + 1))) : path_bits(row, W, (long)q0 + 64L * w);
+                    const uint64_t lo = REV ? r[WL - 1 - i] : r[i], hi = REV ? r[WL - i] : r[i + 1];
+                    uint64_t Eq = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+                    if (REV) Eq = __brevll(Eq);
                     const uint64_t pv = Pv[i], mv = Mv[i];
                     const uint64_t Xv = Eq | mv;
                     Eq |= hin_m;
@@ -520,8 +535,10 @@ __device__ __noinline__ void path_warp_sweep(const uint64_t *peq, const uint8_t 
                     Pv[i] = Mh | ~(Xv | Ph);
                     Mv[i] = Ph & Xv;
                     if (STORE) {
-                        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(PM + ((long)c * Wq + w) * 2);
-                        *dst = make_ulonglong2(Pv[i], Mv[i]);
+                        const long k = (long)c * Wq + w0 + i;
+                        *reinterpret_cast<ulonglong2 *>(PM + 2 * k) = make_ulonglong2(Pv[i], Mv[i]);
+                        end[i] += (int)op - (int)om;
+                        E[k] = end[i];
                     }
                     hin_p = op; hin_m = om;
                 }
@@ -546,8 +563,10 @@ __device__ __noinline__ void path_warp_sweep(const uint64_t *peq, const uint8_t 
             if (i < nw) {
                 const int r0 = (w0 + i) * 64;
                 const int nb = min(64, qlen - r0);
+                uint64_t p = Pv[i], mm = Mv[i];
                 for (int b = 0; b < nb; ++b) {
-                    sc += (int)((Pv[i] >> b) & 1ull) - (int)((Mv[i] >> b) & 1ull);
+                    sc += (int)(p & 1ull) - (int)(mm & 1ull);
+                    p >>= 1; mm >>= 1;
                     out[r0 + b] = sc;
                 }
             }
@@ -556,15 +575,15 @@ __device__ __noinline__ void path_warp_sweep(const uint64_t *peq, const uint8_t 
     __syncwarp();
 }
 
-template <bool STORE>
+template <bool STORE, bool REV>
 __device__ __forceinline__ void path_warp_sweep_any(const uint64_t *peq, const uint8_t *tcodes, int W, int q0, int q1, int tfirst, int ncol,
-                                                    bool reverse, uint64_t *PM, int32_t *out)
+                                                    uint64_t *PM, int32_t *out)
 {
     const int Wq = (q1 - q0 + 63) >> 6;
-    if (Wq <= 32) path_warp_sweep<1, STORE>(peq, tcodes, W, q0, q1, tfirst, ncol, reverse, PM, out);
-    else if (Wq <= 64) path_warp_sweep<2, STORE>(peq, tcodes, W, q0, q1, tfirst, ncol, reverse, PM, out);
-    else if (Wq <= 128) path_warp_sweep<4, STORE>(peq, tcodes, W, q0, q1, tfirst, ncol, reverse, PM, out);
-    else path_warp_sweep<8, STORE>(peq, tcodes, W, q0, q1, tfirst, ncol, reverse, PM, out);
+    if (Wq <= 32) path_warp_sweep<1, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out);
+    else if (Wq <= 64) path_warp_sweep<2, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out);
+    else if (Wq <= 128) path_warp_sweep<4, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out);
+    else path_warp_sweep<8, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out);
 }
 
 // ed_path_pair for a whole warp (every lane follows the same control flow; m <= 64 * ED_PATH_WARP_MAX_W)
@@ -590,15 +609,15 @@ __device__ int ed_path_pair_warp(const uint64_t *peq, const uint8_t *tcodes, int
         const long long blocks = (qlen + 63) >> 6;
         const long long state = (2ll * 8 + 4) * blocks * tlen + 2ll * 4 * tlen;   // the reference's 1 MB rule (edlib.cpp:1204-1206)
         if (state < 1024 * 1024) {
-            path_warp_sweep_any<true>(peq, tcodes, W, q0, q1, a0, tlen, false, s.dir, nullptr);
+            path_warp_sweep_any<true, false>(peq, tcodes, W, q0, q1, a0, tlen, s.dir, nullptr);
             int k = 0;
             if (lane == 0) k = path_leaf_walk(s.dir, qlen, tlen, s.tmp, out + n);
             n += __shfl_sync(FULL, k, 0);
             continue;
         }
         const int lw = tlen / 2, rw = tlen - lw;
-        path_warp_sweep_any<false>(peq, tcodes, W, q0, q1, a0, lw, false, nullptr, s.left);
-        path_warp_sweep_any<false>(peq, tcodes, W, q0, q1, a1 - 1, rw, true, nullptr, s.right);
+        path_warp_sweep_any<false, false>(peq, tcodes, W, q0, q1, a0, lw, nullptr, s.left);
+        path_warp_sweep_any<false, true>(peq, tcodes, W, q0, q1, a1 - 1, rw, nullptr, s.right);
         // first query index whose two halves add up to the optimum, then the two boundary cases (edlib.cpp:1330-1372)
         int idx = -2, ls = 0, rs = 0;
         for (int base = 0; base <= qlen - 2 && idx == -2; base += 32) {
@@ -873,7 +892,7 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
         const int64_t budget = (int64_t)3 << 29;   // 1.5 GB of scratch per kernel at most
         auto layout = [&](EdPathArgs &xa, int64_t qcap) {
             const int64_t Wq = (qcap + 63) / 64;
-            xa.leaf_bytes = (int32_t)std::min<int64_t>(ED_PATH_LEAF_BYTES, 16 * Wq * maxt);
+            xa.leaf_bytes = (int32_t)std::min<int64_t>(ED_PATH_LEAF_BYTES, (20 * Wq * maxt + 15) & ~15ll);
             xa.vec_bytes = (int32_t)(8 * Wq);
             xa.col_bytes = (int32_t)((4 * (qcap + 1) + 7) & ~7ll);
             xa.stride = (xa.leaf_bytes + 2 * (int64_t)xa.vec_bytes + 2 * (int64_t)xa.col_bytes + qcap + maxt + 1 + 15) & ~15ll;
@@ -896,7 +915,7 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
         if (split) {
             layout(xa, std::min<int64_t>(std::max(max_query_len, 1), 64 * ED_PATH_WARP_MAX_W));
             int64_t warps = std::min<int64_t>((npairs + 3) / 4 * 4, (int64_t)e->sm_count * 16);
-            warps = std::max<int64_t>(4, std::min(warps, budget / xa.stride) / 4 * 4);
+            warps = std::max<int64_t>(4, std::min(warps, 2 * budget / xa.stride) / 4 * 4);   // up to 3 GB: a full leaf per warp
             xa.scratch = ws.alloc<uint8_t>((size_t)(warps * xa.stride));
             if (!xa.scratch) { set_error("ed_batch: device workspace allocation failed (path scratch)"); return DB200_ERR_NOMEM; }
             xa.counter = counters + (ci++);

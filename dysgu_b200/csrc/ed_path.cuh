@@ -33,8 +33,8 @@ constexpr int ED_PATH_STACK = 64;
 
 struct EdPathScratch {
     uint64_t *Pv, *Mv;        // [ceil(m / 64)] each
-    int32_t *left, *right;    // [m] score columns of the two halves
-    uint64_t *dir;            // [ED_PATH_LEAF_BYTES / 8] (Pv, Mv) of every leaf column
+    int32_t *left, *right;    // [m] score columns of the two halves (left doubles as the leaf sweep's running last rows)
+    uint64_t *dir;            // [ED_PATH_LEAF_BYTES / 8] stored leaf: (Pv, Mv) and last-row value per word and column
     uint8_t *tmp;             // [m + n] operations of a leaf, last first
 };
 
@@ -93,14 +93,16 @@ DB200_HD void path_score_column(const uint64_t *peq, const uint8_t *tcodes, int 
     }
 }
 
-// D[i][j] of a stored leaf column: j + 1 symbols of the target above the matrix plus the vertical deltas of rows 0..i
-DB200_HD int path_leaf_cell(const uint64_t *pm, int i, int j)
+// Stored leaf: for every column j and 64-row word w the vertical delta vectors PM[(j * Wq + w) * 2 + {0, 1}] = (Pv, Mv) and,
+// behind them, the value of the word's last row E[j * Wq + w] = D[64 * w + 63][j] - the reference keeps the same three
+// things per block (edlib.cpp:1204-1206: 2 words + 1 int), so its 1 MB rule bounds this layout by ED_PATH_LEAF_BYTES.
+// D[i][j] = the end of i's word minus the deltas of the rows below i in that word (rows past the query's end continue
+// the recurrence consistently, whatever their match bits are).
+DB200_HD int path_leaf_cell(const uint64_t *PM, const int32_t *E, int Wq, int i, int j)
 {
-    int s = j + 1;
-    const int full = i >> 6;
-    for (int w = 0; w < full; ++w) s += DB200_POPC64(pm[2 * w]) - DB200_POPC64(pm[2 * w + 1]);
-    const uint64_t mask = ~0ull >> (63 - (i & 63));
-    return s + DB200_POPC64(pm[2 * full] & mask) - DB200_POPC64(pm[2 * full + 1] & mask);
+    const long k = (long)j * Wq + (i >> 6);
+    const uint64_t below = (i & 63) == 63 ? 0ull : (~0ull << ((i & 63) + 1));
+    return E[k] - DB200_POPC64(PM[2 * k] & below) + DB200_POPC64(PM[2 * k + 1] & below);
 }
 
 // The walk back over the stored columns of a leaf (edlib.cpp:958-1157): from the bottom-right corner, preferring "up"
@@ -108,9 +110,10 @@ DB200_HD int path_leaf_cell(const uint64_t *pm, int i, int j)
 DB200_HD int path_leaf_walk(const uint64_t *PM, int qlen, int tlen, uint8_t *tmp, uint8_t *out)
 {
     const int Wq = (qlen + 63) >> 6;
+    const int32_t *E = reinterpret_cast<const int32_t *>(PM + (long)tlen * Wq * 2);
     int i = qlen - 1, j = tlen - 1, n = 0;
-    int cur = path_leaf_cell(PM + (long)j * Wq * 2, i, j);
-    int left = j > 0 ? path_leaf_cell(PM + (long)(j - 1) * Wq * 2, i, j - 1) : i + 1;   // D[i][j-1]; column -1 holds i + 1
+    int cur = path_leaf_cell(PM, E, Wq, i, j);
+    int left = j > 0 ? path_leaf_cell(PM, E, Wq, i, j - 1) : i + 1;   // D[i][j-1]; column -1 holds i + 1
     while (i >= 0 && j >= 0) {
         const uint64_t *pc = PM + (long)j * Wq * 2 + 2 * (i >> 6);
         const int sh = i & 63;
@@ -128,7 +131,7 @@ DB200_HD int path_leaf_walk(const uint64_t *PM, int qlen, int tlen, uint8_t *tmp
             cur = (op == 2) ? left : diag;
             if (op != 2) --i;
             --j;
-            if (i >= 0 && j >= 0) left = j > 0 ? path_leaf_cell(PM + (long)(j - 1) * Wq * 2, i, j - 1) : i + 1;
+            if (i >= 0 && j >= 0) left = j > 0 ? path_leaf_cell(PM, E, Wq, i, j - 1) : i + 1;
         }
     }
     for (; j >= 0; --j) tmp[n++] = 2;                           // the rest of the first row: deletions
@@ -138,16 +141,18 @@ DB200_HD int path_leaf_walk(const uint64_t *PM, int qlen, int tlen, uint8_t *tmp
 }
 
 // Traceback of a sub-problem small enough for the reference's direct method (edlib.cpp:1204-1221, 958-1157).  The sweep
-// keeps the vertical delta vectors (Pv, Mv) of every column - 16 bytes per 64 cells, the reference's own 1 MB rule bounds
-// them by ED_PATH_LEAF_BYTES - and the walk rebuilds the three neighbour values from them: up and diagonal from one bit
-// each, left from a prefix population count whenever the column changes.  Returns the number of operations written to
+// keeps the vertical delta vectors (Pv, Mv) and the last-row value of every word of every column, and the walk rebuilds the
+// three neighbour values from them: up and diagonal from one bit each, left from one population count whenever the
+// column changes.  Returns the number of operations written to
 // out (in alignment order).
 DB200_HD int path_leaf(const uint64_t *peq, const uint8_t *tcodes, int W, int q0, int q1, int t0, int t1, const EdPathScratch &s, uint8_t *out)
 {
     const int qlen = q1 - q0, tlen = t1 - t0;
     const int Wq = (qlen + 63) >> 6;
-    uint64_t *PM = s.dir;                                           // [tlen][Wq][2]
-    for (int w = 0; w < Wq; ++w) { s.Pv[w] = ~0ull; s.Mv[w] = 0ull; }
+    uint64_t *PM = s.dir;                                           // [tlen][Wq][2], then the words' last rows [tlen][Wq]
+    int32_t *E = reinterpret_cast<int32_t *>(PM + (long)tlen * Wq * 2);
+    int32_t *end = s.left;                                          // running value of every word's last row (column -1: 64 w + 64)
+    for (int w = 0; w < Wq; ++w) { s.Pv[w] = ~0ull; s.Mv[w] = 0ull; end[w] = 64 * (w + 1); }
     for (int j = 0; j < tlen; ++j) {
         const uint64_t *row = peq + (long)tcodes[t0 + j] * W;
         uint64_t *pm = PM + (long)j * Wq * 2;
@@ -166,6 +171,8 @@ DB200_HD int path_leaf(const uint64_t *peq, const uint8_t *tcodes, int W, int q0
             const uint64_t npv = Mh | ~(Xv | Ph), nmv = Ph & Xv;
             s.Pv[w] = npv; s.Mv[w] = nmv;
             pm[2 * w] = npv; pm[2 * w + 1] = nmv;
+            end[w] += (int)op - (int)om;
+            E[(long)j * Wq + w] = end[w];
             hp = op; hm = om;
         }
     }
