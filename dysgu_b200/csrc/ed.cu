@@ -447,16 +447,22 @@ struct EdPathArgs {
 // global one of the query against target[start .. end] of the pair's first location; pairs without a result (distance
 // above k, an empty sequence: edlib.cpp:161-179 returns before the path step) report length 0.  All of the work is in
 // ed_path.cuh, which the CPU test suite runs against the reference's vectors.
+// SHORT: every query this kernel meets has fewer than ED_PATH_WARP_MIN_W words, so the vectors and score columns sit in
+// the thread's local memory (interleaved over the warp's lanes, unlike the per-thread regions of the scratch).
+template <bool SHORT>
 __global__ void __launch_bounds__(64) ed_path_kernel(EdPathArgs a)
 {
+    constexpr int SW = ED_PATH_WARP_MIN_W - 1;
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     uint8_t *base = a.scratch + tid * a.stride;
+    uint64_t lPv[SHORT ? SW : 1], lMv[SHORT ? SW : 1];
+    int32_t lleft[SHORT ? 64 * SW : 1], lright[SHORT ? 64 * SW : 1];
     EdPathScratch s;
     s.dir = reinterpret_cast<uint64_t *>(base);
-    s.Pv = reinterpret_cast<uint64_t *>(base + a.leaf_bytes);
-    s.Mv = reinterpret_cast<uint64_t *>(base + a.leaf_bytes + a.vec_bytes);
-    s.left = reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes);
-    s.right = reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + a.col_bytes);
+    s.Pv = SHORT ? lPv : reinterpret_cast<uint64_t *>(base + a.leaf_bytes);
+    s.Mv = SHORT ? lMv : reinterpret_cast<uint64_t *>(base + a.leaf_bytes + a.vec_bytes);
+    s.left = SHORT ? lleft : reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes);
+    s.right = SHORT ? lright : reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + a.col_bytes);
     s.tmp = base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + 2 * (int64_t)a.col_bytes;
     while (true) {
         const int64_t p = atomicAdd(a.counter, 1);
@@ -887,9 +893,11 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     if (want_path) {
         // Pairs of 8..256 query words go to the warp kernel, the rest to the thread kernel.  Scratch per worker: the
         // reference's 1 MB rule bounds the stored columns of a leaf, the rest follows the longest query it can meet.
-        const int64_t maxt = std::max(max_target_len, 1);
+        // the aligned slice of the infix / prefix modes is never longer than query + distance <= twice the query
+        const int64_t maxt = prm->mode == DB200_ED_MODE_NW ? std::max(max_target_len, 1)
+                                                           : std::max<int64_t>(1, std::min<int64_t>(max_target_len, 2 * (int64_t)max_query_len));
         const bool split = Wmax >= ED_PATH_WARP_MIN_W;
-        const int64_t budget = (int64_t)3 << 29;   // 1.5 GB of scratch per kernel at most
+        const int64_t budget = (int64_t)3 << 30;   // 3 GB of scratch per kernel at most
         auto layout = [&](EdPathArgs &xa, int64_t qcap) {
             const int64_t Wq = (qcap + 63) / 64;
             xa.leaf_bytes = (int32_t)std::min<int64_t>(ED_PATH_LEAF_BYTES, (20 * Wq * maxt + 15) & ~15ll);
@@ -903,19 +911,21 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
         xa.path_buf = d_path_buf; xa.path_len = d_path_len; xa.npairs = npairs; xa.split = split ? 1 : 0;
         {
             const int64_t qmax = std::max(max_query_len, 1);
-            layout(xa, (split && Wmax <= ED_PATH_WARP_MAX_W) ? std::min<int64_t>(qmax, 64 * (ED_PATH_WARP_MIN_W - 1)) : qmax);
+            const bool short_only = Wmax <= ED_PATH_WARP_MAX_W;   // longer queries than the warp kernel takes come back here
+            layout(xa, short_only ? std::min<int64_t>(qmax, 64 * (ED_PATH_WARP_MIN_W - 1)) : qmax);
             int64_t threads = std::min<int64_t>((npairs + 63) / 64 * 64, (int64_t)e->sm_count * 256);
             threads = std::max<int64_t>(64, std::min(threads, budget / xa.stride) / 64 * 64);
             xa.scratch = ws.alloc<uint8_t>((size_t)(threads * xa.stride));
             if (!xa.scratch) { set_error("ed_batch: device workspace allocation failed (path scratch)"); return DB200_ERR_NOMEM; }
             xa.counter = counters + (ci++);
-            ed_path_kernel<<<(unsigned)(threads / 64), 64, 0, st>>>(xa);
+            if (short_only) ed_path_kernel<true><<<(unsigned)(threads / 64), 64, 0, st>>>(xa);
+            else ed_path_kernel<false><<<(unsigned)(threads / 64), 64, 0, st>>>(xa);
             count_launch(e);
         }
         if (split) {
             layout(xa, std::min<int64_t>(std::max(max_query_len, 1), 64 * ED_PATH_WARP_MAX_W));
             int64_t warps = std::min<int64_t>((npairs + 3) / 4 * 4, (int64_t)e->sm_count * 16);
-            warps = std::max<int64_t>(4, std::min(warps, 2 * budget / xa.stride) / 4 * 4);   // up to 3 GB: a full leaf per warp
+            warps = std::max<int64_t>(4, std::min(warps, budget / xa.stride) / 4 * 4);
             xa.scratch = ws.alloc<uint8_t>((size_t)(warps * xa.stride));
             if (!xa.scratch) { set_error("ed_batch: device workspace allocation failed (path scratch)"); return DB200_ERR_NOMEM; }
             xa.counter = counters + (ci++);
