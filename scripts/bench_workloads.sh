@@ -2,7 +2,7 @@
 # every named shape through bench.py (one JSON line each) -> gpurun_out/bench_workloads.jsonl
 out=gpurun_out/bench_workloads.jsonl
 : > $out
-for w in ${WLS:-remap_windows pe_contigs long_contigs remap_chain hifi_nw ont_nw hifi_hw}; do
+for w in ${WLS:-remap_windows pe_contigs long_contigs remap_chain hifi_nw ont_nw hifi_hw remap_path hifi_path}; do
   timeout 600 python bench.py --workload $w --steps ${STEPS:-5} --warmup 3 >> $out 2> gpurun_out/bench_$w.err || echo "{\"workload\": \"$w\", \"failed\": true}" >> $out
 done
 python - <<'PY'
