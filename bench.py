@@ -297,7 +297,7 @@ def run_ours(args):
     d_voff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     d_status = torch.zeros(n, dtype=torch.int32, device=dev)
     d_path = torch.zeros(path_cap if want_path else 1, dtype=torch.uint8, device=dev)
-    d_plen = torch.zeros(n if want_path else 1, dtype=torch.int32, device=dev)
+    d_poff = torch.zeros(n + 1 if want_path else 1, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def device_step():
@@ -308,7 +308,7 @@ def run_ours(args):
         elif want_path:
             rc = L.db200_ed_path_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
                                               d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_var.data_ptr(), var_cap,
-                                              d_voff.data_ptr(), None, d_path.data_ptr(), path_cap, d_plen.data_ptr(),
+                                              d_voff.data_ptr(), None, d_path.data_ptr(), path_cap, d_poff.data_ptr(), None,
                                               C.c_void_p(stream.cuda_stream))
         else:
             rc = L.db200_ed_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
@@ -328,8 +328,8 @@ def run_ours(args):
     bad = int((d_status != 0).sum().item()) if kind == "sw" else int((d_res[:, 0] != 0).sum().item())
     if bad:
         raise SystemExit("bench.py: %d pairs reported a non-zero status" % bad)
-    if want_path and int((d_plen < 0).sum().item()):
-        raise SystemExit("bench.py: pairs without an alignment path")
+    if want_path and int(d_poff[-1].item()) <= 0:
+        raise SystemExit("bench.py: no alignment paths")
     checksum = int(d_res[:, 0 if kind == "sw" else 1].sum().item())
 
     L.db200_profile_enable(local_rank, 1)
@@ -374,7 +374,7 @@ def run_ours(args):
     hvoff = pinned_array(L, (n + 1,), np.int64)
     hstat = pinned_array(L, (n,), np.int32)
     hpath = pinned_array(L, (path_cap if want_path else 1,), np.uint8); hpath[:] = 0
-    hplen = pinned_array(L, (n if want_path else 1,), np.int32)
+    hpoff = pinned_array(L, (n + 1 if want_path else 1,), np.int64)
 
     def host_step():
         if kind == "sw":
@@ -383,7 +383,7 @@ def run_ours(args):
         elif want_path:
             rc = L.db200_ed_path_batch_host(local_rank, C.byref(prm_c), hq.ctypes.data, hqo.ctypes.data, ht.ctypes.data, hto.ctypes.data, n,
                                             None, hres.ctypes.data, hvar.ctypes.data, var_cap, hvoff.ctypes.data, hpath.ctypes.data,
-                                            path_cap, hplen.ctypes.data)
+                                            path_cap, hpoff.ctypes.data)
         else:
             rc = L.db200_ed_batch_host(local_rank, C.byref(prm_c), hq.ctypes.data, hqo.ctypes.data, ht.ctypes.data, hto.ctypes.data, n,
                                        None, hres.ctypes.data, hvar.ctypes.data, var_cap, hvoff.ctypes.data)
@@ -406,7 +406,7 @@ def run_ours(args):
         raise SystemExit("bench.py: host and device arms disagree")
     nvar = int(hvoff[n])
     h2d = q_bytes + t_bytes + 2 * 8 * (n + 1)
-    d2h = 4 * res_cols * n + 8 * (n + 1) + (4 * n + 4 * nvar if kind == "sw" else 8 * nvar) + (q_bytes + t_bytes + 4 * n if want_path else 0)
+    d2h = 4 * res_cols * n + 8 * (n + 1) + (4 * n + 4 * nvar if kind == "sw" else 8 * nvar) + (int(hpoff[n]) + 8 * (n + 1) if want_path else 0)
 
     if rank != 0:
         if dist is not None:
@@ -471,10 +471,11 @@ def run_ours(args):
             ncmp = 7 if kind == "sw" else 4
             mism = int((r.fixed[:, :ncmp] != hres[:sample, :ncmp]).any(axis=1).sum())
             cpu_baseline["parity_mismatches_on_sample"] = mism
-            if want_path:   # the reference's alignment arrays against ours, operation by operation (same slot per pair)
+            if want_path:   # the reference's alignment arrays (one slot per pair) against ours (back to back), operation by operation
                 ln = r.path_len.astype(np.int64)
                 idx = np.repeat(np.asarray(r.path_off, dtype=np.int64) - (np.cumsum(ln) - ln), ln) + np.arange(int(ln.sum()), dtype=np.int64)
-                cpu_baseline["path_mismatches_on_sample"] = int((r.path_len != hplen[:sample]).sum()) + int((r.path[idx] != hpath[idx]).sum())
+                same_len = bool(np.array_equal(np.diff(hpoff[:sample + 1]), ln))
+                cpu_baseline["path_mismatches_on_sample"] = int((r.path[idx] != hpath[:int(ln.sum())]).sum()) if same_len else int((np.diff(hpoff[:sample + 1]) != ln).sum())
                 cpu_baseline["path_operations_on_sample"] = int(ln.sum())
         except Exception as exc:
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % str(exc)[:100]}

@@ -72,7 +72,7 @@ def lib():
         L.db200_ed_path_batch_device.argtypes = [C.c_int, C.POINTER(EdParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                                  C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                                 C.c_void_p]
+                                                 C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

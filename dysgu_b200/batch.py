@@ -129,13 +129,16 @@ def sw_align_batch(queries, targets, match=2, mismatch=-3, gap_open=5, gap_exten
 class EdResults:
     """Results of an edit-distance batch (fields follow EdlibAlignResult, edlib.h:162-218)."""
 
-    def __init__(self, fixed, loc, loc_off, path=None, path_off=None, path_len=None):
+    def __init__(self, fixed, loc, loc_off, path=None, path_off=None):
         self.fixed = fixed      # int32 [n,4]: status, editDistance, alphabetLength, numLocations
         self.loc = loc          # int32 [total,2]: (start, end); start == ED_NO_START -> None
         self.loc_off = loc_off
         self.path = path        # task "path": uint8 edit operations (0 match, 1 insertion, 2 deletion, 3 mismatch)
-        self.path_off = path_off
-        self.path_len = path_len
+        self.path_off = path_off  # int64 [n+1]
+
+    @property
+    def path_len(self):
+        return None if self.path_off is None else np.diff(self.path_off)
 
     def __len__(self):
         return self.fixed.shape[0]
@@ -146,9 +149,9 @@ class EdResults:
 
     def alignment(self, i):
         """Edit operations of pair i (EdlibAlignResult.alignment), None where the reference returns none."""
-        if self.path is None or self.path_len[i] <= 0:
+        if self.path is None or self.path_off[i + 1] <= self.path_off[i]:
             return None
-        return self.path[self.path_off[i]:self.path_off[i] + self.path_len[i]]
+        return self.path[self.path_off[i]:self.path_off[i + 1]]
 
     def cigar(self, i, extended=True):
         """edlibAlignmentToCigar of pair i (edlib.cpp:298-347; the wrapper uses the extended format, edlib.pyx:143-147)."""
@@ -208,12 +211,12 @@ def ed_align_batch(queries, targets, mode="NW", task="distance", k=-1, additiona
     if prm.task == ED_TASKS["path"]:
         pcap = int(q.off[-1] + t.off[-1]) + 1
         path = np.zeros(pcap, dtype=np.uint8)
-        plen = np.zeros(max(n, 1), dtype=np.int32)
+        poff = np.zeros(n + 1, dtype=np.int64)
         rc = L.db200_ed_path_batch_host(default_device() if device is None else device, C.byref(prm), _ptr(qbuf), _ptr(q.off),
                                         _ptr(tbuf), _ptr(t.off), n, _ptr(karr), _ptr(fixed), _ptr(loc), cap, _ptr(loff), _ptr(path),
-                                        pcap, _ptr(plen))
+                                        pcap, _ptr(poff))
         _lib.check(rc, "db200_ed_path_batch_host")
-        return EdResults(fixed, loc[:loff[n]], loff, path, (q.off + t.off)[:n], plen[:n])
+        return EdResults(fixed, loc[:loff[n]], loff, path[:poff[n]], poff)
     rc = L.db200_ed_batch_host(default_device() if device is None else device, C.byref(prm), _ptr(qbuf), _ptr(q.off), _ptr(tbuf),
                                _ptr(t.off), n, _ptr(karr), _ptr(fixed), _ptr(loc), cap, _ptr(loff))
     _lib.check(rc, "db200_ed_batch_host")

@@ -433,8 +433,9 @@ struct EdPathArgs {
     const db200_ed_result *results;
     const int64_t *loc_off;
     const int32_t *loc_buf;
-    uint8_t *path_buf;          // pair p writes at path_buf[q_off + t_off ..), at most m + n operations
+    uint8_t *path_buf;          // slots: pair p writes at path_buf[q_off + t_off ..), at most m + n operations
     int32_t *path_len;
+    int32_t *failed;            // set when a pair found no split consistent with its distance (an internal error)
     int64_t npairs;
     uint8_t *scratch;           // one region of `stride` bytes per thread: leaf columns | Pv | Mv | left | right | tmp
     int64_t stride;
@@ -477,15 +478,16 @@ __global__ void __launch_bounds__(64) ed_path_kernel(EdPathArgs a)
             len = ed_path_pair(a.peq + pr.peq_off, a.tcodes + pr.t_off, pr.W, pr.m, start, end + 1, r.edit_distance, s,
                                a.path_buf + pr.q_off + pr.t_off);
         }
-        a.path_len[p] = len;   // -1: no split consistent with the distance was found (an internal error, reported by the host)
+        if (len < 0) { *a.failed = 1; len = 0; }
+        a.path_len[p] = len;
     }
 }
 
 // ---- long pairs: one warp per pair ---------------------------------------------------------------------------------------
 // The same steps as ed_path_pair, with the two sweeps - score columns of the halving step, stored columns of a leaf - run
 // as a wavefront over the lanes: lane l owns WL consecutive 64-row words in registers and works on column s - l at step s,
-// the horizontal delta of a lane boundary travels with __shfl_up_sync.  The walk back over a leaf is the scalar
-// path_leaf_walk on lane 0.
+// the horizontal delta of a lane boundary travels with __shfl_up_sync.  The walk back over a leaf fetches the stored
+// columns 32 at a time (path_leaf_walk_warp).
 
 template <int WL, bool STORE, bool REV>
 __device__ __noinline__ void path_warp_sweep(const uint64_t *peq, const uint8_t *tcodes, int W, int q0, int q1, int tfirst, int ncol,
@@ -592,6 +594,73 @@ __device__ __forceinline__ void path_warp_sweep_any(const uint64_t *peq, const u
     else path_warp_sweep<8, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out);
 }
 
+// path_leaf_walk for a whole warp.  The scalar walk waits for three dependent loads per step; here lane l holds the stored
+// (Pv, Mv, last-row value) of column jb - l at the current row's word, fetched 32 columns at a time, every lane follows the
+// same walk and a step reads its two columns with shuffles.  Column -1 is a lane's constant (all deltas +1, D[r][-1] = r + 1).
+__device__ int path_leaf_walk_warp(const uint64_t *PM, int qlen, int tlen, uint8_t *tmp, uint8_t *out)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int Wq = (qlen + 63) >> 6;
+    const int32_t *E = reinterpret_cast<const int32_t *>(PM + (long)tlen * Wq * 2);
+    auto below = [](int i) { return (i & 63) == 63 ? 0ull : (~0ull << ((i & 63) + 1)); };
+    int i = qlen - 1, j = tlen - 1, n = 0;
+    int cur = 0, left = 0;
+    bool first = true;
+    while (i >= 0 && j >= 0) {
+        const int wi = i >> 6, jb = j;
+        const int col = jb - lane;
+        uint64_t cP = ~0ull, cM = 0ull;
+        int cE = 64 * wi + 64;
+        if (col >= 0) {
+            const long k = (long)col * Wq + wi;
+            const ulonglong2 pm = *reinterpret_cast<const ulonglong2 *>(PM + 2 * k);
+            cP = pm.x; cM = pm.y; cE = E[k];
+        }
+        {   // D[i][j-1] from lane 1 (and D[i][j] from lane 0 at the very start)
+            const uint64_t b = below(i);
+            const int mine = cE - __popcll(cP & b) + __popcll(cM & b);
+            if (first) { cur = __shfl_sync(FULL, mine, 0); first = false; }
+            left = __shfl_sync(FULL, mine, 1);
+        }
+        while (i >= 0 && j >= 0 && (i >> 6) == wi && jb - j <= 30) {
+            const int src = jb - j, sh = i & 63;
+            const uint64_t pc0 = __shfl_sync(FULL, cP, src), pc1 = __shfl_sync(FULL, cM, src);
+            const uint64_t pl0 = __shfl_sync(FULL, cP, src + 1), pl1 = __shfl_sync(FULL, cM, src + 1);
+            const int vc = (int)((pc0 >> sh) & 1ull) - (int)((pc1 >> sh) & 1ull);
+            const int vl = (int)((pl0 >> sh) & 1ull) - (int)((pl1 >> sh) & 1ull);
+            const int up = cur - vc, diag = left - vl;
+            const int op = (up + 1 == cur) ? 1 : ((left + 1 == cur) ? 2 : (diag == cur ? 0 : 3));
+            if (lane == 0) tmp[n] = (uint8_t)op;
+            ++n;
+            if (op == 1) { --i; cur = up; left = diag; }
+            else {
+                cur = (op == 2) ? left : diag;
+                if (op != 2) --i;
+                --j;
+                // the new left neighbour D[i][j-1] while its column is still held; otherwise the next fetch recomputes it
+                if (i >= 0 && j >= 0 && (i >> 6) == wi && jb - j <= 30) {
+                    const int s2 = jb - j + 1;
+                    const uint64_t lP = __shfl_sync(FULL, cP, s2), lM = __shfl_sync(FULL, cM, s2);
+                    const int lE = __shfl_sync(FULL, cE, s2);
+                    const uint64_t b = below(i);
+                    left = lE - __popcll(lP & b) + __popcll(lM & b);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // the rest of the first row (deletions), then of the first column (insertions); then alignment order
+    const int nd = j + 1, ni = i + 1;
+    for (int k = lane; k < nd; k += 32) tmp[n + k] = 2;
+    for (int k = lane; k < ni; k += 32) tmp[n + nd + k] = 1;
+    n += nd + ni;
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) out[k] = tmp[n - 1 - k];
+    __syncwarp();
+    return n;
+}
+
 // ed_path_pair for a whole warp (every lane follows the same control flow; m <= 64 * ED_PATH_WARP_MAX_W)
 __device__ int ed_path_pair_warp(const uint64_t *peq, const uint8_t *tcodes, int W, int m, int t0, int t1, int best, const EdPathScratch &s,
                                  uint8_t *out)
@@ -616,9 +685,7 @@ __device__ int ed_path_pair_warp(const uint64_t *peq, const uint8_t *tcodes, int
         const long long state = (2ll * 8 + 4) * blocks * tlen + 2ll * 4 * tlen;   // the reference's 1 MB rule (edlib.cpp:1204-1206)
         if (state < 1024 * 1024) {
             path_warp_sweep_any<true, false>(peq, tcodes, W, q0, q1, a0, tlen, s.dir, nullptr);
-            int k = 0;
-            if (lane == 0) k = path_leaf_walk(s.dir, qlen, tlen, s.tmp, out + n);
-            n += __shfl_sync(FULL, k, 0);
+            n += path_leaf_walk_warp(s.dir, qlen, tlen, s.tmp, out + n);
             continue;
         }
         const int lw = tlen / 2, rw = tlen - lw;
@@ -672,8 +739,35 @@ __global__ void __launch_bounds__(128) ed_path_warp_kernel(EdPathArgs a)
             len = ed_path_pair_warp(a.peq + pr.peq_off, a.tcodes + pr.t_off, pr.W, pr.m, start, end + 1, r.edit_distance, s,
                                     a.path_buf + pr.q_off + pr.t_off);
         }
-        if (lane == 0) a.path_len[p] = len;
+        if (lane == 0) {
+            if (len < 0) { *a.failed = 1; len = 0; }
+            a.path_len[p] = len;
+        }
     }
+}
+
+// warp per pair: the operations move from their slot to the pair's place in the caller's buffer (CSR, like the locations)
+struct EdPathPackArgs {
+    const EdPair *pairs;
+    const uint8_t *slots;
+    const int32_t *path_len;
+    const int64_t *path_off;
+    uint8_t *out;
+    int64_t cap, npairs;
+    int32_t *overflow;
+};
+
+__global__ void ed_path_pack_kernel(EdPathPackArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (p >= a.npairs) return;
+    const int len = a.path_len[p];
+    if (len <= 0) return;
+    const int64_t dst = a.path_off[p];
+    if (dst + len > a.cap) { if (lane == 0) *a.overflow = 1; return; }
+    const uint8_t *src = a.slots + a.pairs[p].q_off + a.pairs[p].t_off;
+    for (int k = lane; k < len; k += 32) a.out[dst + k] = src[k];
 }
 
 template <bool REV>
@@ -715,18 +809,16 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_k, db200_ed_result *d_results,
                          int32_t *d_loc_buf, int64_t loc_cap, int64_t *d_loc_off, int64_t *loc_total, cudaStream_t st,
-                         uint8_t *d_path_buf, int64_t path_cap, int32_t *d_path_len)
+                         uint8_t *d_path_buf, int64_t path_cap, int64_t *d_path_off, int64_t *path_total)
 {
     if (npairs < 0 || !prm || !d_results) { set_error("ed_batch: bad arguments"); return DB200_ERR_ARG; }
     const bool want_path = prm->task == DB200_ED_TASK_PATH;
-    if (want_path && (!d_path_buf || !d_path_len)) {
+    if (want_path && (!d_path_buf || !d_path_off)) {
         set_error("ed_batch: task 'path' needs the path buffers of db200_ed_path_batch_host / db200_ed_path_batch_device");
         return DB200_ERR_ARG;
     }
-    if (want_path && path_cap < q_bytes + t_bytes) {
-        set_error("ed_batch: path buffer too small (%lld bytes needed)", (long long)(q_bytes + t_bytes));
-        return DB200_ERR_CAPACITY;
-    }
+    if (want_path && npairs == 0) DB200_CUDA_CHECK(cudaMemsetAsync(d_path_off, 0, sizeof(int64_t), st));
+    if (want_path && npairs == 0 && path_total) *path_total = 0;
     if (prm->task < 0 || prm->task > 2) { set_error("ed_batch: bad task"); return DB200_ERR_ARG; }
     if (npairs == 0) {
         if (d_loc_off) DB200_CUDA_CHECK(cudaMemsetAsync(d_loc_off, 0, sizeof(int64_t), st));
@@ -908,7 +1000,10 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
         EdPathArgs xa;
         memset(&xa, 0, sizeof(xa));
         xa.pairs = pairs; xa.peq = peq; xa.tcodes = tcodes; xa.results = d_results; xa.loc_off = d_loc_off; xa.loc_buf = d_loc_buf;
-        xa.path_buf = d_path_buf; xa.path_len = d_path_len; xa.npairs = npairs; xa.split = split ? 1 : 0;
+        uint8_t *slots = ws.alloc<uint8_t>((size_t)(q_bytes + t_bytes + 16));
+        int32_t *plen = ws.alloc<int32_t>((size_t)npairs);
+        if (!slots || !plen) { set_error("ed_batch: device workspace allocation failed (path slots)"); return DB200_ERR_NOMEM; }
+        xa.path_buf = slots; xa.path_len = plen; xa.failed = overflow + 1; xa.npairs = npairs; xa.split = split ? 1 : 0;
         {
             const int64_t qmax = std::max(max_query_len, 1);
             const bool short_only = Wmax <= ED_PATH_WARP_MAX_W;   // longer queries than the warp kernel takes come back here
@@ -932,15 +1027,27 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
             ed_path_warp_kernel<<<(unsigned)(warps / 4), 128, 0, st>>>(xa);
             count_launch(e);
         }
+        exclusive_scan_i32_i64(e, plen, d_path_off, npairs, scan_tmp, st);
+        EdPathPackArgs ka;
+        ka.pairs = pairs; ka.slots = slots; ka.path_len = plen; ka.path_off = d_path_off; ka.out = d_path_buf; ka.cap = path_cap;
+        ka.npairs = npairs; ka.overflow = overflow + 2;
+        ed_path_pack_kernel<<<gwarp, TB, 0, st>>>(ka);
+        count_launch(e);
         prof_mark(e, st, ST_ED_PATH);
     }
     DB200_CUDA_CHECK(cudaGetLastError());
-    if (loc_total) {
-        int32_t ovf = 0;
-        DB200_CUDA_CHECK(cudaMemcpyAsync(loc_total, d_loc_off + npairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        DB200_CUDA_CHECK(cudaMemcpyAsync(&ovf, overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (loc_total || (want_path && path_total)) {
+        int32_t ovf[3] = {0, 0, 0};
+        int64_t ltot = 0, ptot = 0;
+        DB200_CUDA_CHECK(cudaMemcpyAsync(&ltot, d_loc_off + npairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        if (want_path) DB200_CUDA_CHECK(cudaMemcpyAsync(&ptot, d_path_off + npairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(ovf, overflow, sizeof(ovf), cudaMemcpyDeviceToHost, st));
         DB200_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (ovf) { set_error("ed_batch: location buffer too small (%lld needed)", (long long)*loc_total); return DB200_ERR_CAPACITY; }
+        if (loc_total) *loc_total = ltot;
+        if (want_path && path_total) *path_total = ptot;
+        if (ovf[0]) { set_error("ed_batch: location buffer too small (%lld needed)", (long long)ltot); return DB200_ERR_CAPACITY; }
+        if (ovf[1]) { set_error("ed_batch: no alignment path consistent with the distance of a pair (internal error)"); return DB200_ERR_INTERNAL; }
+        if (ovf[2]) { set_error("ed_batch: path buffer too small (%lld bytes needed)", (long long)ptot); return DB200_ERR_CAPACITY; }
     }
     return DB200_OK;
 }

@@ -707,8 +707,8 @@ int db200_ed_batch_device(int device, const db200_ed_params *params, const uint8
 int db200_ed_path_batch_device(int device, const db200_ed_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
                                const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs, int32_t max_query_len,
                                int32_t max_target_len, const int32_t *d_k, db200_ed_result *d_results, int32_t *d_loc_buf, int64_t loc_cap,
-                               int64_t *d_loc_off, int64_t *loc_total, uint8_t *d_path_buf, int64_t path_cap, int32_t *d_path_len,
-                               void *stream)
+                               int64_t *d_loc_off, int64_t *loc_total, uint8_t *d_path_buf, int64_t path_cap, int64_t *d_path_off,
+                               int64_t *path_total, void *stream)
 {
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
@@ -717,27 +717,24 @@ int db200_ed_path_batch_device(int device, const db200_ed_params *params, const 
     e->aux_set = 0;
     return ed_batch_device_impl(e, e->arena[0], params, d_qbuf, d_qoff, q_bytes, d_tbuf, d_toff, t_bytes, npairs, max_query_len,
                                 max_target_len, d_k, d_results, d_loc_buf, loc_cap, d_loc_off, loc_total, (cudaStream_t)stream,
-                                d_path_buf, path_cap, d_path_len);
+                                d_path_buf, path_cap, d_path_off, path_total);
 }
 
 }  // extern "C"
 
 static int ed_batch_host_impl(int device, const db200_ed_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
                               const int64_t *toff, int64_t npairs, const int32_t *k, db200_ed_result *results, int32_t *loc_buf,
-                              int64_t loc_cap, int64_t *loc_off, uint8_t *path_buf, int64_t path_cap, int32_t *path_len)
+                              int64_t loc_cap, int64_t *loc_off, uint8_t *path_buf, int64_t path_cap, int64_t *path_off)
 {
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
     if (npairs < 0 || !params || !qoff || !toff || !results || !loc_buf || !loc_off) { set_error("ed_batch_host: bad arguments"); return DB200_ERR_ARG; }
     const bool want_path = params->task == DB200_ED_TASK_PATH;
-    if (want_path && (!path_buf || !path_len)) {
+    if (want_path && (!path_buf || !path_off)) {
         set_error("ed_batch_host: task 'path' needs the path buffers of db200_ed_path_batch_host");
         return DB200_ERR_ARG;
     }
-    if (want_path && path_cap < qoff[npairs] - qoff[0] + toff[npairs] - toff[0]) {
-        set_error("ed_path_batch_host: path buffer too small (%lld bytes needed)", (long long)(qoff[npairs] - qoff[0] + toff[npairs] - toff[0]));
-        return DB200_ERR_CAPACITY;
-    }
+    if (want_path) path_off[0] = 0;
     loc_off[0] = 0;
     // Chunks flow through two slots: while chunk i is aligned on its slot's stream, chunk i+1 is copied to the device on the
     // copy stream (the match-vector pool size is read back inside each chunk, so the host thread follows the compute closely;
@@ -767,7 +764,7 @@ static int ed_batch_host_impl(int device, const db200_ed_params *params, const u
         c0 = c1;
     }
     struct Staged { uint8_t *d_q, *d_t; int64_t *d_off; int32_t *d_k; db200_ed_result *d_res; int64_t *d_loff; int32_t *d_loc; int64_t cap;
-                    uint8_t *d_path; int32_t *d_plen; };
+                    uint8_t *d_path; int64_t *d_poff; };
     Staged staged[2] = {};
     cudaStream_t cst = e->copy_stream;
     auto stage = [&](size_t ci) -> int {
@@ -796,8 +793,8 @@ static int ed_batch_host_impl(int device, const db200_ed_params *params, const u
         s.d_loff = io.alloc<int64_t>((size_t)n + 1);
         s.d_loc = io.alloc<int32_t>((size_t)(2 * s.cap + 16));
         s.d_path = want_path ? io.alloc<uint8_t>((size_t)(c.qb + c.tb + 16)) : nullptr;
-        s.d_plen = want_path ? io.alloc<int32_t>((size_t)n) : nullptr;
-        if (!s.d_q || !s.d_t || !s.d_off || (k && !s.d_k) || !s.d_res || !s.d_loff || !s.d_loc || (want_path && (!s.d_path || !s.d_plen))) {
+        s.d_poff = want_path ? io.alloc<int64_t>((size_t)n + 1) : nullptr;
+        if (!s.d_q || !s.d_t || !s.d_off || (k && !s.d_k) || !s.d_res || !s.d_loff || !s.d_loc || (want_path && (!s.d_path || !s.d_poff))) {
             set_error("ed_batch_host: device allocation failed");
             return DB200_ERR_NOMEM;
         }
@@ -808,7 +805,7 @@ static int ed_batch_host_impl(int device, const db200_ed_params *params, const u
         DB200_CUDA_CHECK(cudaEventRecord(e->ev_copy[slot], cst));
         return DB200_OK;
     };
-    int64_t written = 0;
+    int64_t written = 0, pwritten = 0;
     if (!chunks.empty()) { const int rc = stage(0); if (rc) return rc; }
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const Chunk &c = chunks[ci];
@@ -821,28 +818,27 @@ static int ed_batch_host_impl(int device, const db200_ed_params *params, const u
         DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_copy[slot], 0));
         e->arena[slot].reset();
         e->aux_set = slot;
-        int64_t total = 0;
+        int64_t total = 0, ptotal = 0;
         int rc = ed_batch_device_impl(e, e->arena[slot], params, s.d_q, s.d_off, c.qb, s.d_t, s.d_off + n + 1, c.tb, n, c.maxq, c.maxt, s.d_k,
-                                      s.d_res, s.d_loc, s.cap, s.d_loff, &total, st, s.d_path, c.qb + c.tb, s.d_plen);
+                                      s.d_res, s.d_loc, s.cap, s.d_loff, &total, st, s.d_path, c.qb + c.tb, s.d_poff, &ptotal);
         if (rc) return rc;
+        if (want_path && pwritten + ptotal > path_cap) { set_error("ed_path_batch_host: path buffer too small (%lld bytes needed so far)", (long long)(pwritten + ptotal)); return DB200_ERR_CAPACITY; }
         if (written + total > loc_cap) { set_error("ed_batch_host: location buffer too small (%lld needed)", (long long)(written + total)); return DB200_ERR_CAPACITY; }
         DB200_CUDA_CHECK(cudaMemcpyAsync(results + c.c0, s.d_res, sizeof(db200_ed_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
         DB200_CUDA_CHECK(cudaMemcpyAsync(loc_off + c.c0, s.d_loff, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
         if (total > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(loc_buf + 2 * written, s.d_loc, sizeof(int32_t) * 2 * (size_t)total, cudaMemcpyDeviceToHost, st));
         if (want_path) {
-            // slot of pair i = qoff[i] + toff[i] relative to the first pair, on the device (per chunk) as on the host
-            if (c.qb + c.tb > 0)
-                DB200_CUDA_CHECK(cudaMemcpyAsync(path_buf + (qoff[c.c0] - qoff[0]) + (toff[c.c0] - toff[0]), s.d_path, (size_t)(c.qb + c.tb), cudaMemcpyDeviceToHost, st));
-            DB200_CUDA_CHECK(cudaMemcpyAsync(path_len + c.c0, s.d_plen, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            DB200_CUDA_CHECK(cudaMemcpyAsync(path_off + c.c0, s.d_poff, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+            if (ptotal > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(path_buf + pwritten, s.d_path, (size_t)ptotal, cudaMemcpyDeviceToHost, st));
         }
         DB200_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (want_path)
-            for (int64_t i = c.c0; i < c.c1; ++i)
-                if (path_len[i] < 0) { set_error("ed_path_batch_host: no alignment path found for pair %lld", (long long)i); return DB200_ERR_INTERNAL; }
+        if (want_path && pwritten) for (int64_t i = 0; i <= n; ++i) path_off[c.c0 + i] += pwritten;
+        pwritten += ptotal;
         if (written) for (int64_t i = 0; i <= n; ++i) loc_off[c.c0 + i] += written;
         written += total;
     }
     loc_off[npairs] = written;
+    if (want_path) path_off[npairs] = pwritten;
     return DB200_OK;
 }
 
@@ -858,10 +854,10 @@ int db200_ed_batch_host(int device, const db200_ed_params *params, const uint8_t
 
 int db200_ed_path_batch_host(int device, const db200_ed_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
                              const int64_t *toff, int64_t npairs, const int32_t *k, db200_ed_result *results, int32_t *loc_buf,
-                             int64_t loc_cap, int64_t *loc_off, uint8_t *path_buf, int64_t path_cap, int32_t *path_len)
+                             int64_t loc_cap, int64_t *loc_off, uint8_t *path_buf, int64_t path_cap, int64_t *path_off)
 {
     if (!params || params->task != DB200_ED_TASK_PATH) { set_error("ed_path_batch_host: params->task must be DB200_ED_TASK_PATH"); return DB200_ERR_ARG; }
-    return ed_batch_host_impl(device, params, qbuf, qoff, tbuf, toff, npairs, k, results, loc_buf, loc_cap, loc_off, path_buf, path_cap, path_len);
+    return ed_batch_host_impl(device, params, qbuf, qoff, tbuf, toff, npairs, k, results, loc_buf, loc_cap, loc_off, path_buf, path_cap, path_off);
 }
 
 // ---- legacy single-pair edlib entry points (edlib.h:146-271) ------------------------------------------------
@@ -920,10 +916,11 @@ db200_EdlibAlignResult db200_edlibAlign(const char *query, int queryLength, cons
     const uint8_t dummy = 0;
     const bool want_path = config.task == DB200_ED_TASK_PATH;
     std::vector<uint8_t> path(want_path ? (size_t)queryLength + (size_t)targetLength + 1 : 0);
-    int32_t path_len = 0;
+    int64_t poff[2] = {0, 0};
     int rc = ed_batch_host_impl(0, &prm, queryLength ? (const uint8_t *)query : &dummy, qoff, targetLength ? (const uint8_t *)target : &dummy,
                                 toff, 1, nullptr, &res, loc.data(), targetLength + 4, loff, want_path ? path.data() : nullptr,
-                                (int64_t)path.size(), want_path ? &path_len : nullptr);
+                                (int64_t)path.size(), want_path ? poff : nullptr);
+    const int32_t path_len = (int32_t)(poff[1] - poff[0]);
     if (rc != DB200_OK) return r;
     r.status = res.status;
     r.editDistance = res.edit_distance;

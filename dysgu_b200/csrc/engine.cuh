@@ -113,6 +113,6 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *params, co
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_k, db200_ed_result *d_results, int32_t *d_loc_buf, int64_t loc_cap,
                          int64_t *d_loc_off, int64_t *loc_total, cudaStream_t st,
-                         uint8_t *d_path_buf = nullptr, int64_t path_cap = 0, int32_t *d_path_len = nullptr);
+                         uint8_t *d_path_buf = nullptr, int64_t path_cap = 0, int64_t *d_path_off = nullptr, int64_t *path_total = nullptr);
 
 }  // namespace db200

@@ -220,11 +220,16 @@ int db200_queue_flush(db200_queue *q)
             if (want_path) {
                 const int64_t pcap = (int64_t)(g->qbuf.n + g->tbuf.n);
                 q->ed_path.resize(pbase + (size_t)pcap + 1);
+                std::vector<int64_t> poff((size_t)n + 1);
                 rc = db200_ed_path_batch_host(q->device, &p, g->qbuf.p, g->qoff.p, g->tbuf.p, g->toff.p, n, g->aux.p, q->ed_res.data() + base,
-                                              q->ed_loc.data() + lbase, cap, loff.data(), q->ed_path.data() + pbase, pcap + 1,
-                                              q->ed_path_len.data() + base);
-                if (rc == DB200_OK)
-                    for (int64_t i = 0; i < n; ++i) q->ed_path_off[base + (size_t)i] = (int64_t)pbase + g->qoff.p[i] + g->toff.p[i];
+                                              q->ed_loc.data() + lbase, cap, loff.data(), q->ed_path.data() + pbase, pcap + 1, poff.data());
+                if (rc == DB200_OK) {
+                    for (int64_t i = 0; i < n; ++i) {
+                        q->ed_path_off[base + (size_t)i] = (int64_t)pbase + poff[(size_t)i];
+                        q->ed_path_len[base + (size_t)i] = (int32_t)(poff[(size_t)i + 1] - poff[(size_t)i]);
+                    }
+                    q->ed_path.resize(pbase + (size_t)poff[(size_t)n]);
+                }
             } else {
                 rc = db200_ed_batch_host(q->device, &p, g->qbuf.p, g->qoff.p, g->tbuf.p, g->toff.p, n, g->aux.p, q->ed_res.data() + base,
                                          q->ed_loc.data() + lbase, cap, loff.data());

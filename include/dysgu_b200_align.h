@@ -206,10 +206,11 @@ int db200_ed_batch_device(int device, const db200_ed_params *params,
  * Hirschberg): everything db200_ed_batch_* reports for task "locations", plus the edit operations (EDLIB_EDOP_*:
  * 0 match, 1 insertion, 2 deletion, 3 mismatch) of the global alignment of the query to
  * target[start .. end] of the pair's FIRST location - the alignment the reference reports, not just one of its cost.
- * params->task must be DB200_ED_TASK_PATH.  The operations of pair i start at path_buf[(qoff[i] - qoff[0]) +
- * (toff[i] - toff[0])] and there are path_len[i] of them (at most len(query) + len(target), so path_cap =
- * total query bytes + total target bytes always suffices and less is refused with DB200_ERR_CAPACITY);
- * path_len[i] == 0 where the reference returns no alignment (distance above k, an empty sequence: edlib.cpp:161-179).
+ * params->task must be DB200_ED_TASK_PATH.  The operations are written back to back into path_buf in pair order;
+ * path_off[i]..path_off[i+1] delimits pair i (CSR like the locations; path_off has npairs + 1 entries).  A pair has at
+ * most len(query) + len(target) operations, so path_cap = total query bytes + total target bytes always suffices; a
+ * smaller buffer that overflows is reported with DB200_ERR_CAPACITY.  A pair has no operations where the reference
+ * returns no alignment (distance above k, an empty sequence: edlib.cpp:161-179).
  * db200_edlibAlignmentToCigar formats one pair's operations as the cigar string of edlib.pyx:143-147.
  */
 int db200_ed_path_batch_host(int device, const db200_ed_params *params,
@@ -217,16 +218,17 @@ int db200_ed_path_batch_host(int device, const db200_ed_params *params,
                              const uint8_t *tbuf, const int64_t *toff, int64_t npairs,
                              const int32_t *k,
                              db200_ed_result *results, int32_t *loc_buf, int64_t loc_cap, int64_t *loc_off,
-                             uint8_t *path_buf, int64_t path_cap, int32_t *path_len);
+                             uint8_t *path_buf, int64_t path_cap, int64_t *path_off);
 
-/* Device-resident variant; d_path_len[i] < 0 flags an internal error for pair i (never seen; the host variant checks it). */
+/* Device-resident variant; synchronises only when loc_total or path_total is non-NULL (they receive the totals, and
+ * capacity / internal errors are only reported then). */
 int db200_ed_path_batch_device(int device, const db200_ed_params *params,
                                const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
                                const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
                                int32_t max_query_len, int32_t max_target_len, const int32_t *d_k,
                                db200_ed_result *d_results, int32_t *d_loc_buf, int64_t loc_cap,
                                int64_t *d_loc_off, int64_t *loc_total,
-                               uint8_t *d_path_buf, int64_t path_cap, int32_t *d_path_len, void *stream);
+                               uint8_t *d_path_buf, int64_t path_cap, int64_t *d_path_off, int64_t *path_total, void *stream);
 
 /* Legacy single-pair entry point with edlib's signature (edlib.h:146-271); task EDLIB_TASK_PATH fills
  * alignment / alignmentLength like the reference. */

@@ -119,3 +119,24 @@ def test_path_properties_on_a_large_batch():
         assert int((ops != 2).sum()) == len(q) and int((ops != 1).sum()) == len(sl)
         eq, ne = ops == 0, ops == 3
         assert np.array_equal(q[qi[eq]], sl[ti[eq]]) and not np.any(q[qi[ne]] == sl[ti[ne]])
+
+
+def test_small_path_buffer_is_refused():
+    """Operations are packed back to back (CSR); a caller buffer they do not fit is an error, never a truncated path."""
+    L = _lib.lib()
+    q = np.frombuffer(b"ACGTACGTAC" * 2, np.uint8).copy()
+    t = np.frombuffer(b"ACGTTCGTAC" * 2, np.uint8).copy()
+    off = np.array([0, 10, 20], np.int64)
+    prm = _lib.EdParams()
+    prm.mode, prm.task, prm.k = batch.ED_MODES["NW"], batch.ED_TASKS["path"], -1
+    fixed = np.zeros((2, 4), np.int32); loc = np.zeros((16, 2), np.int32); loff = np.zeros(3, np.int64)
+    poff = np.zeros(3, np.int64)
+    for cap, ok in ((20, True), (19, False)):
+        path = np.zeros(64, np.uint8)
+        rc = L.db200_ed_path_batch_host(0, C.byref(prm), q.ctypes.data, off.ctypes.data, t.ctypes.data, off.ctypes.data, 2, None,
+                                        fixed.ctypes.data, loc.ctypes.data, 16, loff.ctypes.data, path.ctypes.data, cap, poff.ctypes.data)
+        assert (rc == 0) == ok
+        if ok:
+            assert list(poff) == [0, 10, 20] and batch.ops_to_cigar(path[:10]) == "4=1X5="
+        else:
+            assert rc == -4 and b"too small" in L.db200_last_error()
