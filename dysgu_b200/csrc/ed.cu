@@ -587,11 +587,17 @@ template <bool STORE, bool REV>
 __device__ __forceinline__ void path_warp_sweep_any(const uint64_t *peq, const uint8_t *tcodes, int W, int q0, int q1, int tfirst, int ncol,
                                                     uint64_t *PM, int32_t *out)
 {
-    const int Wq = (q1 - q0 + 63) >> 6;
-    if (Wq <= 32) path_warp_sweep<1, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out);
-    else if (Wq <= 64) path_warp_sweep<2, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out);
-    else if (Wq <= 128) path_warp_sweep<4, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out);
-    else path_warp_sweep<8, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out);
+    // the fewest words per lane that cover the sub-problem: a lane's words run one after the other, idle lanes cost nothing
+    switch (((q1 - q0 + 63) >> 6) + 31 >> 5) {
+        case 1: path_warp_sweep<1, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out); break;
+        case 2: path_warp_sweep<2, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out); break;
+        case 3: path_warp_sweep<3, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out); break;
+        case 4: path_warp_sweep<4, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out); break;
+        case 5: path_warp_sweep<5, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out); break;
+        case 6: path_warp_sweep<6, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out); break;
+        case 7: path_warp_sweep<7, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out); break;
+        default: path_warp_sweep<8, STORE, REV>(peq, tcodes, W, q0, q1, tfirst, ncol, PM, out); break;
+    }
 }
 
 // path_leaf_walk for a whole warp.  The scalar walk waits for three dependent loads per step; here lane l holds the stored
@@ -723,14 +729,19 @@ __global__ void __launch_bounds__(128) ed_path_warp_kernel(EdPathArgs a)
     s.left = reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes);
     s.right = reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + a.col_bytes);
     s.tmp = base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + 2 * (int64_t)a.col_bytes;
-    while (true) {
+    // three rounds over the pairs, the costliest class first (a 10 kb x 10 kb pair keeps its warp busy for milliseconds:
+    // started last it would be the tail of the launch)
+    int round = 0;
+    while (round < 3) {
         __syncwarp();
         int64_t p = 0;
-        if (lane == 0) p = atomicAdd(a.counter, 1);
+        if (lane == 0) p = atomicAdd(a.counter + round, 1);
         p = __shfl_sync(FULL, p, 0);
-        if (p >= a.npairs) break;
+        if (p >= a.npairs) { ++round; continue; }
         const EdPair pr = a.pairs[p];
         if (pr.W < ED_PATH_WARP_MIN_W || pr.W > ED_PATH_WARP_MAX_W) continue;   // ed_path_kernel's pairs
+        const long long cells = (long long)pr.m * pr.n;
+        if ((cells >= (1ll << 25) ? 0 : cells >= (1ll << 21) ? 1 : 2) != round) continue;
         const db200_ed_result r = a.results[p];
         int len = 0;
         if (!pr.special && r.status == 0 && r.edit_distance >= 0 && r.num_locations > 0) {
@@ -1023,7 +1034,8 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
             warps = std::max<int64_t>(4, std::min(warps, budget / xa.stride) / 4 * 4);
             xa.scratch = ws.alloc<uint8_t>((size_t)(warps * xa.stride));
             if (!xa.scratch) { set_error("ed_batch: device workspace allocation failed (path scratch)"); return DB200_ERR_NOMEM; }
-            xa.counter = counters + (ci++);
+            xa.counter = counters + ci;   // one per round
+            ci += 3;
             ed_path_warp_kernel<<<(unsigned)(warps / 4), 128, 0, st>>>(xa);
             count_launch(e);
         }
