@@ -4,7 +4,7 @@ ssw.c / edlib.cpp (oracle/_ref, all host threads) - or the oracle restatement wh
 
 Vectorised generators (numpy) so that millions of pairs are cheap; every integer output is compared:
 SW score1, score2, ref_begin1, ref_end1, read_begin1, read_end1, ref_end2, the cigar array; edit distance,
-alphabetLength and the full (start, end) location lists.
+alphabetLength, the full (start, end) location lists and, for task "path", every edit operation.
 
     python scripts/parity_sweep.py [--pairs 200000] [--seed 1]        # pairs per family and setting
 
@@ -121,8 +121,21 @@ def cmp_ed(r, ref):
     return bad
 
 
+def cmp_path(r, ref):
+    """edit operations of task "path": ours back to back (CSR), the reference driver's one slot per pair"""
+    ln = ref.path_len.astype(np.int64)
+    bad = np.diff(r.path_off) != ln
+    if not bad.any() and ln.sum():
+        idx = np.repeat(np.asarray(ref.path_off, dtype=np.int64) - (np.cumsum(ln) - ln), ln) + np.arange(int(ln.sum()), dtype=np.int64)
+        diff = ref.path[idx] != r.path[:int(ln.sum())]
+        if diff.any():
+            bad[np.unique(np.repeat(np.arange(len(ln)), ln)[diff])] = True
+    return bad
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--tasks", default="all", choices=["all", "path", "nopath"], help="path: only the edlib task 'path' settings")
     ap.add_argument("--pairs", type=int, default=100000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-len", type=int, default=600)
@@ -136,7 +149,12 @@ def main():
         (1, -4, 6, 1, 1, 1), (5, -4, 10, 2, 2, 1), (2, -8, 6, 1, 0, 1)]
     ed_settings = [("NW", "distance", None), ("HW", "locations", None), ("SHW", "locations", None), ("HW", "locations", 20),
                    ("NW", "locations", 40)]
-    total = bad_total = 0
+    if use_ref and a.tasks != "nopath":   # the path checker is the compiled reference itself (no restatement under oracle/)
+        ed_settings += [("NW", "path", None), ("HW", "path", None), ("SHW", "path", None), ("HW", "path", 20), ("NW", "path", 40)]
+    if a.tasks == "path":
+        sw_settings = []
+        ed_settings = [e for e in ed_settings if e[1] == "path"]
+    total = bad_total = ops_total = 0
     t0 = time.time()
     fams = list(families(rng, a.pairs, a.max_len))
     for name, q, t in fams:
@@ -158,9 +176,12 @@ def main():
             else:
                 ref = O.oracle_ed(qc, tc, mode, task, k, csr=True)
             bad = cmp_ed(r, ref)
+            if task == "path":
+                bad |= cmp_path(r, ref)
+                ops_total += int(ref.path_len.sum())
             total += len(q); bad_total += int(bad.sum())
             print("ED  %-14s %s/%s k=%s  pairs=%d  diffs=%d" % (name, mode, task, k, len(q), int(bad.sum())), flush=True)
-    print("TOTAL alignments compared: %d, differences: %d, %.0f s" % (total, bad_total, time.time() - t0))
+    print("TOTAL alignments compared: %d (edit operations of task 'path': %d), differences: %d, %.0f s" % (total, ops_total, bad_total, time.time() - t0))
     sys.exit(1 if bad_total else 0)
 
 
