@@ -15,6 +15,12 @@
  *   - *_device entry points take device pointers on `device` and enqueue everything on `stream`
  *     (a cudaStream_t passed as void*; NULL = the legacy default stream); outputs are device
  *     pointers too.  They return after enqueueing unless stated otherwise.
+ *   - Threads: the batch entry points may be called from several host threads (the reference's cores are
+ *     reentrant and edlib.pyx:129 releases the GIL); calls on the same device run one after the other
+ *     (a per-device lock held for the whole *_host call and for the enqueue of a *_device call), calls
+ *     on different devices run concurrently.  Results of a *_device call must have been consumed
+ *     (or the stream synchronised) before the next call on that device - the workspace is reused.
+ *     A ticket queue belongs to one thread.  After fork() the child creates its own engine lazily.
  *   - All functions return DB200_OK (0) or a negative DB200_ERR_* code; db200_last_error() gives
  *     a thread-local message.  There is no CPU fallback: without a CUDA device every compute
  *     entry point fails with DB200_ERR_CUDA.
