@@ -717,7 +717,7 @@ __device__ int ed_path_pair_warp(const uint64_t *peq, const uint8_t *tcodes, int
     return n;
 }
 
-__global__ void __launch_bounds__(128, 5) ed_path_warp_kernel(EdPathArgs a)
+__global__ void __launch_bounds__(128) ed_path_warp_kernel(EdPathArgs a)
 {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -1030,8 +1030,10 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
         }
         if (split) {
             layout(xa, std::min<int64_t>(std::max(max_query_len, 1), 64 * ED_PATH_WARP_MAX_W));
-            int64_t warps = std::min<int64_t>((npairs + 3) / 4 * 4, (int64_t)e->sm_count * 20);   // five blocks of four warps per SM
-            warps = std::max<int64_t>(4, std::min(warps, (budget + (budget >> 2)) / xa.stride) / 4 * 4);
+            // four blocks of four warps per SM at 122 registers (capping the registers for a fifth block spilled and ran
+            // the HiFi path stage at 40 instead of 36 ms)
+            int64_t warps = std::min<int64_t>((npairs + 3) / 4 * 4, (int64_t)e->sm_count * 16);
+            warps = std::max<int64_t>(4, std::min(warps, budget / xa.stride) / 4 * 4);
             xa.scratch = ws.alloc<uint8_t>((size_t)(warps * xa.stride));
             if (!xa.scratch) { set_error("ed_batch: device workspace allocation failed (path scratch)"); return DB200_ERR_NOMEM; }
             xa.counter = counters + ci;   // one per round
