@@ -442,6 +442,8 @@ struct EdPathArgs {
     int32_t leaf_bytes, vec_bytes, col_bytes;
     int32_t *counter;
     int32_t split;              // 1: pairs of ED_PATH_WARP_MIN_W..MAX_W query words belong to ed_path_warp_kernel
+    const int32_t *order;       // pair ids sorted by configuration and target length (the forward pass's task list), or null
+    const int32_t *seg_begin, *seg_count;
 };
 
 // Thread per pair, pairs handed out through a counter (their cost spans five orders of magnitude).  The alignment is the
@@ -465,9 +467,19 @@ __global__ void __launch_bounds__(64) ed_path_kernel(EdPathArgs a)
     s.left = SHORT ? lleft : reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes);
     s.right = SHORT ? lright : reinterpret_cast<int32_t *>(base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + a.col_bytes);
     s.tmp = base + a.leaf_bytes + 2 * (int64_t)a.vec_bytes + 2 * (int64_t)a.col_bytes;
+    // A warp takes 32 consecutive entries at a time and meets again before the next 32: in the sorted task list these are
+    // pairs of one configuration and one 64-column length bin, so the lanes run sweeps and walks of similar length.
+    const int lane = threadIdx.x & 31;
+    const int64_t total = a.order ? (int64_t)a.seg_begin[ED_NCFG - 1] + a.seg_count[ED_NCFG - 1] : a.npairs;
     while (true) {
-        const int64_t p = atomicAdd(a.counter, 1);
-        if (p >= a.npairs) break;
+        __syncwarp();
+        int first = 0;
+        if (lane == 0) first = atomicAdd(a.counter, 32);
+        first = __shfl_sync(0xFFFFFFFFu, first, 0);
+        if (first >= total) break;
+        const int64_t idx = (int64_t)first + lane;
+        if (idx >= total) continue;
+        const int64_t p = a.order ? a.order[total - 1 - idx] : idx;   // longest queries first
         const EdPair pr = a.pairs[p];
         if (a.split && pr.W >= ED_PATH_WARP_MIN_W && pr.W <= ED_PATH_WARP_MAX_W) continue;   // ed_path_warp_kernel's pairs
         const db200_ed_result r = a.results[p];
@@ -1014,7 +1026,9 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
         uint8_t *slots = ws.alloc<uint8_t>((size_t)(q_bytes + t_bytes + 16));
         int32_t *plen = ws.alloc<int32_t>((size_t)npairs);
         if (!slots || !plen) { set_error("ed_batch: device workspace allocation failed (path slots)"); return DB200_ERR_NOMEM; }
+        DB200_CUDA_CHECK(cudaMemsetAsync(plen, 0, sizeof(int32_t) * (size_t)npairs, st));   // pairs without DP are in no task list
         xa.path_buf = slots; xa.path_len = plen; xa.failed = overflow + 1; xa.npairs = npairs; xa.split = split ? 1 : 0;
+        xa.order = band ? nullptr : tasks; xa.seg_begin = seg_begin; xa.seg_count = seg_count;
         {
             const int64_t qmax = std::max(max_query_len, 1);
             const bool short_only = Wmax <= ED_PATH_WARP_MAX_W;   // longer queries than the warp kernel takes come back here
