@@ -84,3 +84,23 @@ def test_queue_needs_a_device():
     with pytest.raises(_lib.AlignEngineError):
         with dysgu_b200.deferred():
             pass
+
+
+def test_python_and_c_cigar_formatting_agree():
+    """batch.ops_to_cigar (vectorised, used for batches) and db200_edlibAlignmentToCigar (the C entry point) on random
+    operation arrays, both formats."""
+    L = _lib.lib()
+    L.db200_edlibAlignmentToCigar.restype = C.c_void_p
+    L.db200_edlibAlignmentToCigar.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        n = int(rng.integers(1, 400))
+        ops = np.repeat(rng.integers(0, 4, size=n, dtype=np.uint8), rng.integers(1, 6, size=n))
+        for fmt in (0, 1):
+            p = L.db200_edlibAlignmentToCigar(ops.tobytes(), len(ops), fmt)
+            s = C.string_at(p).decode()
+            libc.free(p)
+            assert s == batch.ops_to_cigar(ops, extended=bool(fmt))
+    assert batch.ops_to_cigar(np.zeros(0, np.uint8)) == ""
