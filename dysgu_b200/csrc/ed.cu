@@ -918,7 +918,6 @@ int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *prm, const
     int64_t peq_total = 0;
     DB200_CUDA_CHECK(cudaMemcpyAsync(&peq_total, peq_off + npairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     DB200_CUDA_CHECK(cudaStreamSynchronize(st));
-    (void)Wmax;
     uint64_t *peq = ws.alloc<uint64_t>((size_t)peq_total + 64);
     if (!peq) { set_error("ed_batch: device workspace allocation failed (Peq, %lld words)", (long long)peq_total); return DB200_ERR_NOMEM; }
 

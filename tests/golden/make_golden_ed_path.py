@@ -41,8 +41,8 @@ def cases(rng):
             t = pairgen.mutate(rng, q, 0.05, 0.05, 0.05, "AC")
         t = t or "A"
         out.append((q, t))
-    for i in range(7):                        # large: the halving regime (state >= 1 MB)
-        L = [1800, 2500, 4000, 7000, 10000, 3000, 3500][i]
+    for i in range(8):                        # large: the halving regime (state >= 1 MB); the last one is beyond the warp kernel's 256 words
+        L = [1800, 2500, 4000, 7000, 10000, 3000, 3500, 17000][i]
         q = pairgen.rand_dna(rng, L)
         if i % 7 == 5:
             t = pairgen.rand_dna(rng, int(L * rng.uniform(0.8, 1.2)))
