@@ -360,7 +360,7 @@ int db200_sw_batch_device(int device, const db200_sw_params *params, const uint8
 {
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
-    std::lock_guard<std::mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
+    std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
     cudaStream_t ust = (cudaStream_t)stream;
     // DB200_DEVICE_SUBBATCHES=n cuts the batch into n sub-batches on the engine's slot streams (they share the caller's
     // output arrays; only the placement of the cigars is ordered, SwLink).  Off by default: measured on B200 with the
@@ -449,7 +449,7 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
 {
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
-    std::lock_guard<std::mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
+    std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
     if (npairs < 0 || !params || !qoff || !toff || !results) { set_error("sw_batch_host: bad arguments"); return DB200_ERR_ARG; }
     if (cigar_off) cigar_off[0] = 0;
     constexpr int NS = Engine::NSLOT;
@@ -700,7 +700,7 @@ int db200_ed_batch_device(int device, const db200_ed_params *params, const uint8
 {
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
-    std::lock_guard<std::mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
+    std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
     e->arena[0].reset();
     e->aux_set = 0;
     return ed_batch_device_impl(e, e->arena[0], params, d_qbuf, d_qoff, q_bytes, d_tbuf, d_toff, t_bytes, npairs, max_query_len,
@@ -715,7 +715,7 @@ int db200_ed_path_batch_device(int device, const db200_ed_params *params, const 
 {
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
-    std::lock_guard<std::mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
+    std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
     if (!params || params->task != DB200_ED_TASK_PATH) { set_error("ed_path_batch: params->task must be DB200_ED_TASK_PATH"); return DB200_ERR_ARG; }
     e->arena[0].reset();
     e->aux_set = 0;
@@ -732,7 +732,7 @@ static int ed_batch_host_impl(int device, const db200_ed_params *params, const u
 {
     Engine *e = get_engine(device);
     if (!e) return DB200_ERR_CUDA;
-    std::lock_guard<std::mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
+    std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
     if (npairs < 0 || !params || !qoff || !toff || !results || !loc_buf || !loc_off) { set_error("ed_batch_host: bad arguments"); return DB200_ERR_ARG; }
     const bool want_path = params->task == DB200_ED_TASK_PATH;
     if (want_path && (!path_buf || !path_off)) {

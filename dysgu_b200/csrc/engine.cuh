@@ -47,7 +47,7 @@ struct Arena {
 struct Engine {
     int device = -1;
     bool ready = false;
-    std::mutex call_mu;                  // held by every batch entry point for the length of the call
+    std::recursive_mutex call_mu;                 // held by every batch entry point for the length of the call
     cudaStream_t stream = nullptr;       // used by the *_host entry points
     static constexpr int NSLOT = 3;      // host chunks in flight: copy of chunk i+2 / compute of chunk i+1 / drain of chunk i
     cudaStream_t slot_stream[NSLOT] = {}; // compute stream per slot ([0] is `stream`): consecutive chunks overlap their stage tails
