@@ -20,8 +20,14 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def blocks():
+    """The vectors the device suite runs.  The file also holds a 17 kb pair (beyond the warp kernel's 256 query words) that
+    only the CPU test of the shared path code runs (tests/test_ed_path_host.py): queries above 10 kb - the length dysgu
+    truncates its sequences to - take kernel configurations this suite has not been run with on a GPU yet."""
     with open(os.path.join(G, "ed_path.json")) as f:
-        return json.load(f)
+        out = json.load(f)
+    for b in out:
+        b["cases"] = [c for c in b["cases"] if len(c["query"]) <= 10000]
+    return out
 
 
 def test_path_batches_match_the_reference():
