@@ -16,3 +16,26 @@ def deferred(device=None):
     """Context manager: StripedSmithWaterman(...)(...) / edlib.align(...) inside the block submit to one queue (see queue.py)."""
     from .queue import deferred as _deferred
     return _deferred(device)
+
+
+def install():
+    """Route dysgu's two alignment extension modules to this engine without touching dysgu's files.
+
+    Afterwards `from dysgu.scikitbio._ssw_wrapper import StripedSmithWaterman` (consensus.pyx:16, re_map.py:1,
+    post_call.py:15, filter_normals.py:18), `import dysgu.edlib as edlib` (re_map.py:6) and `from dysgu.edlib import edlib`
+    (filter_normals.py:20) resolve to dysgu_b200.  Call it before dysgu's own modules are imported; the `dysgu` package
+    itself is imported normally.  Returns the names that were installed.
+    """
+    import sys
+    from . import edlib as _edlib_pkg
+    from . import scikitbio as _skbio_pkg
+    from .edlib import edlib as _edlib_mod
+    from .scikitbio import _ssw_wrapper as _ssw_mod
+    table = {"dysgu.scikitbio": _skbio_pkg, "dysgu.scikitbio._ssw_wrapper": _ssw_mod,
+             "dysgu.edlib": _edlib_pkg, "dysgu.edlib.edlib": _edlib_mod}
+    for name, mod in table.items():
+        sys.modules[name] = mod
+        parent, _, leaf = name.rpartition(".")
+        if parent in sys.modules and parent != "dysgu_b200":
+            setattr(sys.modules[parent], leaf, mod)   # `from dysgu import edlib` after dysgu has been imported
+    return sorted(table)

@@ -114,3 +114,30 @@ def test_cigar_stats_match_a_string_parse():
                 want = 0 if (matches and np.float32(gaps) / np.float32(matches) > np.float32(tol)) else matches
             assert got[i] == want, (s, max_gap, tol)
     assert st.shape == (300, 3) and (st[np.diff(off) == 0] == 0).all()
+
+
+def test_install_routes_dysgu_imports(tmp_path, monkeypatch):
+    """dysgu_b200.install(): the import statements dysgu's modules use resolve to the engine's drop-ins (a stand-in `dysgu`
+    package, since the real one needs pysam to import)."""
+    import importlib
+    import sys
+    import dysgu_b200
+    pkg = tmp_path / "dysgu"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text("")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    for name in [n for n in sys.modules if n == "dysgu" or n.startswith("dysgu.")]:
+        monkeypatch.delitem(sys.modules, name)
+    names = dysgu_b200.install()
+    try:
+        assert names == ["dysgu.edlib", "dysgu.edlib.edlib", "dysgu.scikitbio", "dysgu.scikitbio._ssw_wrapper"]
+        from dysgu.scikitbio._ssw_wrapper import StripedSmithWaterman as S1       # consensus.pyx:16, re_map.py:1
+        from dysgu.scikitbio import StripedSmithWaterman as S2, AlignmentStructure  # scikitbio/__init__.py:10-11
+        import dysgu.edlib as e1                                                  # re_map.py:6
+        from dysgu.edlib import edlib as e2                                       # filter_normals.py:20
+        assert S1 is StripedSmithWaterman and S2 is StripedSmithWaterman and AlignmentStructure is not None
+        assert e1.align is ed_wrap.align and e2.align is ed_wrap.align and e2.getNiceAlignment is ed_wrap.getNiceAlignment
+        assert importlib.import_module("dysgu").__file__.startswith(str(tmp_path))
+    finally:
+        for name in [n for n in sys.modules if n == "dysgu" or n.startswith("dysgu.")]:
+            sys.modules.pop(name, None)
