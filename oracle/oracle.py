@@ -54,6 +54,7 @@ def oracle_lib():
         _oracle = C.CDLL(path)
         _oracle.sw_oracle_batch_nt.restype = C.c_int
         _oracle.ed_oracle_batch.restype = C.c_int
+        _oracle.ed_path_oracle_batch.restype = C.c_int
     return _oracle
 
 
@@ -205,6 +206,31 @@ def oracle_ed(queries, targets, mode="NW", task="distance", k=None, csr=False):
     qcsr = queries if csr else to_csr(queries)
     tcsr = targets if csr else to_csr(targets)
     return _ed_batch(oracle_lib().ed_oracle_batch, qcsr, tcsr, mode, task, k)
+
+
+def oracle_ed_path(queries, targets, mode="NW", k=None, additional_equalities=None, csr=False):
+    """edlib.align(..., task="path") by the scalar restatement (ed_path_oracle.c): the fields of oracle_ed plus the edit
+    operations, pair i at path[path_off[i] : path_off[i] + path_len[i]] (the reference driver's layout)."""
+    qbuf, qoff = queries if csr else to_csr(queries)
+    tbuf, toff = targets if csr else to_csr(targets)
+    n = len(qoff) - 1
+    fixed = np.zeros((n, 4), dtype=np.int32)
+    cap = int(np.diff(toff).sum()) + 2 * n + 16
+    loc = np.zeros((max(cap, 1), 2), dtype=np.int32)
+    loff = np.zeros(n + 1, dtype=np.int64)
+    karr = None if k is None else np.ascontiguousarray(np.broadcast_to(np.asarray(k, dtype=np.int32), (n,)))
+    eq = b"".join(bytes([a if isinstance(a, int) else ord(a), b if isinstance(b, int) else ord(b)]) for a, b in (additional_equalities or []))
+    poff = (np.asarray(qoff) - qoff[0] + np.asarray(toff) - toff[0])[:n]
+    path = np.zeros(int(qoff[n] - qoff[0] + toff[n] - toff[0]) + 1, dtype=np.uint8)
+    plen = np.zeros(max(n, 1), dtype=np.int32)
+    rc = oracle_lib().ed_path_oracle_batch(_p(qbuf, C.c_char), _p(qoff, C.c_int64), _p(tbuf, C.c_char), _p(toff, C.c_int64), C.c_int64(n),
+                                           C.c_int32(MODES[mode] if isinstance(mode, str) else mode),
+                                           _p(karr, C.c_int32) if karr is not None else None, eq if eq else None, C.c_int32(len(eq) // 2),
+                                           _p(fixed, C.c_int32), _p(loc, C.c_int32), C.c_int64(cap), _p(loff, C.c_int64),
+                                           _p(path, C.c_uint8), _p(plen, C.c_int32))
+    if rc != 0:
+        raise RuntimeError("ed_path_oracle_batch failed: %r" % rc)
+    return EdBatchResult(fixed, loc[:loff[n]], loff, path=path, path_off=poff, path_len=plen[:n])
 
 
 def ref_ed(queries, targets, mode="NW", task="distance", k=None, nthreads=1, csr=False, want_loc=True):

@@ -54,6 +54,25 @@ def chunk_ed(args):
     return len(qs), bad
 
 
+def chunk_path(args):
+    """task "path": the scalar restatement (ed_path_oracle.c) against the reference's alignment arrays"""
+    seed, n, max_len = args
+    qs, ts = pairgen.ed_pairs(seed, n, max_len)
+    mode = ["HW", "NW", "SHW"][seed % 3]
+    k = [None, None, 5, 40][(seed // 3) % 4]
+    a = O.oracle_ed_path(qs, ts, mode, k)
+    b = O.ref_ed(qs, ts, mode, "path", k, nthreads=1)
+    bad = 0
+    for i in range(len(qs)):
+        pa = a.path[a.path_off[i]:a.path_off[i] + a.path_len[i]]
+        pb = b.path[b.path_off[i]:b.path_off[i] + b.path_len[i]]
+        if a.as_dict(i) != b.as_dict(i) or not np.array_equal(pa, pb):
+            bad += 1
+            if bad <= 3:
+                print("PATH DIFF", mode, k, qs[i], ts[i], a.as_dict(i), b.as_dict(i))
+    return len(qs), bad, int(b.path_len.sum())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=20000)
@@ -75,7 +94,12 @@ def main():
         for n, b in ex.map(chunk_ed, jobs):
             tot2 += n; bad2 += b
     print("ED: compared %d pairs, %d differences" % (tot2, bad2))
-    sys.exit(1 if (bad or bad2) else 0)
+    tot3 = bad3 = ops3 = 0
+    with ThreadPoolExecutor(a.threads) as ex:
+        for n, b, o in ex.map(chunk_path, jobs):
+            tot3 += n; bad3 += b; ops3 += o
+    print("ED path: compared %d pairs (%d edit operations), %d differences" % (tot3, ops3, bad3))
+    sys.exit(1 if (bad or bad2 or bad3) else 0)
 
 
 if __name__ == "__main__":

@@ -81,3 +81,24 @@ def test_oracle_equals_compiled_reference_random():
         a = O.oracle_ed(qs, ts, mode, "locations")
         b = O.ref_ed(qs, ts, mode, "locations")
         assert all(a.as_dict(i) == b.as_dict(i) for i in range(len(qs)))
+
+
+def test_ed_path_oracle_matches_golden():
+    """The scalar restatement of task "path" (oracle/ed_path_oracle.c) against the reference wrapper's vectors: direct
+    traceback and the halving regime (up to 17 kb x 17 kb), NW / SHW / HW, k cut-offs, additionalEqualities."""
+    from dysgu_b200.batch import ops_to_cigar
+    checked = none = 0
+    for b in load("ed_path.json"):
+        qs = [c["query"].encode() for c in b["cases"]]
+        ts = [c["target"].encode() for c in b["cases"]]
+        eqs = [tuple(e) for e in b.get("equalities", [])]
+        r = O.oracle_ed_path(qs, ts, b["mode"], None if b["k"] == -1 else b["k"], eqs)
+        for i, c in enumerate(b["cases"]):
+            key = (b["mode"], b["k"], i, len(qs[i]), len(ts[i]))
+            d = r.as_dict(i)
+            assert d["editDistance"] == c["editDistance"] and d["locations"] == [tuple(x) for x in c["locations"]], key
+            ops = r.path[r.path_off[i]:r.path_off[i] + r.path_len[i]]
+            assert (ops_to_cigar(ops) if len(ops) else None) == c["cigar"], key
+            checked += 1
+            none += c["cigar"] is None
+    assert checked > 1500 and none > 100
