@@ -73,6 +73,14 @@ def lib():
                                                  C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                                  C.c_void_p, C.c_void_p]
+    if hasattr(L, "db200_sw_cigar_text"):
+        L.db200_sw_cigar_text.restype = C.c_int
+        L.db200_sw_cigar_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        L.db200_sw_aligned_text.restype = C.c_int
+        L.db200_sw_aligned_text.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                            C.c_int64, C.c_void_p]
+        L.db200_ed_cigar_text.restype = C.c_int
+        L.db200_ed_cigar_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     _lib = L
     return L
 

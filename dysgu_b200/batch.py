@@ -50,6 +50,21 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data
 
 
+def _csr_text(call):
+    """Run one of the db200_*_text formatters (sizes first, then the text) -> (bytes, int64 offsets[n+1])."""
+    rc, off = call(None, 0)
+    _lib.check(rc, "text formatting")
+    buf = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+    rc, off = call(buf, int(off[-1]))
+    _lib.check(rc, "text formatting")
+    return buf.tobytes()[:int(off[-1])], off
+
+
+def _split_text(text: bytes, off) -> list:
+    s = text.decode("ascii")
+    return [s[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
 class SwResults:
     """Results of a Smith-Waterman batch (fields follow s_align, ssw.h:38-48)."""
 
@@ -75,6 +90,40 @@ class SwResults:
 
     def as_tuple(self, i):
         return tuple(int(x) for x in self.fixed[i, :7]) + (self.cigar_str(i),)
+
+    def cigar_strings(self) -> list:
+        """AlignmentStructure.cigar of every pair (_ssw_wrapper.pyx:240-275), formatted by one C call (db200_sw_cigar_text)."""
+        n = len(self)
+        L = _lib.lib()
+        off = np.zeros(n + 1, dtype=np.int64)
+        cig = self.cigar if self.cigar.size else np.zeros(1, np.uint32)
+        coff = np.ascontiguousarray(self.cigar_off, dtype=np.int64)
+
+        def call(buf, cap):
+            return L.db200_sw_cigar_text(_ptr(cig), _ptr(coff), n, _ptr(buf), cap, _ptr(off)), off
+        return _split_text(*_csr_text(call))
+
+    def aligned_strings(self, queries, targets):
+        """(aligned_query_sequence, aligned_target_sequence) of every pair with zero-based coordinates
+        (_ssw_wrapper.pyx:302-364), formatted by two C calls (db200_sw_aligned_text) over the batch the results came from."""
+        n = len(self)
+        L = _lib.lib()
+        cig = self.cigar if self.cigar.size else np.zeros(1, np.uint32)
+        coff = np.ascontiguousarray(self.cigar_off, dtype=np.int64)
+        fixed = np.ascontiguousarray(self.fixed, dtype=np.int32)
+        out = []
+        for which, seqs in ((0, _as_batch(queries)), (1, _as_batch(targets))):
+            if len(seqs) != n:
+                raise ValueError("sequences and results differ in length")
+            off = np.zeros(n + 1, dtype=np.int64)
+            sbuf = seqs.buf if seqs.buf.size else np.zeros(1, np.uint8)
+            soff = np.ascontiguousarray(seqs.off, dtype=np.int64)
+
+            def call(buf, cap, which=which, sbuf=sbuf, soff=soff, off=off):
+                return L.db200_sw_aligned_text(which, _ptr(sbuf), _ptr(soff), _ptr(fixed), _ptr(cig), _ptr(coff), n, _ptr(buf), cap,
+                                               _ptr(off)), off
+            out.append(_split_text(*_csr_text(call)))
+        return out[0], out[1]
 
     def cigar_stats(self):
         """Per pair, straight from the BAM-encoded cigar arrays (no string round trip): int64 [n, 3] =
@@ -157,6 +206,21 @@ class EdResults:
         """edlibAlignmentToCigar of pair i (edlib.cpp:298-347; the wrapper uses the extended format, edlib.pyx:143-147)."""
         ops = self.alignment(i)
         return None if ops is None else ops_to_cigar(ops, extended)
+
+    def cigar_strings(self, extended=True) -> list:
+        """The cigar of every pair of a task "path" batch (None where the reference returns none), one C call
+        (db200_ed_cigar_text)."""
+        if self.path is None:
+            return [None] * len(self)
+        n = len(self)
+        L = _lib.lib()
+        off = np.zeros(n + 1, dtype=np.int64)
+        path = self.path if self.path.size else np.zeros(1, np.uint8)
+        poff = np.ascontiguousarray(self.path_off, dtype=np.int64)
+
+        def call(buf, cap):
+            return L.db200_ed_cigar_text(_ptr(path), _ptr(poff), n, 1 if extended else 0, _ptr(buf), cap, _ptr(off)), off
+        return [s if s else None for s in _split_text(*_csr_text(call))]
 
     def as_dict(self, i):
         st, ed, al, nl = (int(x) for x in self.fixed[i])

@@ -269,6 +269,27 @@ void db200_edlibFreeAlignResult(db200_EdlibAlignResult result);
 char *db200_edlibAlignmentToCigar(const unsigned char *alignment, int alignmentLength, int cigarFormat);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Batch text formatting on the host.  The strings dysgu's callers read from the   */
+/* result objects, for every pair of a batch in one call, from the arrays the batch entry       */
+/* points return.  No CUDA involved.  Output is CSR text: pair i is out[out_off[i]..out_off[i+1]) */
+/* (not NUL-terminated); with out == NULL only out_off is filled (sizes), so a caller sizes its   */
+/* buffer with a first call.                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+/* AlignmentStructure.cigar (_ssw_wrapper.pyx:240-275): "%d%c" per BAM-encoded op, M/I/D. */
+int db200_sw_cigar_text(const uint32_t *cigar_buf, const int64_t *cigar_off, int64_t npairs,
+                        char *out, int64_t out_cap, int64_t *out_off);
+/* aligned_query_sequence (which = 0; seq = the queries, '-' where the cigar deletes) or
+ * aligned_target_sequence (which = 1; seq = the targets, '-' where it inserts) with zero-based
+ * coordinates (_ssw_wrapper.pyx:302-364, including "our sequence end is sometimes beyond the cigar"). */
+int db200_sw_aligned_text(int which, const uint8_t *seq_buf, const int64_t *seq_off,
+                          const db200_sw_result *results, const uint32_t *cigar_buf, const int64_t *cigar_off,
+                          int64_t npairs, char *out, int64_t out_cap, int64_t *out_off);
+/* edlibAlignmentToCigar for every pair of a task "path" batch (format 0 standard, 1 extended;
+ * edlib.cpp:298-347); a pair without operations gives an empty string. */
+int db200_ed_cigar_text(const uint8_t *path_buf, const int64_t *path_off, int64_t npairs, int format,
+                        char *out, int64_t out_cap, int64_t *out_off);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Ticket queue: submit / flush / fetch (SURVEY 8b "new batched ABI").                          */
 /* The reference's call sites are synchronous per pair - StripedSmithWaterman(q)(t)             */
 /* (_ssw_wrapper.pyx:613-652) and edlib.align (edlib.pyx:57-156).  A caller that collects its   */
