@@ -93,3 +93,23 @@ def test_path_cigars_of_a_batch():
         std = res.cigar_strings(extended=False)
         assert all((s is None) == (g is None) and (s is None or set(s) <= set("0123456789MID")) for s, g in zip(std, got))
         assert [res.cigar(i) for i in range(len(cs))] == got
+
+
+def test_formatters_report_bad_input_and_small_buffers():
+    import ctypes as C
+    from dysgu_b200 import _lib
+    L = _lib.lib()
+    cig = np.array([(17 << 4) | 0, (2 << 4) | 1, (5 << 4) | 2], np.uint32)
+    coff = np.array([0, 3], np.int64)
+    off = np.zeros(2, np.int64)
+    assert L.db200_sw_cigar_text(cig.ctypes.data, coff.ctypes.data, 1, None, 0, off.ctypes.data) == 0 and off[1] == 7   # "17M2I5D"
+    buf = np.zeros(16, np.uint8)
+    assert L.db200_sw_cigar_text(cig.ctypes.data, coff.ctypes.data, 1, buf.ctypes.data, 6, off.ctypes.data) == -4          # DB200_ERR_CAPACITY
+    assert b"too small" in L.db200_last_error()
+    assert L.db200_sw_cigar_text(cig.ctypes.data, coff.ctypes.data, 1, buf.ctypes.data, 7, off.ctypes.data) == 0
+    assert buf[:7].tobytes() == b"17M2I5D"
+    bad = np.array([(3 << 4) | 7], np.uint32)                                                                              # op 7 is not M/I/D
+    assert L.db200_sw_cigar_text(bad.ctypes.data, np.array([0, 1], np.int64).ctypes.data, 1, None, 0, off.ctypes.data) == -2
+    ops = np.array([0, 0, 9], np.uint8)
+    assert L.db200_ed_cigar_text(ops.ctypes.data, np.array([0, 3], np.int64).ctypes.data, 1, 1, None, 0, off.ctypes.data) == -2
+    assert L.db200_ed_cigar_text(ops.ctypes.data, np.array([0, 2], np.int64).ctypes.data, 1, 2, None, 0, off.ctypes.data) == -2   # unknown format
