@@ -154,6 +154,15 @@ class LazyAlignmentStructure(AlignmentStructure):
         raise AttributeError(name)
 
 
+def _require_ascii(seq):
+    """The reference indexes a 128-entry table per character (_ssw_wrapper.pyx:676-678): the first code point above 127
+    raises IndexError.  str.isascii() answers the common case without a Python-level loop over the sequence."""
+    if not seq.isascii():
+        for ch in seq:
+            if ord(ch) > 127:
+                raise IndexError("index %d is out of bounds for axis 0 with size 128" % ord(ch))
+
+
 class StripedSmithWaterman:
     """Same constructor and call surface as the reference class (_ssw_wrapper.pyx:397-709)."""
 
@@ -192,9 +201,7 @@ class StripedSmithWaterman:
                 self.mask_length = mask_length
         else:
             self.mask_length = mask_length
-        for ch in query_sequence:  # the reference indexes a 128-entry table (:676-678)
-            if ord(ch) > 127:
-                raise IndexError("index %d is out of bounds for axis 0 with size 128" % ord(ch))
+        _require_ascii(query_sequence)
         self._query_bytes = query_sequence.encode("ascii")
 
     def _get_bit_flag(self, override_skip_babp, score_only):
@@ -214,9 +221,7 @@ class StripedSmithWaterman:
     def _run(self, targets):
         tb = []
         for t in targets:
-            for ch in t:
-                if ord(ch) > 127:
-                    raise IndexError("index %d is out of bounds for axis 0 with size 128" % ord(ch))
+            _require_ascii(t)
             tb.append(t.encode("ascii"))
         res = _batch.sw_align_batch([self._query_bytes] * len(tb), tb, match=self.match_score, mismatch=self.mismatch_score,
                                     gap_open=self.gap_open_penalty, gap_extend=self.gap_extend_penalty,
@@ -238,9 +243,7 @@ class StripedSmithWaterman:
         if q is None:
             return self._run([target_sequence])[0]
         # deferred mode: submit now, resolve on first use
-        for ch in target_sequence:
-            if ord(ch) > 127:
-                raise IndexError("index %d is out of bounds for axis 0 with size 128" % ord(ch))
+        _require_ascii(target_sequence)
         ticket = q.submit_sw(self._query_bytes, target_sequence.encode("ascii"), match=self.match_score, mismatch=self.mismatch_score,
                              gap_open=self.gap_open_penalty, gap_extend=self.gap_extend_penalty, score_size=self.score_size,
                              flag=self.bit_flag, filters=self.score_filter, filterd=self.distance_filter, mask_len=self.mask_length,
