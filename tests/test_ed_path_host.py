@@ -57,3 +57,31 @@ def test_paths_match_the_reference(lib):
             checked += 1
             big += len(c["query"]) >= 1800
     assert checked > 1000 and big >= 10
+
+
+def test_paths_match_the_scalar_oracle_on_random_pairs(lib):
+    """The shared path code (bit-vector sweeps, stored-column leaves) against the integer-matrix restatement
+    (oracle/ed_path_oracle.c) on random global alignments, with wildcard equalities on a third of them and a handful of
+    pairs in the halving regime."""
+    import random
+    import numpy as np
+    import pairgen
+    from oracle import oracle as O
+    rng = random.Random(31337)
+    eqs = [("N", "A"), ("N", "C"), ("N", "G"), ("N", "T")]
+    for block in range(3):
+        qs, ts = [], []
+        for i in range(2500 if block < 2 else 12):
+            L = rng.choice([1, 5, 63, 64, 65, 128, 129, 200, 400, 700]) if block < 2 else rng.choice([2600, 3300, 4800])
+            alpha = "ACGTN" if block == 1 else ("AC" if i % 7 == 0 else "ACGT")
+            q = pairgen.rand_dna(rng, L, alpha)
+            e = rng.choice([0.0, 0.01, 0.05, 0.2])
+            t = (pairgen.mutate(rng, q, e, e, e, alpha) if i % 5 else pairgen.rand_dna(rng, rng.randint(1, 2 * L), alpha)) or "A"
+            qs.append(q.encode()); ts.append(t.encode())
+        use = eqs if block == 1 else []
+        r = O.oracle_ed_path(qs, ts, "NW", None, use)
+        eqb = "".join(a + b for a, b in use).encode()
+        for i in range(len(qs)):
+            d, cig = host_path(lib, qs[i], ts[i], eqb)
+            ops = r.path[r.path_off[i]:r.path_off[i] + r.path_len[i]]
+            assert d == r.fixed[i, 1] and cig == cigar_of(bytes(ops)), (block, i, len(qs[i]), len(ts[i]))
