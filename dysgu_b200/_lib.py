@@ -45,6 +45,8 @@ def lib():
     L.db200_workspace_bytes.restype = C.c_int64
     L.db200_kernel_launches.restype = C.c_int64
     L.db200_ed_word_steps.restype = C.c_int64
+    L.db200_forked_after_init.restype = C.c_int
+    L.db200_default_device.restype = C.c_int
     L.db200_host_alloc.restype = C.c_void_p
     L.db200_host_alloc.argtypes = [C.c_int64]
     L.db200_host_free.argtypes = [C.c_void_p]

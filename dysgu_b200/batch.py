@@ -12,6 +12,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
+from . import server as _server
 from .workloads import SeqBatch
 
 SW_FIELDS = ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len")
@@ -151,6 +152,11 @@ def sw_align_batch(queries, targets, match=2, mismatch=-3, gap_open=5, gap_exten
     n = len(q)
     if len(t) != n:
         raise ValueError("queries and targets differ in length")
+    if _server.should_route():   # forked after the parent initialised CUDA: the parent's engine runs the batch
+        return SwResults(*_server.remote("sw", (q, t), dict(match=match, mismatch=mismatch, gap_open=gap_open, gap_extend=gap_extend,
+                                                            score_size=score_size, flag=flag, filters=filters, filterd=filterd,
+                                                            mask_len=mask_len, matrix=matrix, want_cigar=want_cigar)))
+    _server.ensure_started()
     L = _lib.lib()
     prm = _lib.SwParams()
     prm.match, prm.mismatch, prm.gap_open, prm.gap_extend = match, mismatch, gap_open, gap_extend
@@ -249,6 +255,9 @@ def ed_align_batch(queries, targets, mode="NW", task="distance", k=-1, additiona
     n = len(q)
     if len(t) != n:
         raise ValueError("queries and targets differ in length")
+    if _server.should_route():
+        return EdResults(*_server.remote("ed", (q, t), dict(mode=mode, task=task, k=k, additional_equalities=additional_equalities)))
+    _server.ensure_started()
     L = _lib.lib()
     if not hasattr(L, "db200_ed_batch_host"):
         raise _lib.AlignEngineError("this build of libdysgu_b200_align.so has no edit-distance entry points")

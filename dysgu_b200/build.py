@@ -1,4 +1,4 @@
-"""Build libdysgu_b200_align.so (and the int_peak micro-benchmark) in-tree with nvcc for sm_100a.
+"""Build libdysgu_b200_align.so (+ libdysgu_b200_compat.so, the int_peak micro-benchmark) in-tree with nvcc for sm_100a.
 
     python -m dysgu_b200.build [--force]
 
@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libdysgu_b200_align.so")
+COMPAT = os.path.join(HERE, "libdysgu_b200_compat.so")
 PEAK = os.path.join(HERE, "int_peak")
 SOURCES = ["engine.cu", "sw.cu", "ed.cu", "queue.cu", "format.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "dysgu_b200_align.h")]
@@ -56,6 +57,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(out)
     if force or jobs or _newer(LIB, objs):
         _run([NVCC] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-o", LIB] + objs)
+    # the reference's own symbol names (ssw_init, edlibAlign, ...) as a library of their own over the engine: what dysgu's
+    # unmodified _ssw_wrapper.pyx / edlib.pyx link against instead of ssw.c / edlib.cpp (oracle/build_compat.sh)
+    compat_src = os.path.join(CSRC, "compat.c")
+    if force or jobs or _newer(COMPAT, [compat_src, LIB] + deps):
+        _run(["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-fvisibility=hidden", compat_src, "-o", COMPAT,
+              "-L" + HERE, "-ldysgu_b200_align", "-Wl,-rpath,$ORIGIN"])
     peak_src = os.path.join(CSRC, "int_peak.cu")
     if force or _newer(PEAK, [peak_src]):
         _run([NVCC] + ARCH + ["-O3", "-lineinfo", peak_src, "-o", PEAK])

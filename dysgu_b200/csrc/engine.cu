@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <unistd.h>
+#include <pthread.h>
+#include <new>
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -57,21 +59,52 @@ void Arena::release()
     used = 0;
 }
 
-// ---- engines (per process; re-created after fork because the pid changes) --------------------------
+// ---- engines (per process) ------------------------------------------------------------------------------
+// fork(): a child of a process that has NOT touched CUDA through this library creates its own engines lazily (the pid
+// changes, the table is cleared).  A child forked AFTER the parent initialised CUDA cannot use the GPU at all - the
+// driver state it inherited is unusable and cannot be re-initialised (this is the order dysgu call -p N produces:
+// re_map.remap_soft_clips in the parent, cluster.pyx:475-478, then the Pool of merge_svs.pyx:396).  That condition is
+// detected here and reported as DB200_ERR_FORKED instead of a misleading "no CUDA device"; the Python layer routes such
+// children to the parent's engine (dysgu_b200/server.py) and dysgu_b200.patch keeps the pool's work in the parent.
 static std::mutex g_mu;
 static Engine *g_engines[64] = {nullptr};
 static pid_t g_pid = 0;
+static bool g_cuda_touched = false;        // this process (or the ancestor it was forked from) has called into the CUDA runtime
+static bool g_forked_after_cuda = false;   // set in the child by the atfork handler
+static std::once_flag g_atfork_once;
+
+static void atfork_child()
+{
+    if (g_cuda_touched) g_forked_after_cuda = true;
+    new (&g_mu) std::mutex();              // the parent may have held it in another thread at fork time
+}
+
+static const char *FORK_MSG =
+    "this process was fork()ed after its parent initialised CUDA: the GPU cannot be used here. Keep the alignment batches in "
+    "the parent (dysgu_b200.patch / dysgu_b200.server) or start the workers with the 'spawn' method";
+
+bool forked_after_cuda() { return g_forked_after_cuda; }
+
+static int cuda_device_count()
+{
+    std::call_once(g_atfork_once, [] { pthread_atfork(nullptr, nullptr, atfork_child); });
+    if (g_forked_after_cuda) return -1;
+    g_cuda_touched = true;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
 
 Engine *get_engine(int device)
 {
     std::lock_guard<std::mutex> lock(g_mu);
-    if (g_pid != getpid()) { // first use, or a fork()ed child: CUDA state of the parent is unusable here
+    if (g_pid != getpid()) { // first use, or a fork()ed child of a parent that had not touched CUDA
         for (auto &e : g_engines) e = nullptr;
         g_pid = getpid();
     }
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
-        cudaGetLastError();
+    const int count = cuda_device_count();
+    if (count < 0) { set_error("%s", FORK_MSG); return nullptr; }
+    if (count == 0) {
         set_error("no CUDA device available: libdysgu_b200_align has no CPU fallback");
         return nullptr;
     }
@@ -104,6 +137,7 @@ Engine *get_engine(int device)
     for (int i = 0; i < Engine::NSLOT; ++i) {
         cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_cig[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_sub_join[i], cudaEventDisableTiming);
     }
     for (int i = 0; i < Engine::NSUB_MAX; ++i) cudaEventCreateWithFlags(&e->ev_sub[i], cudaEventDisableTiming);
@@ -237,12 +271,23 @@ extern "C" {
 
 int db200_device_count(void)
 {
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return count;
+    const int count = cuda_device_count();
+    return count < 0 ? 0 : count;
 }
 
-int db200_init(int device) { return get_engine(device) ? DB200_OK : DB200_ERR_CUDA; }
+int db200_forked_after_init(void) { return forked_after_cuda() ? 1 : 0; }
+
+int db200_init(int device) { return get_engine(device) ? DB200_OK : (forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA); }
+
+// Device of the legacy single-pair entry points (their signatures have no device argument): DB200_DEVICE, else
+// LOCAL_RANK, else 0 - the rule of the Python layer (batch.default_device).
+int db200_default_device(void)
+{
+    const char *v = getenv("DB200_DEVICE");
+    if (!v || !*v) v = getenv("LOCAL_RANK");
+    const int d = (v && *v) ? atoi(v) : 0;
+    return d < 0 ? 0 : d;
+}
 
 void db200_shutdown(void)
 {
@@ -257,7 +302,7 @@ void db200_shutdown(void)
         if (e->pinned) cudaFreeHost(e->pinned);
         for (int k = 0; k < Engine::NSLOT; ++k) {
             for (int i = 0; i < Engine::NAUX; ++i) { cudaStreamDestroy(e->aux[k][i]); cudaEventDestroy(e->ev_join[k][i]); }
-            cudaEventDestroy(e->ev_fork[k]); cudaEventDestroy(e->ev_copy[k]); cudaEventDestroy(e->ev_done[k]);
+            cudaEventDestroy(e->ev_fork[k]); cudaEventDestroy(e->ev_copy[k]); cudaEventDestroy(e->ev_done[k]); cudaEventDestroy(e->ev_cig[k]);
             cudaEventDestroy(e->ev_sub_join[k]);
             cudaStreamDestroy(e->slot_stream[k]);   // [0] is e->stream
         }
@@ -310,7 +355,7 @@ int64_t db200_ed_word_steps(int device, int reset)
 int db200_profile_enable(int device, int on)
 {
     Engine *e = get_engine(device);
-    if (!e) return DB200_ERR_CUDA;
+    if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
     e->profiling = on != 0;
     e->marks.clear();
     e->ev_used = 0;
@@ -322,7 +367,7 @@ int db200_profile_enable(int device, int on)
 int db200_profile_collect(int device, float *ms, int nstages)
 {
     Engine *e = get_engine(device);
-    if (!e) return DB200_ERR_CUDA;
+    if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
     DB200_CUDA_CHECK(cudaDeviceSynchronize());
     for (int i = 0; i < nstages; ++i) ms[i] = 0.f;
     for (size_t i = 1; i < e->marks.size(); ++i) {
@@ -359,7 +404,7 @@ int db200_sw_batch_device(int device, const db200_sw_params *params, const uint8
                           int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, void *stream)
 {
     Engine *e = get_engine(device);
-    if (!e) return DB200_ERR_CUDA;
+    if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
     std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
     cudaStream_t ust = (cudaStream_t)stream;
     // DB200_DEVICE_SUBBATCHES=n cuts the batch into n sub-batches on the engine's slot streams (they share the caller's
@@ -433,8 +478,13 @@ static int sw_finalize_slot(Engine *e, int slot, SwSlot &sl, uint32_t *cigar_buf
             set_error("sw_batch_host: cigar buffer too small");
             return DB200_ERR_CAPACITY;
         }
-        if (total > 0)
+        if (total > 0) {
             DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_buf + cig_written, sl.d_cig, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+            // the slot's io arena is re-carved for the next chunk right after this returns: its H2D (copy stream) must not
+            // overtake this asynchronous read of the old cigar block
+            DB200_CUDA_CHECK(cudaEventRecord(e->ev_cig[slot], st));
+            DB200_CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, e->ev_cig[slot], 0));
+        }
     }
     // entries [c0, c0+n) only: entry c0+n belongs to the next chunk's copy (or is set at the very end)
     if (cigar_off && cig_written) for (int64_t i = 0; i < sl.n; ++i) cigar_off[sl.c0 + i] += cig_written;
@@ -443,13 +493,31 @@ static int sw_finalize_slot(Engine *e, int slot, SwSlot &sl, uint32_t *cigar_buf
     return DB200_OK;
 }
 
+static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
+                              const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
+                              int64_t cigar_cap, int64_t *cigar_off, int32_t *status);
+
 int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
                         const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
                         int64_t cigar_cap, int64_t *cigar_off, int32_t *status)
 {
     Engine *e = get_engine(device);
-    if (!e) return DB200_ERR_CUDA;
+    if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
     std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
+    const int rc = sw_batch_host_body(e, device, params, qbuf, qoff, tbuf, toff, npairs, mask_len, results, cigar_buf, cigar_cap, cigar_off, status);
+    if (rc != DB200_OK) {
+        // chunks of other slots may still be copying into the caller's arrays: nothing of this call is left in flight on return
+        for (int k = 0; k < Engine::NSLOT; ++k) cudaStreamSynchronize(e->slot_stream[k]);
+        cudaStreamSynchronize(e->copy_stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
+                              const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
+                              int64_t cigar_cap, int64_t *cigar_off, int32_t *status)
+{
     if (npairs < 0 || !params || !qoff || !toff || !results) { set_error("sw_batch_host: bad arguments"); return DB200_ERR_ARG; }
     if (cigar_off) cigar_off[0] = 0;
     constexpr int NS = Engine::NSLOT;
@@ -545,7 +613,9 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
         if (rc) return rc;
         DB200_CUDA_CHECK(cudaMemcpyAsync(results + c0, d_res, sizeof(db200_sw_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (status) DB200_CUDA_CHECK(cudaMemcpyAsync(status + c0, d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
-        if (cigar_off) DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_off + c0, d_coff, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+        // n entries only: entry c0 + n is the first one of the next chunk's copy (another stream); the chunk's total travels
+        // through total_word and cigar_off[npairs] is set at the very end
+        if (cigar_off) DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_off + c0, d_coff, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
         DB200_CUDA_CHECK(cudaMemcpyAsync(total_word, d_coff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         DB200_CUDA_CHECK(cudaEventRecord(e->ev_done[slot], st));
         if (timeline) { cudaEventRecord(rec.ev[3], st); rec.host_ms = host_now() - host0; tl.push_back(rec); }
@@ -670,9 +740,13 @@ db200_s_align *db200_ssw_align(const db200_s_profile *prof, const int8_t *ref, i
     int32_t status = 0;
     int64_t coff[2] = {0, 0};
     std::vector<uint32_t> cig((size_t)(qoff[1] + toff[1] + 4));
-    int rc = db200_sw_batch_host(0, &prm, prof->read_ascii.data(), qoff, t.data(), toff, 1, &maskLen, &r, cig.data(), (int64_t)cig.size(),
+    int rc = db200_sw_batch_host(db200_default_device(), &prm, prof->read_ascii.data(), qoff, t.data(), toff, 1, &maskLen, &r, cig.data(), (int64_t)cig.size(),
                                  coff, &status);
-    if (rc != DB200_OK || status != DB200_PAIR_OK) return nullptr; // as ssw_align does on error (ssw.c:803-812)
+    if (rc != DB200_OK || status != DB200_PAIR_OK) {
+        // as ssw_align does on error (ssw.c:803-812): a message on stderr and NULL (the reference wrapper does not check it)
+        fprintf(stderr, "db200_ssw_align: %s\n", rc != DB200_OK ? g_err : "pair rejected (empty sequence, score range or 8-bit overflow with score_size 0)");
+        return nullptr;
+    }
     db200_s_align *a = (db200_s_align *)calloc(1, sizeof(db200_s_align));
     a->score1 = (uint16_t)r.score1; a->score2 = (uint16_t)r.score2;
     a->ref_begin1 = r.ref_begin1; a->ref_end1 = r.ref_end1; a->read_begin1 = r.read_begin1; a->read_end1 = r.read_end1;
@@ -699,7 +773,7 @@ int db200_ed_batch_device(int device, const db200_ed_params *params, const uint8
                           int64_t *d_loc_off, int64_t *loc_total, void *stream)
 {
     Engine *e = get_engine(device);
-    if (!e) return DB200_ERR_CUDA;
+    if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
     std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
     e->arena[0].reset();
     e->aux_set = 0;
@@ -714,7 +788,7 @@ int db200_ed_path_batch_device(int device, const db200_ed_params *params, const 
                                int64_t *path_total, void *stream)
 {
     Engine *e = get_engine(device);
-    if (!e) return DB200_ERR_CUDA;
+    if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
     std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
     if (!params || params->task != DB200_ED_TASK_PATH) { set_error("ed_path_batch: params->task must be DB200_ED_TASK_PATH"); return DB200_ERR_ARG; }
     e->arena[0].reset();
@@ -731,7 +805,7 @@ static int ed_batch_host_impl(int device, const db200_ed_params *params, const u
                               int64_t loc_cap, int64_t *loc_off, uint8_t *path_buf, int64_t path_cap, int64_t *path_off)
 {
     Engine *e = get_engine(device);
-    if (!e) return DB200_ERR_CUDA;
+    if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
     std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
     if (npairs < 0 || !params || !qoff || !toff || !results || !loc_buf || !loc_off) { set_error("ed_batch_host: bad arguments"); return DB200_ERR_ARG; }
     const bool want_path = params->task == DB200_ED_TASK_PATH;
@@ -922,7 +996,7 @@ db200_EdlibAlignResult db200_edlibAlign(const char *query, int queryLength, cons
     const bool want_path = config.task == DB200_ED_TASK_PATH;
     std::vector<uint8_t> path(want_path ? (size_t)queryLength + (size_t)targetLength + 1 : 0);
     int64_t poff[2] = {0, 0};
-    int rc = ed_batch_host_impl(0, &prm, queryLength ? (const uint8_t *)query : &dummy, qoff, targetLength ? (const uint8_t *)target : &dummy,
+    int rc = ed_batch_host_impl(db200_default_device(), &prm, queryLength ? (const uint8_t *)query : &dummy, qoff, targetLength ? (const uint8_t *)target : &dummy,
                                 toff, 1, nullptr, &res, loc.data(), targetLength + 4, loff, want_path ? path.data() : nullptr,
                                 (int64_t)path.size(), want_path ? poff : nullptr);
     const int32_t path_len = (int32_t)(poff[1] - poff[0]);

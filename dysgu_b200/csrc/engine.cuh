@@ -63,6 +63,7 @@ struct Engine {
     int64_t *d_sub_words = nullptr;      // [NSUB_MAX + 1] cigar cursor between sub-batches; [NSUB_MAX + 1] Myers word steps evaluated
     cudaEvent_t ev_copy[NSLOT] = {};
     cudaEvent_t ev_done[NSLOT] = {};
+    cudaEvent_t ev_cig[NSLOT] = {};      // cigar block of the slot's previous chunk has left its io arena
     Arena arena[NSLOT];                  // compute workspace (one per in-flight chunk)
     Arena io[NSLOT];                     // device copies of host inputs / outputs (one per in-flight chunk)
     int64_t launches = 0;
@@ -81,6 +82,7 @@ struct Engine {
 };
 
 Engine *get_engine(int device);  // nullptr + error set on failure
+bool forked_after_cuda();        // this process was forked after its parent initialised CUDA (no GPU use possible)
 
 inline void count_launch(Engine *e, int n = 1) { e->launches += n; }
 

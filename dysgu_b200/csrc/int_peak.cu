@@ -15,13 +15,15 @@
 #define ITERS 4096
 
 enum Op { OP_VIADDMNMX_RELU = 0, OP_VIMNMX3_RELU, OP_VIMNMX, OP_VIADD16X2, OP_PRMT, OP_LOP3, OP_IADD3, OP_IMAD,
-          OP_SHF, OP_ADD64, OP_MIX_DPX_IMAD, OP_MIX_SW, OP_COUNT };
+          OP_SHF, OP_ADD64, OP_MIX_DPX_IMAD, OP_MIX_SW, OP_MYERS, OP_MYERS_ILP2, OP_COUNT };
 
 static const char *op_names[OP_COUNT] = {"viaddmnmx_s16x2_relu", "vimnmx3_s16x2_relu", "vimnmx_s16x2", "viadd_16x2", "prmt",
                                          "lop3", "iadd3", "imad", "shf_funnel", "add_u64", "mix_dpx_imad",
-                                         "mix_sw_cell"};
+                                         "mix_sw_cell", "myers_word_step", "myers_word_step_ilp2"};
 // lane-ops issued per loop iteration and chain (for the throughput figure)
-static const int op_count_per_iter[OP_COUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 7};
+// (myers_word_step*: ONE unit per iteration and chain = one 64-row Myers/Hyyro word step, edlib.cpp:411-443, with all
+//  operands in registers - the figure is word steps per second, the roof of the edit-distance kernels)
+static const int op_count_per_iter[OP_COUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 7, 1, 1};
 
 template <int OP>
 __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed)
@@ -36,6 +38,12 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed)
         w[c] = ((unsigned long long)a[c] << 32) | b[c];
     }
     const uint32_t k1 = seed | 0x00010001u, k2 = (seed >> 3) | 0x00030002u;
+    uint32_t carry_p[CHAINS], carry_m[CHAINS];
+    int score = 0;
+#pragma unroll
+    uint64_t eqv[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) { carry_p[c] = 0; carry_m[c] = 0; eqv[c] = (uint64_t)(tid * 2654435761u + c * 40503u) * 0x9E3779B97F4A7C15ull; }
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
@@ -45,7 +53,7 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed)
             else if (OP == OP_VIMNMX) a[c] = __vmaxs2(a[c], b[c] ^ k1);
             else if (OP == OP_VIADD16X2) a[c] = __vadd2(a[c], k1);
             else if (OP == OP_PRMT) a[c] = __byte_perm(a[c], b[c], 0x5410 + (k1 & 0x2222));
-            else if (OP == OP_LOP3) a[c] = (a[c] & k1) ^ b[c];
+            else if (OP == OP_LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[c]) : "r"(b[c]), "r"(k1));   // one 3-input LOP3
             else if (OP == OP_IADD3) a[c] = a[c] + b[c] + k1;
             else if (OP == OP_IMAD) a[c] = a[c] * k1 + b[c];
             else if (OP == OP_SHF) a[c] = __funnelshift_l(a[c], b[c], k1 & 31);
@@ -53,6 +61,28 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed)
             else if (OP == OP_MIX_DPX_IMAD) {
                 a[c] = __viaddmax_s16x2_relu(a[c], k1, b[c]);
                 b[c] = b[c] * k2 + k1;
+            } else if (OP == OP_MYERS || OP == OP_MYERS_ILP2) {
+                // one Myers/Hyyro word step on a 64-bit word (the kernels' myers_word, ed_kernels.cuh): Pv = w[c], Mv = (a, b),
+                // the match vector is a rotating register value, the horizontal carries travel from chain to chain like they
+                // travel from word to word of a column.  CHAINS independent words per thread (8: what a thread of the
+                // multi-word kernels holds); the ILP2 variant runs two independent columns of four words.
+                uint64_t Pv = w[c], Mv = ((uint64_t)a[c] << 32) | b[c];
+                uint64_t Eq = eqv[c] ^ (uint64_t)(uint32_t)it;   // a match vector that changes per column at the cost of one LOP3
+                const int src = (OP == OP_MYERS_ILP2) ? ((c & 3) == 0 ? -1 : c - 1) : (c == 0 ? -1 : c - 1);
+                const uint32_t hp = src < 0 ? 1u : carry_p[src], hm = src < 0 ? 0u : carry_m[src];
+                const uint64_t Xv = Eq | Mv;
+                Eq |= (uint64_t)hm;
+                const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                uint64_t Ph = Mv | ~(Xh | Pv);
+                uint64_t Mh = Pv & Xh;
+                carry_p[c] = (uint32_t)(Ph >> 63);
+                carry_m[c] = (uint32_t)(Mh >> 63);
+                Ph = (Ph << 1) | (uint64_t)hp;
+                Mh = (Mh << 1) | (uint64_t)hm;
+                Pv = Mh | ~(Xv | Ph);
+                Mv = Ph & Xv;
+                w[c] = Pv; a[c] = (uint32_t)(Mv >> 32); b[c] = (uint32_t)Mv;
+                score += (int)carry_p[c] - (int)carry_m[c];
             } else if (OP == OP_MIX_SW) {
                 // the op mix of one packed Smith-Waterman cell pair (see sw_kernels.cuh)
                 uint32_t u = __viaddmax_s16x2_relu(b[c], k1, a[c]);
@@ -67,7 +97,8 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed)
     }
     uint32_t acc = 0;
 #pragma unroll
-    for (int c = 0; c < CHAINS; ++c) acc ^= a[c] ^ b[c] ^ (uint32_t)w[c] ^ (uint32_t)(w[c] >> 32);
+    for (int c = 0; c < CHAINS; ++c) acc ^= a[c] ^ b[c] ^ (uint32_t)w[c] ^ (uint32_t)(w[c] >> 32) ^ carry_p[c] ^ carry_m[c];
+    acc ^= (uint32_t)score;
     if (acc == 0x12345678u) out[tid] = acc; // keep the chains alive
 }
 
@@ -113,6 +144,8 @@ int main()
     r[9] = run_one<9>(d_out, prop.multiProcessorCount, prop.clockRate);
     r[10] = run_one<10>(d_out, prop.multiProcessorCount, prop.clockRate);
     r[11] = run_one<11>(d_out, prop.multiProcessorCount, prop.clockRate);
+    r[12] = run_one<12>(d_out, prop.multiProcessorCount, prop.clockRate);
+    r[13] = run_one<13>(d_out, prop.multiProcessorCount, prop.clockRate);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d, \"lane_ops_per_s\": {", prop.name, prop.multiProcessorCount,
            prop.clockRate);
     for (int i = 0; i < OP_COUNT; ++i) printf("%s\"%s\": %.4e", i ? ", " : "", op_names[i], r[i]);

@@ -915,6 +915,10 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         const int64_t *total_src = link ? link->d_end : (d_cigar_off ? d_cigar_off : cig_off_tmp) + npairs;
         DB200_CUDA_CHECK(cudaMemcpyAsync(cigar_total, total_src, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         DB200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (d_cigar_buf && *cigar_total > cigar_cap) {   // the gather kernel skipped what did not fit (overflow flag 3)
+            set_error("sw_batch_device: cigar buffer too small (%lld ops, capacity %lld)", (long long)*cigar_total, (long long)cigar_cap);
+            return DB200_ERR_CAPACITY;
+        }
     }
     return DB200_OK;
 }

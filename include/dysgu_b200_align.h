@@ -14,13 +14,21 @@
  *   - *_host entry points take host pointers and perform H2D / compute / D2H internally.
  *   - *_device entry points take device pointers on `device` and enqueue everything on `stream`
  *     (a cudaStream_t passed as void*; NULL = the legacy default stream); outputs are device
- *     pointers too.  They return after enqueueing unless stated otherwise.
+ *     pointers too.  The SW device call returns after enqueueing unless cigar_total is requested; the edit-distance device
+ *     calls synchronise the stream once per call (the size of the match-vector pool is read back before the scoring
+ *     kernels are enqueued) and again when loc_total / path_total are requested.
  *   - Threads: the batch entry points may be called from several host threads (the reference's cores are
  *     reentrant and edlib.pyx:129 releases the GIL); calls on the same device run one after the other
  *     (a per-device lock held for the whole *_host call and for the enqueue of a *_device call), calls
  *     on different devices run concurrently.  Results of a *_device call must have been consumed
  *     (or the stream synchronised) before the next call on that device - the workspace is reused.
- *     A ticket queue belongs to one thread.  After fork() the child creates its own engine lazily.
+ *     A ticket queue belongs to one thread.
+ *   - fork(): a child of a process that has not yet called a compute / init / device-count entry point creates its own
+ *     engine lazily.  A child forked AFTER the parent initialised CUDA cannot use the GPU (a CUDA restriction): every
+ *     compute entry point then fails with DB200_ERR_FORKED and a message saying so (db200_forked_after_init() == 1).
+ *     That is the order `dysgu call -p N` produces (re_map in the parent, cluster.pyx:475-478, then the Pool of
+ *     merge_svs.pyx:396); dysgu_b200.patch keeps that pool's work in the parent as device batches and
+ *     dysgu_b200/server.py serves forked children from the parent's engine.
  *   - All functions return DB200_OK (0) or a negative DB200_ERR_* code; db200_last_error() gives
  *     a thread-local message.  There is no CPU fallback: without a CUDA device every compute
  *     entry point fails with DB200_ERR_CUDA.
@@ -40,6 +48,7 @@ extern "C" {
 #define DB200_ERR_NOMEM -3     /* device or host allocation failed */
 #define DB200_ERR_CAPACITY -4  /* caller-provided output buffer too small */
 #define DB200_ERR_INTERNAL -5
+#define DB200_ERR_FORKED -6    /* the process was fork()ed after its parent initialised CUDA: no GPU use is possible here */
 
 /* per-pair status values written to the status arrays */
 #define DB200_PAIR_OK 0
@@ -53,8 +62,13 @@ extern "C" {
 /* engine                                                                                       */
 /* ------------------------------------------------------------------------------------------ */
 int db200_device_count(void);
-/* Creates (lazily, per process - safe after fork) the engine state for `device`. */
+/* Creates (lazily, per process) the engine state for `device`; see the fork() note above. */
 int db200_init(int device);
+/* 1 if this process was fork()ed after its parent initialised CUDA through this library (compute calls fail with DB200_ERR_FORKED). */
+int db200_forked_after_init(void);
+/* Device used by the legacy single-pair entry points (their reference signatures carry no device): the environment
+ * variable DB200_DEVICE, else LOCAL_RANK, else 0. */
+int db200_default_device(void);
 void db200_shutdown(void);
 const char *db200_last_error(void);
 const char *db200_version(void);
@@ -127,7 +141,8 @@ int db200_sw_batch_host(int device, const db200_sw_params *params,
  * known to the caller, needed to size the workspace without a device round trip (0 disables
  * the column-tiled kernel, i.e. targets longer than 1024 are then reported as unsupported).
  * Everything is enqueued on `stream`; the call only synchronises when cigar_total is non-NULL
- * (it then receives the number of cigar ops).
+ * (it then receives the number of cigar ops, and a cigar_cap that was too small is reported as
+ * DB200_ERR_CAPACITY; without cigar_total an overflowing pair keeps its cigar_len but its ops are not written).
  */
 int db200_sw_batch_device(int device, const db200_sw_params *params,
                           const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
@@ -226,8 +241,8 @@ int db200_ed_path_batch_host(int device, const db200_ed_params *params,
                              db200_ed_result *results, int32_t *loc_buf, int64_t loc_cap, int64_t *loc_off,
                              uint8_t *path_buf, int64_t path_cap, int64_t *path_off);
 
-/* Device-resident variant; synchronises only when loc_total or path_total is non-NULL (they receive the totals, and
- * capacity / internal errors are only reported then). */
+/* Device-resident variant; synchronises once for the match-vector pool size and again when loc_total or path_total is
+ * non-NULL (they receive the totals, and capacity / internal errors are only reported then). */
 int db200_ed_path_batch_device(int device, const db200_ed_params *params,
                                const uint8_t *d_qbuf, const int64_t *d_qoff, int64_t q_bytes,
                                const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,

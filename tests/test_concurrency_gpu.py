@@ -79,3 +79,71 @@ FORK_SCRIPT = textwrap.dedent("""
 def test_forked_pool_workers_create_their_own_engine():
     r = subprocess.run([sys.executable, "-c", FORK_SCRIPT % ROOT], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "fork ok" in r.stdout, (r.stdout, r.stderr[-2000:])
+
+
+# The order `dysgu call -p N` really produces: the PARENT aligns first (re_map.remap_soft_clips, cluster.pyx:475-478), then
+# forks the pool of merge_svs.pyx:396 whose workers align again.  CUDA cannot be used in such children; the parent's
+# alignment server (dysgu_b200/server.py) runs their batches on the parent's engine.
+FORK_AFTER_INIT_SCRIPT = textwrap.dedent("""
+    import multiprocessing as mp, os, sys
+    sys.path.insert(0, %r)
+    from dysgu_b200.scikitbio import StripedSmithWaterman
+    from dysgu_b200.edlib import align
+    from dysgu_b200 import _lib, batch, workloads
+
+    def work(i):
+        a = StripedSmithWaterman("ACGTTGCAACGTACGTTTGACCA", match_score=2, mismatch_score=-8, gap_open_penalty=6, gap_extend_penalty=1)("ttgcaacgtaggtttga")
+        e = align("ACGTTGCA", "TTACGTAGCATT", "HW", "locations")
+        q, t, prm = workloads.remap_windows(300, seed=40 + i)
+        r = batch.sw_align_batch(q, t, **prm)
+        return (a.optimal_alignment_score, a.cigar, e["editDistance"], e["locations"], int(r.fixed.sum()), int(r.cigar.sum()),
+                int(_lib.lib().db200_forked_after_init()), os.getpid())
+
+    if __name__ == "__main__":
+        q, t, prm = workloads.remap_windows(2000, seed=1)
+        batch.sw_align_batch(q, t, **prm)                     # the parent touches the GPU first
+        want = []
+        for i in range(4):
+            q, t, prm = workloads.remap_windows(300, seed=40 + i)
+            r = batch.sw_align_batch(q, t, **prm)
+            want.append((int(r.fixed.sum()), int(r.cigar.sum())))
+        with mp.get_context("fork").Pool(2) as pool:
+            res = pool.map(work, range(4))
+        for i, r in enumerate(res):
+            assert r[:4] == (24, "17M", 1, [(2, 9)]), r
+            assert r[4:6] == want[i], (r, want[i])
+            assert r[6] == 1 and r[7] != os.getpid(), r          # really a forked child that cannot use CUDA itself
+        print("fork after init ok")
+""")
+
+
+def test_pool_forked_after_the_parent_used_the_gpu_is_served_by_the_parent():
+    r = subprocess.run([sys.executable, "-c", FORK_AFTER_INIT_SCRIPT % ROOT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "fork after init ok" in r.stdout, (r.stdout, r.stderr[-3000:])
+
+
+FORK_NO_SERVER_SCRIPT = textwrap.dedent("""
+    import multiprocessing as mp, sys
+    sys.path.insert(0, %r)
+    from dysgu_b200 import _lib, batch
+
+    def work(i):
+        try:
+            batch.sw_align_batch([b"ACGTACGTACGT"], [b"ACGTACGTACGT"])
+        except _lib.AlignEngineError as exc:
+            return str(exc)
+        return "no error"
+
+    if __name__ == "__main__":
+        batch.sw_align_batch([b"ACGTACGTACGT"], [b"ACGTACGTACGT"])
+        with mp.get_context("fork").Pool(1) as pool:
+            msg = pool.map(work, [0])[0]
+        assert "fork()ed after its parent initialised CUDA" in msg and "code -6" in msg, msg
+        print("clear error ok")
+""")
+
+
+def test_without_the_server_a_forked_child_gets_a_clear_error():
+    env = dict(os.environ, DB200_NO_SERVER="1")
+    r = subprocess.run([sys.executable, "-c", FORK_NO_SERVER_SCRIPT % ROOT], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "clear error ok" in r.stdout, (r.stdout, r.stderr[-3000:])

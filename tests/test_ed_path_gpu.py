@@ -20,14 +20,10 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def blocks():
-    """The vectors the device suite runs.  The file also holds a 17 kb pair (beyond the warp kernel's 256 query words) that
-    only the CPU test of the shared path code runs (tests/test_ed_path_host.py): queries above 10 kb - the length dysgu
-    truncates its sequences to - take kernel configurations this suite has not been run with on a GPU yet."""
+    """The vectors the device suite runs: all of them, including the 17 kb pair that takes the global-scratch instance of
+    the thread kernel (beyond the warp kernel's 256 query words)."""
     with open(os.path.join(G, "ed_path.json")) as f:
-        out = json.load(f)
-    for b in out:
-        b["cases"] = [c for c in b["cases"] if len(c["query"]) <= 10000]
-    return out
+        return json.load(f)
 
 
 def test_path_batches_match_the_reference():

@@ -1,10 +1,8 @@
-"""NOT COLLECTED (the file name does not match test_*.py): the GPU test to enable first next round - rename it to
-test_long_queries_gpu.py once it has passed on a B200.
-
-Edit-distance queries above 10,240 symbols run Myers configurations (192, 256, 512, 1024 words per pair) that no GPU test
-has exercised yet, and for task "path" queries above 16,384 symbols take the global-scratch instance of the thread
-kernel.  Checker: the scalar oracle (distance, locations, edit operations).
-"""
+"""GPU: edit-distance queries above 10,240 symbols - the 192 / 256 / 512 / 1024-word Myers configurations and, for task
+"path", the global-scratch instance of the thread kernel (queries above 16,384 symbols).  dysgu reaches this range through
+filter_normals.clip_align_matches (filter_normals.py:676-684: read clips of 16 kb and more go to edlib HW); edlib itself
+handles any length (edlib.cpp:193-212).  Checker: the scalar oracle (distance, locations, edit operations).
+First run on a B200 in round 2 (profiles/r02_pytest_gpu.txt)."""
 import random
 
 import numpy as np
@@ -48,3 +46,24 @@ def test_long_queries_all_tasks(mode):
                 ops = ref.path[ref.path_off[i]:ref.path_off[i] + ref.path_len[i]]
                 got = r.alignment(i)
                 assert np.array_equal(got if got is not None else np.zeros(0, np.uint8), ops), (mode, i, len(qs[i]))
+
+
+def test_query_of_65536_symbols():
+    """The longest query the product accepts (1024 words): NW and HW distance + locations against the scalar oracle."""
+    rng = random.Random(65536)
+    q = pairgen.rand_dna(rng, 65536)
+    t = pairgen.mutate(rng, q[300:], 0.01, 0.01, 0.01)
+    t_hw = pairgen.rand_dna(rng, 500) + pairgen.mutate(rng, q, 0.004, 0.004, 0.004) + pairgen.rand_dna(rng, 700)
+    qs, ts = [q.encode(), q.encode()], [t.encode(), t_hw.encode()]
+    for mode in ("NW", "HW"):
+        ref = O.oracle_ed(qs, ts, mode, "locations")
+        r = batch.ed_align_batch(qs, ts, mode=mode, task="locations")
+        assert np.array_equal(r.fixed, ref.fixed), mode
+        assert np.array_equal(r.loc, ref.loc) and np.array_equal(r.loc_off, ref.loc_off), mode
+
+
+def test_query_above_65536_is_refused_not_wrong():
+    """Documented deviation: beyond 65,536 query symbols the status is EDLIB_STATUS_ERROR, never a number."""
+    q = b"ACGT" * 16400   # 65,600
+    r = batch.ed_align_batch([q], [q], mode="NW", task="distance")
+    assert int(r.fixed[0, 0]) == 1
