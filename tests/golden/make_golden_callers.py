@@ -37,6 +37,50 @@ def ref_check_contig_match(a, b, diffs=8, ol_length=21):
     return 1 if not (expected - s + total) > diffs else 0
 
 
+def ref_merge_align_regions(locations):
+    """re_map.merge_align_regions restated for the generator only (re_map.py:85-111): neighbouring edlib hits whose start and
+    end both lie within 10 bp of the block being grown are folded into it; of the blocks, the one whose length is closest
+    to 1000 is kept.  Where the reference checkout exists the real function is used and this restatement is checked
+    against it."""
+    real = _real_merge_align_regions()
+    mine = _restated_merge_align_regions(locations)
+    if real is not None:
+        assert real([tuple(x) for x in locations]) == mine, (locations, mine)
+    return mine
+
+
+def _restated_merge_align_regions(locations):
+    if len(locations) <= 1:
+        return locations
+    blocks = []
+    for s, e in locations:
+        if blocks and abs(s - blocks[-1][0]) < 10 and abs(e - blocks[-1][1]) < 10:
+            blocks[-1][1] = e
+        else:
+            blocks.append([s, e])
+    best = min(range(len(blocks)), key=lambda i: (abs(blocks[i][1] - blocks[i][0] - 1000), i))
+    return [blocks[best]]
+
+
+_REAL = []
+
+
+def _real_merge_align_regions():
+    """The function object from the reference's own re_map.py (source parsed where it lies; nothing is copied)."""
+    if not _REAL:
+        path = os.path.join(os.environ.get("DYSGU_REFERENCE", "/root/reference"), "dysgu", "re_map.py")
+        fn = None
+        if os.path.exists(path):
+            import ast
+            tree = ast.parse(open(path).read())
+            node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "merge_align_regions")
+            scope = {}
+            exec(compile(ast.Module([node], []), path, "exec"), scope)
+            fn = scope["merge_align_regions"]
+        _REAL.append(fn)
+    return _REAL[0]
+
+
 def revcomp(s):
     return s.translate(str.maketrans("ACGTacgt", "TGCAtgca"))[::-1]
 
@@ -124,9 +168,7 @@ def main():
         rec = {"adjacent_match": adjm, "locs": [], "aln": None}
         if not adjm:
             el = edlib_align(clip.upper(), w, mode="HW", task="locations")
-            sys.path.insert(0, ROOT)
-            from dysgu_b200.callers import merge_align_regions
-            locs = merge_align_regions(el["locations"])
+            locs = ref_merge_align_regions(el["locations"])
             rec["locs"] = locs
             if locs:
                 l0, l1 = locs[0]
