@@ -57,6 +57,12 @@ def lib():
     L.db200_sw_batch_device.argtypes = [C.c_int, C.POINTER(SwParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.db200_sw_batch_host_multi.restype = C.c_int
+    L.db200_sw_batch_host_multi.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SwParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.db200_ed_batch_host_multi.restype = C.c_int
+    L.db200_ed_batch_host_multi.argtypes = [C.c_void_p, C.c_int32, C.POINTER(EdParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     if hasattr(L, "db200_ed_batch_host"):
         L.db200_ed_batch_host.restype = C.c_int
         L.db200_ed_batch_host.argtypes = [C.c_int, C.POINTER(EdParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

@@ -146,8 +146,10 @@ class SwResults:
 
 
 def sw_align_batch(queries, targets, match=2, mismatch=-3, gap_open=5, gap_extend=2, score_size=2, flag=1, filters=0,
-                   filterd=0, mask_len=None, matrix=None, device=None, want_cigar=True) -> SwResults:
-    """Align queries[i] (profiled sequence) against targets[i]; semantics of ssw_init + ssw_align per pair."""
+                   filterd=0, mask_len=None, matrix=None, device=None, want_cigar=True, devices=None) -> SwResults:
+    """Align queries[i] (profiled sequence) against targets[i]; semantics of ssw_init + ssw_align per pair.
+    `devices` (a list of device ids) spreads the batch over several GPUs through db200_sw_batch_host_multi: contiguous
+    ranges of equal work, one host thread per device, results in pair order (`SwResults.pairs_per_device`)."""
     q, t = _as_batch(queries), _as_batch(targets)
     n = len(q)
     if len(t) != n:
@@ -155,7 +157,7 @@ def sw_align_batch(queries, targets, match=2, mismatch=-3, gap_open=5, gap_exten
     if _server.should_route():   # forked after the parent initialised CUDA: the parent's engine runs the batch
         return SwResults(*_server.remote("sw", (q, t), dict(match=match, mismatch=mismatch, gap_open=gap_open, gap_extend=gap_extend,
                                                             score_size=score_size, flag=flag, filters=filters, filterd=filterd,
-                                                            mask_len=mask_len, matrix=matrix, want_cigar=want_cigar)))
+                                                            mask_len=mask_len, matrix=matrix, want_cigar=want_cigar, devices=devices)))
     _server.ensure_started()
     L = _lib.lib()
     prm = _lib.SwParams()
@@ -174,6 +176,17 @@ def sw_align_batch(queries, targets, match=2, mismatch=-3, gap_open=5, gap_exten
     cigar = np.zeros(max(cap, 1), dtype=np.uint32)
     qbuf = q.buf if q.buf.size else np.zeros(1, np.uint8)
     tbuf = t.buf if t.buf.size else np.zeros(1, np.uint8)
+    if devices is not None and len(devices) > 1:
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        per_dev = np.zeros(len(devs), dtype=np.int64)
+        rc = L.db200_sw_batch_host_multi(_ptr(devs), len(devs), C.byref(prm), _ptr(qbuf), _ptr(q.off), _ptr(tbuf), _ptr(t.off), n, _ptr(ml),
+                                         _ptr(fixed), _ptr(cigar) if want_cigar else None, cap, _ptr(coff), _ptr(status), _ptr(per_dev))
+        _lib.check(rc, "db200_sw_batch_host_multi")
+        res = SwResults(fixed, cigar[:coff[n]] if want_cigar else cigar[:0], coff, status)
+        res.pairs_per_device = per_dev
+        return res
+    if devices is not None and len(devices) == 1:
+        device = int(devices[0])
     rc = L.db200_sw_batch_host(default_device() if device is None else device, C.byref(prm), _ptr(qbuf), _ptr(q.off), _ptr(tbuf),
                                _ptr(t.off), n, _ptr(ml), _ptr(fixed), _ptr(cigar) if want_cigar else None, cap, _ptr(coff),
                                _ptr(status))
@@ -249,14 +262,15 @@ def ops_to_cigar(ops, extended=True) -> str:
     return "".join("%d%s" % (e - b, chr(letters[b])) for b, e in zip(starts, ends))
 
 
-def ed_align_batch(queries, targets, mode="NW", task="distance", k=-1, additional_equalities=None, device=None) -> EdResults:
-    """edlib.align semantics per pair (edlib.pyx:57-156): tasks 'distance', 'locations' and 'path'."""
+def ed_align_batch(queries, targets, mode="NW", task="distance", k=-1, additional_equalities=None, device=None, devices=None) -> EdResults:
+    """edlib.align semantics per pair (edlib.pyx:57-156): tasks 'distance', 'locations' and 'path'.  `devices`: as in
+    sw_align_batch (db200_ed_batch_host_multi; tasks 'distance' and 'locations')."""
     q, t = _as_batch(queries), _as_batch(targets)
     n = len(q)
     if len(t) != n:
         raise ValueError("queries and targets differ in length")
     if _server.should_route():
-        return EdResults(*_server.remote("ed", (q, t), dict(mode=mode, task=task, k=k, additional_equalities=additional_equalities)))
+        return EdResults(*_server.remote("ed", (q, t), dict(mode=mode, task=task, k=k, additional_equalities=additional_equalities, devices=devices)))
     _server.ensure_started()
     L = _lib.lib()
     if not hasattr(L, "db200_ed_batch_host"):
@@ -290,6 +304,19 @@ def ed_align_batch(queries, targets, mode="NW", task="distance", k=-1, additiona
                                         pcap, _ptr(poff))
         _lib.check(rc, "db200_ed_path_batch_host")
         return EdResults(fixed, loc[:loff[n]], loff, path[:poff[n]], poff)
+    if devices is not None and len(devices) > 1:
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        per_dev = np.zeros(len(devs), dtype=np.int64)
+        cap += 16 * len(devs)
+        loc = np.zeros((cap, 2), dtype=np.int32)
+        rc = L.db200_ed_batch_host_multi(_ptr(devs), len(devs), C.byref(prm), _ptr(qbuf), _ptr(q.off), _ptr(tbuf), _ptr(t.off), n, _ptr(karr),
+                                         _ptr(fixed), _ptr(loc), cap, _ptr(loff), _ptr(per_dev))
+        _lib.check(rc, "db200_ed_batch_host_multi")
+        res = EdResults(fixed, loc[:loff[n]], loff)
+        res.pairs_per_device = per_dev
+        return res
+    if devices is not None and len(devices) == 1:
+        device = int(devices[0])
     rc = L.db200_ed_batch_host(default_device() if device is None else device, C.byref(prm), _ptr(qbuf), _ptr(q.off), _ptr(tbuf),
                                _ptr(t.off), n, _ptr(karr), _ptr(fixed), _ptr(loc), cap, _ptr(loff))
     _lib.check(rc, "db200_ed_batch_host")

@@ -256,9 +256,16 @@ struct EdBandArgs {
     unsigned long long *wsteps;  // word steps evaluated (statistics)
 };
 
+// Columns whose target symbols and match-vector words are fetched together before any of them is stepped: the loads of
+// a batch are independent (the window position is a function of the column index alone), so their latencies overlap
+// instead of adding up once per column - ncu of the one-column version showed 12.8 of 16.7 cycles per issued
+// instruction waiting on the long scoreboard (profiles/r02_ed_banded_nw_before.txt).
+__host__ __device__ constexpr int ed_band_cols(int wb) { return wb <= 3 ? 8 : (wb <= 5 ? 4 : 2); }
+
 template <int WB, bool LAST>
 __global__ void __launch_bounds__(128) ed_banded_nw_kernel(EdBandArgs a)
 {
+    constexpr int CB = ed_band_cols(WB);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_first = a.seg_count[a.round];
     const int n_carry = a.carry_count ? *a.carry_count : 0;
@@ -281,10 +288,24 @@ __global__ void __launch_bounds__(128) ed_banded_nw_kernel(EdBandArgs a)
     const int wb_max = W - nwin;
     bool failed = false;
     int jdone = n;
-    for (int j = 0; j < n; ++j) {
-        if (!full) {
-            const int want = min(max(j - H, 0) >> 6, wb_max);
-            if (want > wb0) {                     // the window moves down by one word
+    for (int j0 = 0; j0 < n && !failed; j0 += CB) {
+        // ---- fetch the batch: symbols, then the window's match-vector words of every column ----------------------
+        uint64_t eq[CB][WB];
+        int wbs[CB];
+#pragma unroll
+        for (int b = 0; b < CB; ++b) {
+            const int j = min(j0 + b, n - 1);
+            wbs[b] = full ? 0 : min(max(j - H, 0) >> 6, wb_max);
+            const uint64_t *row = peq + (int64_t)tc[j] * W + wbs[b];
+#pragma unroll
+            for (int w = 0; w < WB; ++w) eq[b][w] = (w < nwin) ? __ldg(row + w) : 0ull;
+        }
+        // ---- step the columns --------------------------------------------------------------------------------------
+#pragma unroll
+        for (int b = 0; b < CB; ++b) {
+            const int j = j0 + b;
+            if (j >= n || failed) break;
+            if (wbs[b] > wb0) {                   // the window moves down by one word
                 const int old_b = 64 * (wb0 + nwin) - 1;
 #pragma unroll
                 for (int w = 0; w + 1 < WB; ++w) { Pv[w] = Pv[w + 1]; Mv[w] = Mv[w + 1]; }
@@ -292,40 +313,42 @@ __global__ void __launch_bounds__(128) ed_banded_nw_kernel(EdBandArgs a)
                 ++wb0;
                 score += min(64 * (wb0 + nwin), m) - 1 - old_b;
             }
-        }
-        const int sym = tc[j];
-        const uint64_t *row = peq + (int64_t)sym * W + wb0;
-        uint32_t hp = 1u, hm = 0u;
-        uint64_t Ph_l = 0, Mh_l = 0;
+            uint32_t hp = 1u, hm = 0u;
+            uint64_t Ph_l = 0, Mh_l = 0;
 #pragma unroll
-        for (int w = 0; w < WB; ++w) {
-            if (w < nwin) {
-                uint32_t op, om;
-                myers_word(Pv[w], Mv[w], __ldg(row + w), hp, hm, op, om, Ph_l, Mh_l);
-                hp = op; hm = om;
-            }
-        }
-        const int bit = (wb0 + nwin == W) ? ((m - 1) & 63) : 63;
-        score += (int)((Ph_l >> bit) & 1ull) - (int)((Mh_l >> bit) & 1ull);
-        // Ukkonen cut-off, once per 64 columns: every path through column j costs at least the value on the corner's
-        // diagonal (row j - (n - m)): vertical neighbours differ by at most 1 and a detour of r rows costs r again on
-        // the way back.  Once that value exceeds c the round cannot succeed.
-        if (!full && (j & 63) == 63) {
-            const int i0 = j - (n - m);
-            if (i0 >= 0) {
-                int v = score;
-#pragma unroll
-                for (int w = 0; w < WB; ++w) {
-                    const int lo = i0 + 1 - 64 * (wb0 + w);          // rows of this word above the diagonal row are excluded
-                    uint64_t mask = lo <= 0 ? ~0ull : (lo >= 64 ? 0ull : (~0ull << lo));
-                    if (w == WB - 1 && bit != 63) mask &= (2ull << bit) - 1ull;
-                    v -= __popcll(Pv[w] & mask) - __popcll(Mv[w] & mask);
+            for (int w = 0; w < WB; ++w) {
+                if (w < nwin) {
+                    uint32_t op, om;
+                    myers_word(Pv[w], Mv[w], eq[b][w], hp, hm, op, om, Ph_l, Mh_l);
+                    hp = op; hm = om;
                 }
-                if (v > c) { score = v; failed = true; jdone = j + 1; break; }
+            }
+            const int bit = (wb0 + nwin == W) ? ((m - 1) & 63) : 63;
+            score += (int)((Ph_l >> bit) & 1ull) - (int)((Mh_l >> bit) & 1ull);
+            // Ukkonen cut-off, once per 64 columns: every path through column j costs at least the value on the corner's
+            // diagonal (row j - (n - m)): vertical neighbours differ by at most 1 and a detour of r rows costs r again on
+            // the way back.  Once that value exceeds c the round cannot succeed.
+            if (!full && (j & 63) == 63) {
+                const int i0 = j - (n - m);
+                if (i0 >= 0) {
+                    int v = score;
+#pragma unroll
+                    for (int w = 0; w < WB; ++w) {
+                        const int lo = i0 + 1 - 64 * (wb0 + w);          // rows of this word above the diagonal row are excluded
+                        uint64_t mask = lo <= 0 ? ~0ull : (lo >= 64 ? 0ull : (~0ull << lo));
+                        if (w == WB - 1 && bit != 63) mask &= (2ull << bit) - 1ull;
+                        v -= __popcll(Pv[w] & mask) - __popcll(Mv[w] & mask);
+                    }
+                    if (v > c) { score = v; failed = true; jdone = j + 1; }
+                }
             }
         }
     }
-    atomicAdd(a.wsteps, (unsigned long long)jdone * (unsigned long long)nwin);
+    {   // statistics: one atomic per converged group of threads instead of one per pair
+        const unsigned mask = __activemask();
+        const unsigned total = __reduce_add_sync(mask, (unsigned)jdone * (unsigned)nwin);
+        if ((threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(a.wsteps, (unsigned long long)total);
+    }
     if (full || (!failed && score <= c) || (pr.k >= 0 && c >= pr.k)) {
         a.nw_score[pair] = score;                 // exact, or known to exceed k (ed_count_kernel turns that into -1)
     } else if (!LAST) {

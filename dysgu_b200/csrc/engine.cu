@@ -520,6 +520,66 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
 {
     if (npairs < 0 || !params || !qoff || !toff || !results) { set_error("sw_batch_host: bad arguments"); return DB200_ERR_ARG; }
     if (cigar_off) cigar_off[0] = 0;
+    // ---- latency path: a few short pairs run in one launch (sw_small.cuh); what it cannot hold goes through the pipeline below
+    static thread_local bool small_inner = false;
+    if (!small_inner && npairs > 0 && npairs <= 64 && qbuf && tbuf) {
+        std::vector<int32_t> st_local;
+        int32_t *st = status;
+        if (!st) { st_local.assign((size_t)npairs, 0); st = st_local.data(); }
+        std::vector<int64_t> coff_local;
+        int64_t *coff = cigar_off;
+        if (!coff) { coff_local.assign((size_t)npairs + 1, 0); coff = coff_local.data(); }
+        int handled = 0;
+        int rc = sw_small_host(e, params, qbuf, qoff, tbuf, toff, npairs, mask_len, results, cigar_buf, cigar_cap, coff, st, &handled);
+        if (rc) return rc;
+        if (handled) {
+            std::vector<int64_t> redo;
+            for (int64_t i = 0; i < npairs; ++i) if (st[i] == 100) redo.push_back(i);   // SW_SMALL_FALLBACK
+            if (redo.empty()) return DB200_OK;
+            // the pairs the small kernel could not hold: one call of the batch pipeline, results spliced back in pair order
+            std::vector<uint8_t> qb, tb;
+            std::vector<int64_t> qo(1, 0), to(1, 0);
+            std::vector<int32_t> ml;
+            for (int64_t i : redo) {
+                qb.insert(qb.end(), qbuf + qoff[i], qbuf + qoff[i + 1]); qo.push_back((int64_t)qb.size());
+                tb.insert(tb.end(), tbuf + toff[i], tbuf + toff[i + 1]); to.push_back((int64_t)tb.size());
+                if (mask_len) ml.push_back(mask_len[i]);
+            }
+            const int64_t gn = (int64_t)redo.size();
+            std::vector<db200_sw_result> r((size_t)gn);
+            std::vector<int32_t> st2((size_t)gn);
+            std::vector<int64_t> co((size_t)gn + 1);
+            std::vector<uint32_t> cg(cigar_buf ? qb.size() + tb.size() + 2 * (size_t)gn + 16 : 1);
+            if (qb.empty()) qb.push_back(0);
+            if (tb.empty()) tb.push_back(0);
+            small_inner = true;
+            rc = sw_batch_host_body(e, device, params, qb.data(), qo.data(), tb.data(), to.data(), gn, mask_len ? ml.data() : nullptr, r.data(),
+                                    cigar_buf ? cg.data() : nullptr, cigar_buf ? (int64_t)cg.size() : 0, co.data(), st2.data());
+            small_inner = false;
+            if (rc) return rc;
+            std::vector<uint32_t> merged;
+            std::vector<int64_t> noff((size_t)npairs + 1, 0);
+            size_t rk = 0;
+            for (int64_t i = 0; i < npairs; ++i) {
+                noff[(size_t)i] = (int64_t)merged.size();
+                if (rk < redo.size() && redo[rk] == i) {
+                    results[i] = r[rk];
+                    st[i] = st2[rk];
+                    if (cigar_buf) merged.insert(merged.end(), cg.begin() + co[rk], cg.begin() + co[rk + 1]);
+                    ++rk;
+                } else if (cigar_buf) merged.insert(merged.end(), cigar_buf + coff[i], cigar_buf + coff[i + 1]);
+            }
+            noff[(size_t)npairs] = (int64_t)merged.size();
+            if (cigar_buf) {
+                if ((int64_t)merged.size() > cigar_cap) { set_error("sw_batch_host: cigar buffer too small"); return DB200_ERR_CAPACITY; }
+                if (!merged.empty()) memcpy(cigar_buf, merged.data(), merged.size() * sizeof(uint32_t));
+            } else {
+                for (int64_t i = 0; i < npairs; ++i) noff[(size_t)i + 1] = noff[(size_t)i] + results[i].cigar_len;
+            }
+            if (cigar_off) memcpy(cigar_off, noff.data(), noff.size() * sizeof(int64_t));
+            return DB200_OK;
+        }
+    }
     constexpr int NS = Engine::NSLOT;
     cudaStream_t *cs = e->slot_stream, cst = e->copy_stream;
     const int64_t MAX_CHUNK_BYTES = (int64_t)1 << 30;

@@ -72,6 +72,8 @@ struct Engine {
     size_t pinned_cap = 0;
     void *pinned_out[NSLOT] = {};
     size_t pinned_out_cap[NSLOT] = {};
+    void *small_host = nullptr, *small_dev = nullptr;   // mapped page-locked staging of the one-launch small-batch path (sw_small.cuh)
+    size_t small_cap = 0;
     size_t trace_slab_bytes = (size_t)4 << 30;  // per-block slabs of the wide banded traceback (DB200_TRACE_SLAB_MB)
     // optional stage profiling (CUDA events recorded on the launching stream between pipeline stages)
     bool profiling = false;
@@ -112,6 +114,10 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *params, co
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
                          int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st, const SwLink *link = nullptr);
+
+int sw_small_host(Engine *e, const db200_sw_params *prm, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
+                  const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
+                  int64_t cigar_cap, int64_t *cigar_off, int32_t *status, int *handled);
 
 int ed_batch_device_impl(Engine *e, Arena &ws, const db200_ed_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff,
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,

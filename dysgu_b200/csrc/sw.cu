@@ -430,7 +430,119 @@ __global__ void sw_second_best_kernel(FinalArgs a)
 
 }  // namespace db200
 #include "sw_trace.cuh"
+#include "sw_small.cuh"
 namespace db200 {
+
+// ------------------------------------------------------------------------------------------------
+// latency path: up to SW_SMALL_MAX_PAIRS short pairs in one launch (sw_small.cuh)
+// ------------------------------------------------------------------------------------------------
+// Returns DB200_OK with *handled = 1 when the batch was taken (pairs flagged SW_SMALL_FALLBACK in status[] are left to the
+// caller), *handled = 0 when the batch is not eligible.
+int sw_small_host(Engine *e, const db200_sw_params *prm, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
+                  const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
+                  int64_t cigar_cap, int64_t *cigar_off, int32_t *status, int *handled)
+{
+    *handled = 0;
+    if (npairs <= 0 || npairs > SW_SMALL_MAX_PAIRS || getenv("DB200_NO_SMALL_PATH")) return DB200_OK;
+    if (!(prm->flag == 0 || prm->flag == 1 || prm->flag == 8 || prm->flag == 9)) return DB200_OK;
+    if (prm->gap_open <= 0 || prm->gap_extend <= 0 || prm->gap_open > 255 || prm->gap_extend > 255 || (prm->mat && prm->n != 5) ||
+        prm->score_size < 0 || prm->score_size > 2)
+        return DB200_OK;   // the batch pipeline reports the argument error
+    int64_t qbytes = 0, tbytes = 0;
+    int maxq = 0, eligible = 0;
+    for (int64_t i = 0; i < npairs; ++i) {
+        const int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+        if (ql < 0 || tl < 0) return DB200_OK;
+        if (ql <= SW_SMALL_MAX_Q && tl <= SW_SMALL_MAX_T) { ++eligible; maxq = std::max<int>(maxq, (int)ql); qbytes += ql; tbytes += tl; }
+        else { qbytes += 0; }
+    }
+    if (eligible * 2 < npairs) return DB200_OK;   // mostly long pairs: one trip through the batch pipeline
+    // staging area in page-locked memory mapped into the device address space
+    const size_t in_bytes = (size_t)(qbytes + tbytes) + sizeof(int32_t) * (size_t)(3 * npairs + 2) + 64;
+    const size_t out_bytes = (size_t)npairs * (sizeof(db200_sw_result) + sizeof(int32_t) + sizeof(uint32_t) * SW_SMALL_CIGAR_STRIDE) + 64;
+    const size_t need = ((in_bytes + 255) & ~(size_t)255) + out_bytes;
+    if (e->small_cap < need) {
+        if (e->small_host) cudaFreeHost(e->small_host);
+        e->small_host = nullptr; e->small_cap = 0;
+        const size_t cap = std::max<size_t>(need * 2, (size_t)1 << 20);
+        if (cudaHostAlloc(&e->small_host, cap, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return DB200_OK; }
+        if (cudaHostGetDevicePointer(&e->small_dev, e->small_host, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(e->small_host); e->small_host = nullptr; return DB200_OK; }
+        e->small_cap = cap;
+    }
+    uint8_t *h = reinterpret_cast<uint8_t *>(e->small_host), *d = reinterpret_cast<uint8_t *>(e->small_dev);
+    int32_t *h_qoff = reinterpret_cast<int32_t *>(h), *h_toff = h_qoff + npairs + 1, *h_mask = h_toff + npairs + 1;
+    uint8_t *h_seq = reinterpret_cast<uint8_t *>(h_mask + npairs);
+    int32_t pos = 0;
+    for (int64_t i = 0; i < npairs; ++i) {     // ineligible pairs travel as empty-length placeholders and are re-flagged below
+        const int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+        const bool ok = ql <= SW_SMALL_MAX_Q && tl <= SW_SMALL_MAX_T;
+        h_qoff[i] = pos;
+        if (ok) { memcpy(h_seq + pos, qbuf + qoff[i], (size_t)ql); pos += (int32_t)ql; }
+        h_mask[i] = mask_len ? mask_len[i] : std::max<int32_t>((int32_t)(ql / 2), 15);
+    }
+    h_qoff[npairs] = pos;
+    for (int64_t i = 0; i < npairs; ++i) {
+        const int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+        const bool ok = ql <= SW_SMALL_MAX_Q && tl <= SW_SMALL_MAX_T;
+        h_toff[i] = pos;
+        if (ok) { memcpy(h_seq + pos, tbuf + toff[i], (size_t)tl); pos += (int32_t)tl; }
+    }
+    h_toff[npairs] = pos;
+    // the query block ends where the target block starts: qoff[n] == toff[0]
+    const size_t out0 = (in_bytes + 255) & ~(size_t)255;
+    db200_sw_result *h_res = reinterpret_cast<db200_sw_result *>(h + out0);
+    int32_t *h_status = reinterpret_cast<int32_t *>(h_res + npairs);
+    uint32_t *h_cig = reinterpret_cast<uint32_t *>(h_status + npairs);
+    SmallArgs a;
+    a.seq = d + (h_seq - h);
+    a.qoff = reinterpret_cast<const int32_t *>(d); a.toff = a.qoff + npairs + 1; a.mask_len = a.toff + npairs + 1;
+    a.results = reinterpret_cast<db200_sw_result *>(d + out0);
+    a.status = reinterpret_cast<int32_t *>(a.results + npairs);
+    a.cigar = reinterpret_cast<uint32_t *>(a.status + npairs);
+    a.maxq = (maxq + 15) & ~15;
+    int bias = 0;
+    for (int x = 0; x < 6; ++x)
+        for (int y = 0; y < 6; ++y) {
+            int v = SW_NEG;
+            if (x < 5 && y < 5) v = prm->mat ? prm->mat[x * 5 + y] : ((x == 4 || y == 4) ? 0 : (x == y ? prm->match : prm->mismatch));
+            a.sc.mat[x * 6 + y] = (int16_t)v;
+            if (x < 5 && y < 5 && v < bias) bias = v;
+        }
+    a.sc.gap_open = prm->gap_open; a.sc.gap_extend = prm->gap_extend;
+    a.bias = -bias; a.score_size = prm->score_size; a.flag = prm->flag;
+    const size_t smem = (size_t)a.maxq + SW_SMALL_MAX_T + 2 * SW_SMALL_MAX_T * sizeof(int16_t) + 3 * (SW_SMALL_XW + 2) * sizeof(int16_t) +
+                        SW_SMALL_RUNS * sizeof(uint32_t) + SW_SMALL_DIR_BYTES;
+    static bool attr_done[16] = {false};
+    if (!attr_done[e->device & 15]) {
+        DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(SW_SMALL_MAX_Q + SW_SMALL_MAX_T + 2 * SW_SMALL_MAX_T * sizeof(int16_t) +
+                                                    3 * (SW_SMALL_XW + 2) * sizeof(int16_t) + SW_SMALL_RUNS * sizeof(uint32_t) + SW_SMALL_DIR_BYTES)));
+        attr_done[e->device & 15] = true;
+    }
+    sw_small_kernel<<<(unsigned)npairs, 32, smem, e->stream>>>(a);
+    count_launch(e);
+    DB200_CUDA_CHECK(cudaGetLastError());
+    DB200_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    int64_t cpos = 0;
+    for (int64_t i = 0; i < npairs; ++i) {
+        const int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+        int st = h_status[i];
+        if (!(ql <= SW_SMALL_MAX_Q && tl <= SW_SMALL_MAX_T)) st = SW_SMALL_FALLBACK;
+        results[i] = h_res[i];
+        status[i] = st;
+        if (cigar_off) cigar_off[i] = cpos;
+        if (st == DB200_PAIR_OK && h_res[i].cigar_len > 0) {
+            if (cigar_buf) {
+                if (cpos + h_res[i].cigar_len > cigar_cap) { set_error("sw_batch_host: cigar buffer too small"); return DB200_ERR_CAPACITY; }
+                memcpy(cigar_buf + cpos, h_cig + (size_t)i * SW_SMALL_CIGAR_STRIDE, sizeof(uint32_t) * (size_t)h_res[i].cigar_len);
+            }
+            cpos += h_res[i].cigar_len;
+        }
+    }
+    if (cigar_off) cigar_off[npairs] = cpos;
+    *handled = 1;
+    return DB200_OK;
+}
 
 __global__ void sw_colmax_len_kernel(const PairMeta *meta, const PairState *state, int64_t npairs, int32_t *lens)
 {

@@ -251,6 +251,25 @@ int db200_ed_path_batch_device(int device, const db200_ed_params *params,
                                int64_t *d_loc_off, int64_t *loc_total,
                                uint8_t *d_path_buf, int64_t path_cap, int64_t *d_path_off, int64_t *path_total, void *stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Several GPUs of one box behind one call.  Pairs are independent: no collective.  */
+/* The batch is cut into one contiguous range per device at equal shares of WORK (cells for     */
+/* Smith-Waterman, 64-row word steps for edit distance - not equal pair counts), every range    */
+/* runs through the single-device host entry point on its own host thread, and all outputs      */
+/* come back in the caller's pair order.  Same arguments as db200_sw_batch_host /               */
+/* db200_ed_batch_host with `device` replaced by a device list; pairs_per_device (may be NULL)  */
+/* receives how many pairs each device took.  What dysgu merge's all-vs-all job lists            */
+/* (merge_svs.pyx:395-416) hand over when several GPUs are present.                             */
+/* ------------------------------------------------------------------------------------------ */
+int db200_sw_batch_host_multi(const int32_t *devices, int32_t ndevices, const db200_sw_params *params,
+                              const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf, const int64_t *toff,
+                              int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
+                              int64_t cigar_cap, int64_t *cigar_off, int32_t *status, int64_t *pairs_per_device);
+int db200_ed_batch_host_multi(const int32_t *devices, int32_t ndevices, const db200_ed_params *params,
+                              const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf, const int64_t *toff,
+                              int64_t npairs, const int32_t *k, db200_ed_result *results, int32_t *loc_buf,
+                              int64_t loc_cap, int64_t *loc_off, int64_t *pairs_per_device);
+
 /* Legacy single-pair entry point with edlib's signature (edlib.h:146-271); task EDLIB_TASK_PATH fills
  * alignment / alignmentLength like the reference. */
 typedef struct { char first; char second; } db200_EdlibEqualityPair;

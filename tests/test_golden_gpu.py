@@ -115,6 +115,34 @@ def test_multi_gpu_threads_match_single_gpu():
     assert np.array_equal(off, one.cigar_off) and np.array_equal(cig, one.cigar)
 
 
+def test_multi_device_entry_points_balance_by_work_and_keep_pair_order():
+    """db200_sw_batch_host_multi / db200_ed_batch_host_multi: ranges cut at equal work, one host thread per device, outputs in
+    pair order.  With one GPU leased the device list names it several times - the ranges then run one after the other
+    (per-device lock) through exactly the same split / splice code; with several GPUs they run side by side."""
+    ndev = _lib.device_count()
+    devices = list(range(min(ndev, 8))) if ndev >= 2 else [0, 0, 0]
+    # lengths sorted ascending: equal pair counts would give the last device most of the work
+    q, t, prm = workloads.pe_contig_pairs(6000, seed=3)
+    order = np.argsort(q.lengths * t.lengths, kind="stable")
+    q, t = q.take(order), t.take(order)
+    one = batch.sw_align_batch(q, t, **prm)
+    many = batch.sw_align_batch(q, t, devices=devices, **prm)
+    assert np.array_equal(many.fixed, one.fixed) and np.array_equal(many.status, one.status)
+    assert np.array_equal(many.cigar_off, one.cigar_off) and np.array_equal(many.cigar, one.cigar)
+    per = many.pairs_per_device
+    assert per.sum() == len(q) and per[0] > per[-1] * 1.5          # short pairs first: the first range holds many more of them
+    cells = (q.lengths * t.lengths).astype(np.float64)
+    b = np.concatenate(([0], np.cumsum(per)))
+    work = np.array([cells[b[i]:b[i + 1]].sum() for i in range(len(per))])
+    assert work.max() / work.mean() < 1.15, work
+    c, w, eprm = workloads.remap_chain(9000, seed=4)
+    e1 = batch.ed_align_batch(c, w, **eprm)
+    e2 = batch.ed_align_batch(c, w, devices=devices, **eprm)
+    assert np.array_equal(e1.fixed, e2.fixed) and np.array_equal(e1.loc, e2.loc) and np.array_equal(e1.loc_off, e2.loc_off)
+    small = batch.sw_align_batch(q.take(np.arange(3)), t.take(np.arange(3)), devices=devices, **prm)   # fewer pairs than 2 x devices
+    assert np.array_equal(small.fixed, one.fixed[:3])
+
+
 def test_additional_equalities_golden():
     """edlib's additionalEqualities (symmetric, not transitive; edlib.cpp:60-91) against vectors produced by the
     reference's own wrapper (tests/golden/make_golden_equalities.py): wildcards, IUPAC pairs, case folding, a symbol that
