@@ -19,8 +19,11 @@ profiles/; the driver's bench line is the default workload):
 
 Metric: alignment GCUPS = sum(len(query) * len(target)) / time, forward matrix counted once.
   value : device-timed (CUDA events on the launching stream), inputs resident in HBM
-  e2e   : the same metric through the host C-ABI call (db200_sw_batch_host) with pinned host buffers,
-          H2D and D2H inside the timed region
+  e2e   : the same metric through the host C-ABI call with pinned host buffers, H2D and D2H inside the timed region.
+          Smith-Waterman workloads: db200_sw_batch_host_packed - the batch pre-encoded once, outside the timed region, in
+          the engine's 4-bit pool format (the reference's C entry points take pre-encoded int8 codes as well, ssw.h:72-125);
+          `e2e_ascii` is the same step through db200_sw_batch_host with raw ASCII CSR buffers (round 1's e2e), and
+          `python_front_door` a 65,536-pair batch through dysgu_b200.batch.sw_align_batch(list, list).
 """
 from __future__ import annotations
 
@@ -46,9 +49,9 @@ UNIT = "GCUPS"
 SW_LANE_OPS_PER_CELL = 3.0
 # measured on this pool's B200s by dysgu_b200/int_peak (profiles/r01_int_peak.json): VIADDMNMX.S16x2 lane-ops/s
 INT_PEAK_FALLBACK = 1.81e13
-# DRAM bytes moved by the forward scoring launches per byte of ASCII input, from the ncu pass in
-# profiles/r01_forward_traffic.txt (563.3 MB for 833.6 MB of input at 524,288 pairs per step)
-FWD_TRAFFIC_PER_INPUT_BYTE = 563.3e6 / 833.55e6
+# register-only Myers / Hyyro word steps per second (int_peak "myers_word_step", profiles/r02_int_peak.json): the roof of the
+# edit-distance kernels - every word step of the kernels issues the same ~23 ALU-pipe instructions the benchmark issues
+MYERS_PEAK_FALLBACK = 7.73e11
 
 
 def load_measured_peaks():
@@ -61,15 +64,34 @@ def load_measured_peaks():
             out["source"] = "measured"
         except Exception:
             pass
-    ip = os.path.join(ROOT, "profiles", "r01_int_peak.json")
     out["int_lane_ops"] = INT_PEAK_FALLBACK
-    if os.path.exists(ip):
-        try:
-            d = json.load(open(ip))
-            out["int_lane_ops"] = float(d["lane_ops_per_s"]["viaddmnmx_s16x2_relu"])
-        except Exception:
-            pass
+    out["myers_word_steps"] = MYERS_PEAK_FALLBACK
+    out["int_source"] = "fallback constants"
+    for name in ("r02_int_peak.json", "r01_int_peak.json"):
+        ip = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(ip):
+            try:
+                d = json.load(open(ip))
+                out["int_lane_ops"] = float(d["lane_ops_per_s"]["viaddmnmx_s16x2_relu"])
+                out["myers_word_steps"] = float(d["lane_ops_per_s"].get("myers_word_step", MYERS_PEAK_FALLBACK))
+                out["int_source"] = "measured: dysgu_b200/int_peak on this pool (profiles/%s)" % name
+                break
+            except Exception:
+                pass
     return out
+
+
+def measured_forward_traffic(pairs):
+    """DRAM bytes of the forward scoring launches of one step, from this round's ncu pass over this very command
+    (scripts/forward_traffic.sh -> profiles/r02_forward_traffic.json).  None unless the pass matches the batch size."""
+    p = os.path.join(ROOT, "profiles", "r02_forward_traffic.json")
+    try:
+        d = json.load(open(p))
+        if int(d["pairs_per_step"]) == int(pairs):
+            return float(d["dram_bytes_per_step"]), "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the forward sw_pass_kernel launches of one step of this command (profiles/r02_forward_traffic.json)"
+    except Exception:
+        pass
+    return None, "no ncu pass for this batch size (scripts/forward_traffic.sh)"
 
 
 class ClockSampler:
@@ -159,7 +181,7 @@ ED_LANE_OPS_PER_WORD_STEP = 44.0
 
 # name -> (kind, generator, default pairs per step per GPU, CPU reference sample, description)
 WORKLOADS = {
-    "remap_windows": ("sw", lambda W, n, s: W.remap_windows(n, seed=s), 1 << 19, 400000,
+    "remap_windows": ("sw", lambda W, n, s: W.remap_windows(n, seed=s), 1 << 19, 1 << 19,
                       "remap_windows: SSW(window 1000/1500/2000 bp; 2,-8,6,1)(soft clip 15-300 bp), score+coords+cigar"),
     "pe_contigs": ("sw", lambda W, n, s: W.pe_contig_pairs(n, seed=s), 1 << 18, 100000,
                    "pe_contigs: check_contig_match SSW (2,-3,10,1), paired-end contigs 100-500 bp, score+coords+cigar"),
@@ -408,6 +430,58 @@ def run_ours(args):
     h2d = q_bytes + t_bytes + 2 * 8 * (n + 1)
     d2h = 4 * res_cols * n + 8 * (n + 1) + (4 * n + 4 * nvar if kind == "sw" else 8 * nvar) + (int(hpoff[n]) + 8 * (n + 1) if want_path else 0)
 
+    # ---- end-to-end arm with the batch pre-encoded on the host (db200_sw_batch_host_packed): the engine's 4-bit pool format,
+    #      written once by db200_sw_pack_host outside the timed region - the counterpart of the int8 codes the reference's
+    #      C entry points take (ssw.h:72-125; the wrapper encodes before ssw_init / ssw_align) at half a byte per base
+    e2e_packed = None
+    if kind == "sw":
+        pq, pt = B.pack_seqs(q, pinned=True), B.pack_seqs(t, pinned=True)
+        hql = pinned_array(L, (n,), np.int32); hql[:] = pq.lengths
+        htl = pinned_array(L, (n,), np.int32); htl[:] = pt.lengths
+        hquo = pinned_array(L, (n + 1,), np.int64); hquo[:] = pq.unit_off
+        htuo = pinned_array(L, (n + 1,), np.int64); htuo[:] = pt.unit_off
+        hres2 = pinned_array(L, (n, res_cols), np.int32)
+
+        def packed_step():
+            rc = L.db200_sw_batch_host_packed(local_rank, C.byref(prm_c), pq.units.ctypes.data, hquo.ctypes.data, hql.ctypes.data,
+                                              pt.units.ctypes.data, htuo.ctypes.data, htl.ctypes.data, n, None, hres2.ctypes.data,
+                                              hvar.ctypes.data, var_cap, hvoff.ctypes.data, hstat.ctypes.data)
+            _lib.check(rc, "db200_sw_batch_host_packed")
+
+        for _ in range(2):
+            packed_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            packed_step()
+        torch.cuda.synchronize(dev)
+        dtp = time.perf_counter() - t0
+        tdp = torch.tensor([dtp], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tdp, op=dist.ReduceOp.MAX)
+        if not np.array_equal(hres2, hres) or int(hvoff[n]) != nvar:
+            raise SystemExit("bench.py: packed and ASCII host arms disagree")
+        e2e_packed = {"value": total_cells * e2e_steps / float(tdp.item()) / 1e9, "unit": UNIT,
+                      "h2d_bytes_per_step": pq.nbytes + pt.nbytes + 2 * 4 * n, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                      "ms_per_step": 1e3 * float(tdp.item()) / e2e_steps,
+                      "input": "pre-encoded 4-bit pool format in page-locked memory (db200_sw_pack_host, outside the timed region - the "
+                               "reference's C entry points take pre-encoded int8 codes as well), db200_sw_batch_host_packed"}
+
+    # ---- the Python front door on a smaller batch: list of bytes in, numpy results out (dysgu_b200.batch.sw_align_batch)
+    front_door = None
+    if kind == "sw" and rank == 0:
+        nf = min(n, 1 << 16)
+        ql, tl_ = q.take(np.arange(nf)).tolist(), t.take(np.arange(nf)).tolist()
+        fcells = float((q.lengths[:nf].astype(np.float64) * t.lengths[:nf].astype(np.float64)).sum())
+        B.sw_align_batch(ql, tl_, device=local_rank, **prm)
+        t0 = time.perf_counter()
+        rr = B.sw_align_batch(ql, tl_, device=local_rank, **prm)
+        dtf = time.perf_counter() - t0
+        if not np.array_equal(rr.fixed[:, :7], hres[:nf, :7]):
+            raise SystemExit("bench.py: Python front door and C ABI disagree")
+        front_door = {"value": fcells / dtf / 1e9, "unit": UNIT, "pairs": nf, "ms": 1e3 * dtf,
+                      "call": "dysgu_b200.batch.sw_align_batch(list[bytes], list[bytes]) -> numpy (pageable buffers, CSR built in Python)"}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -427,12 +501,13 @@ def run_ours(args):
         roofline = {
             "bound": "int_alu", "kernel": "sw_pass_kernel (forward scoring pass, all length buckets)",
             "achieved": achieved, "peak": peak, "unit": "Tlaneop/s (s16x2 DPX lane-instructions)",
-            "frac": (achieved / peak) if achieved else None, "peak_source": "measured: dysgu_b200/int_peak on this pool (profiles/r01_int_peak.json)",
+            "frac": (achieved / peak) if achieved else None, "peak_source": peaks["int_source"],
+            "frac_whole_step": lane_ops / (ms_max / args.steps * 1e-3) / 1e12 / peak,
             "ops_per_cell": SW_LANE_OPS_PER_CELL, "kernel_ms_per_step": k_ms, "kernel_gcups": cells / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None,
             "hbm_algorithmic_gbs": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None, "hbm_peak_gbs": peaks["hbm_gbs"],
             "hbm_peak_source": peaks["source"],
-            "traffic": (q_bytes + t_bytes) * FWD_TRAFFIC_PER_INPUT_BYTE if name == "remap_windows" else None, "algorithmic_bytes": alg_bytes,
-            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the forward launches of one step (profiles/r01_forward_traffic.txt), scaled by input bytes",
+            "traffic": measured_forward_traffic(n)[0] if name == "remap_windows" else None, "algorithmic_bytes": alg_bytes,
+            "traffic_source": measured_forward_traffic(n)[1],
             "stage_ms_per_step": stages,
         }
         roofline["hbm"] = {"bound": "hbm", "achieved": roofline["hbm_algorithmic_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -440,14 +515,17 @@ def run_ours(args):
                            "note": "integer dynamic programming: the kernel is bound by the ALU pipe (frac above), not by HBM"}
     else:
         k_ms = stage_ms[12] / args.steps         # banded rounds + ed_myers_kernel forward launches of one step
-        lane_ops = word_steps * ED_LANE_OPS_PER_WORD_STEP
-        achieved = lane_ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
+        # word steps actually evaluated per second against the measured register-only Myers word-step rate (int_peak
+        # "myers_word_step"): both sides count the same unit, so the fraction is what the ALU pipe could still give.
+        peak_ws = peaks["myers_word_steps"] / 1e12
+        achieved = word_steps / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
         alg_bytes = float(q_bytes + t_bytes) + 16.0 * n
         roofline = {
             "bound": "int_alu", "kernel": "ed_banded_nw_kernel + ed_myers_kernel (forward pass, all configurations)" if prm["mode"] == "NW"
             else "ed_myers_kernel (forward pass, all configurations)",
-            "achieved": achieved, "peak": peak, "unit": "Tlaneop/s (int32-equivalent ALU lane-ops, 44 per 64-row Myers word step)",
-            "frac": (achieved / peak) if achieved else None, "peak_source": "measured: dysgu_b200/int_peak on this pool (profiles/r01_int_peak.json)",
+            "achieved": achieved, "peak": peak_ws, "unit": "T word steps/s (one Myers / Hyyro update of a 64-row word, edlib.cpp:411-443)",
+            "frac": (achieved / peak_ws) if achieved else None, "peak_source": peaks["int_source"] + " myers_word_step",
+            "frac_algorithmic_44_ops": (word_steps * ED_LANE_OPS_PER_WORD_STEP / (k_ms * 1e-3) / 1e12 / peak) if k_ms > 0 else None,
             "ops_per_word_step": ED_LANE_OPS_PER_WORD_STEP, "word_steps_per_step": word_steps,
             "word_steps_full_matrix": float(((q.lengths + 63) // 64 * t.lengths).sum()),
             "kernel_ms_per_step": k_ms, "kernel_gcups": cells / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None,
@@ -477,6 +555,12 @@ def run_ours(args):
             ncmp = 7 if kind == "sw" else 4
             mism = int((r.fixed[:, :ncmp] != hres[:sample, :ncmp]).any(axis=1).sum())
             cpu_baseline["parity_mismatches_on_sample"] = mism
+            if kind == "sw":   # cigars: same CSR offsets and the same BAM-encoded operations
+                same_off = bool(np.array_equal(np.asarray(r.cigar_off[:sample + 1]), hvoff[:sample + 1]))
+                nops = int(r.cigar_off[sample])
+                cpu_baseline["cigar_ops_on_sample"] = nops
+                cpu_baseline["cigar_mismatches_on_sample"] = int((np.asarray(r.cigar[:nops]) != hvar[:nops]).sum()) if same_off else \
+                    int((np.diff(np.asarray(r.cigar_off[:sample + 1])) != np.diff(hvoff[:sample + 1])).sum())
             if want_path:   # the reference's alignment arrays (one slot per pair) against ours (back to back), operation by operation
                 ln = r.path_len.astype(np.int64)
                 idx = np.repeat(np.asarray(r.path_off, dtype=np.int64) - (np.cumsum(ln) - ln), ln) + np.arange(int(ln.sum()), dtype=np.int64)
@@ -486,6 +570,9 @@ def run_ours(args):
         except Exception as exc:
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % str(exc)[:100]}
 
+    e2e_ascii = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                 "ms_per_step": 1e3 * float(tdt.item()) / e2e_steps,
+                 "input": "ASCII CSR batches in page-locked memory, db200_%s_batch_host" % kind}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -495,8 +582,9 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (%.0f MB per step)" % ((q_bytes + t_bytes) / 1e6), "sharding": "pairs by rank, no collective",
                    "host": numa_note},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "ms_per_step": 1e3 * float(tdt.item()) / e2e_steps},
+        "e2e": e2e_packed if e2e_packed else e2e_ascii,
+        "e2e_ascii": e2e_ascii,
+        "python_front_door": front_door,
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

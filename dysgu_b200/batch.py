@@ -194,6 +194,104 @@ def sw_align_batch(queries, targets, match=2, mismatch=-3, gap_open=5, gap_exten
     return SwResults(fixed, cigar[:coff[n]] if want_cigar else cigar[:0], coff, status)
 
 
+class PackedSeqs:
+    """One side of a batch in the engine's pool format (db200_sw_pack_host): uint32 units (4 words = 32 bases per unit),
+    int64 unit offsets [n + 1], int32 lengths [n]."""
+
+    def __init__(self, units, unit_off, lengths):
+        self.units, self.unit_off, self.lengths = units, unit_off, lengths
+
+    def __len__(self):
+        return len(self.lengths)
+
+    @property
+    def nbytes(self):
+        return int(self.unit_off[-1]) * 16
+
+
+def pack_seqs(seqs, threads=0, pinned=False) -> PackedSeqs:
+    """ASCII batch -> pool format on the host (encoding of _ssw_wrapper.pyx:60-68, 4 bits per base)."""
+    b = _as_batch(seqs)
+    L = _lib.lib()
+    n = len(b)
+    uoff = np.zeros(n + 1, dtype=np.int64)
+    lens = np.zeros(max(n, 1), dtype=np.int32)
+    _lib.check(L.db200_sw_pack_host(None, _ptr(b.off), None, n, None, 0, _ptr(uoff), _ptr(lens), 0), "db200_sw_pack_host (sizing)")
+    nwords = max(int(uoff[-1]) * 4, 1)
+    if pinned:
+        ptr = L.db200_host_alloc(nwords * 4)
+        if not ptr:
+            raise _lib.AlignEngineError("pinned allocation failed")
+        units = np.frombuffer((C.c_uint8 * (nwords * 4)).from_address(ptr), dtype=np.uint32, count=nwords)
+    else:
+        units = np.zeros(nwords, dtype=np.uint32)
+    buf = b.buf if b.buf.size else np.zeros(1, np.uint8)
+    _lib.check(L.db200_sw_pack_host(_ptr(buf), _ptr(b.off), None, n, _ptr(units), int(uoff[-1]), _ptr(uoff), _ptr(lens),
+                                    threads or (os.cpu_count() or 1)), "db200_sw_pack_host")
+    return PackedSeqs(units, uoff, lens[:n])
+
+
+def _sw_outputs(n, cap):
+    return (np.zeros((n, 8), dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros(n + 1, dtype=np.int64), np.zeros(max(cap, 1), dtype=np.uint32))
+
+
+def _sw_params(match, mismatch, gap_open, gap_extend, score_size, flag, filters, filterd, matrix):
+    prm = _lib.SwParams()
+    prm.match, prm.mismatch, prm.gap_open, prm.gap_extend = match, mismatch, gap_open, gap_extend
+    prm.score_size, prm.flag, prm.filters, prm.filterd = score_size, flag, filters, filterd
+    mat_arr = None
+    if matrix is not None:
+        mat_arr = np.ascontiguousarray(matrix, dtype=np.int8).reshape(25)
+        prm.mat = mat_arr.ctypes.data_as(C.POINTER(C.c_int8))
+        prm.n = 5
+    return prm, mat_arr
+
+
+def sw_align_packed(queries: PackedSeqs, targets: PackedSeqs, match=2, mismatch=-3, gap_open=5, gap_extend=2, score_size=2, flag=1,
+                    filters=0, filterd=0, mask_len=None, matrix=None, device=None) -> SwResults:
+    """sw_align_batch for batches that are already in pool format (db200_sw_batch_host_packed): half the PCIe bytes of ASCII."""
+    n = len(queries)
+    if len(targets) != n:
+        raise ValueError("queries and targets differ in length")
+    prm, keep = _sw_params(match, mismatch, gap_open, gap_extend, score_size, flag, filters, filterd, matrix)
+    ml = None if mask_len is None else np.ascontiguousarray(np.broadcast_to(np.asarray(mask_len, dtype=np.int32), (n,)))
+    cap = int(queries.lengths.astype(np.int64).sum() + targets.lengths.astype(np.int64).sum() + 2 * n + 16)
+    fixed, status, coff, cigar = _sw_outputs(n, cap)
+    rc = _lib.lib().db200_sw_batch_host_packed(default_device() if device is None else device, C.byref(prm), _ptr(queries.units),
+                                               _ptr(queries.unit_off), _ptr(queries.lengths), _ptr(targets.units), _ptr(targets.unit_off),
+                                               _ptr(targets.lengths), n, _ptr(ml), _ptr(fixed), _ptr(cigar), cap, _ptr(coff), _ptr(status))
+    _lib.check(rc, "db200_sw_batch_host_packed")
+    return SwResults(fixed, cigar[:coff[n]], coff, status)
+
+
+def sw_align_slices(qsrc, qstart, qlen, targets, match=2, mismatch=-3, gap_open=5, gap_extend=2, score_size=2, flag=1, filters=0,
+                    filterd=0, mask_len=None, matrix=None, device=None, tsrc=None, tstart=None, tlen=None) -> SwResults:
+    """Queries are slices qsrc[qstart[i] : qstart[i] + qlen[i]] of one shared buffer that is uploaded once (overlapping windows of
+    a reference region, re_map.py:429-434); targets either a CSR batch (`targets`) or slices of `tsrc` as well
+    (db200_sw_batch_host_slices)."""
+    qsrc = np.ascontiguousarray(np.frombuffer(qsrc, dtype=np.uint8) if isinstance(qsrc, (bytes, bytearray)) else qsrc, dtype=np.uint8)
+    qstart = np.ascontiguousarray(qstart, dtype=np.int64)
+    qlen = np.ascontiguousarray(qlen, dtype=np.int32)
+    n = len(qlen)
+    if tsrc is None:
+        t = _as_batch(targets)
+        tb, to, tl, tbytes = (t.buf if t.buf.size else np.zeros(1, np.uint8)), t.off, None, int(t.off[-1])
+        tsum = tbytes
+    else:
+        tb = np.ascontiguousarray(np.frombuffer(tsrc, dtype=np.uint8) if isinstance(tsrc, (bytes, bytearray)) else tsrc, dtype=np.uint8)
+        to, tl, tbytes = np.ascontiguousarray(tstart, dtype=np.int64), np.ascontiguousarray(tlen, dtype=np.int32), int(tb.size)
+        tsum = int(tl.astype(np.int64).sum())
+    prm, keep = _sw_params(match, mismatch, gap_open, gap_extend, score_size, flag, filters, filterd, matrix)
+    ml = None if mask_len is None else np.ascontiguousarray(np.broadcast_to(np.asarray(mask_len, dtype=np.int32), (n,)))
+    cap = int(qlen.astype(np.int64).sum() + tsum + 2 * n + 16)
+    fixed, status, coff, cigar = _sw_outputs(n, cap)
+    rc = _lib.lib().db200_sw_batch_host_slices(default_device() if device is None else device, C.byref(prm), _ptr(qsrc), int(qsrc.size),
+                                               _ptr(qstart), _ptr(qlen), _ptr(tb), tbytes, _ptr(to), _ptr(tl), n, _ptr(ml), _ptr(fixed),
+                                               _ptr(cigar), cap, _ptr(coff), _ptr(status))
+    _lib.check(rc, "db200_sw_batch_host_slices")
+    return SwResults(fixed, cigar[:coff[n]], coff, status)
+
+
 class EdResults:
     """Results of an edit-distance batch (fields follow EdlibAlignResult, edlib.h:162-218)."""
 

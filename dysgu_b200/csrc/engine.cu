@@ -298,6 +298,7 @@ void db200_shutdown(void)
         cudaSetDevice(e->device);
         cudaDeviceSynchronize();
         for (int i = 0; i < Engine::NSLOT; ++i) { e->arena[i].release(); e->io[i].release(); }
+        e->src.release();
         for (int i = 0; i < Engine::NSLOT; ++i) if (e->pinned_out[i]) cudaFreeHost(e->pinned_out[i]);
         if (e->pinned) cudaFreeHost(e->pinned);
         for (int k = 0; k < Engine::NSLOT; ++k) {
@@ -493,18 +494,30 @@ static int sw_finalize_slot(Engine *e, int slot, SwSlot &sl, uint32_t *cigar_buf
     return DB200_OK;
 }
 
-static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
-                              const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
-                              int64_t cigar_cap, int64_t *cigar_off, int32_t *status);
+// One side of a host batch: CSR (len == nullptr: sequence i = buf[off[i], off[i + 1])) or slices of a shared source buffer of
+// src_bytes bytes (sequence i = buf[off[i], off[i] + len[i])).
+struct HostSeqs {
+    const uint8_t *buf;
+    const int64_t *off;
+    const int32_t *len;
+    int64_t src_bytes;
+    bool packed = false;   // pre-packed form: buf holds pool units (16 bytes = 32 bases), off[] counts units, len[] bases
+    int64_t length(int64_t i) const { return len ? (int64_t)len[i] : off[i + 1] - off[i]; }
+    const uint8_t *ptr(int64_t i) const { return buf + off[i]; }
+};
 
-int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
-                        const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
-                        int64_t cigar_cap, int64_t *cigar_off, int32_t *status)
+static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *params, const HostSeqs &Q, const HostSeqs &T, int64_t npairs,
+                              const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap, int64_t *cigar_off,
+                              int32_t *status);
+
+static int sw_batch_host_locked(int device, const db200_sw_params *params, const HostSeqs &Q, const HostSeqs &T, int64_t npairs,
+                                const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap, int64_t *cigar_off,
+                                int32_t *status)
 {
     Engine *e = get_engine(device);
     if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
     std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);   // one batch call per device at a time (arenas, streams and slots are per engine)
-    const int rc = sw_batch_host_body(e, device, params, qbuf, qoff, tbuf, toff, npairs, mask_len, results, cigar_buf, cigar_cap, cigar_off, status);
+    const int rc = sw_batch_host_body(e, device, params, Q, T, npairs, mask_len, results, cigar_buf, cigar_cap, cigar_off, status);
     if (rc != DB200_OK) {
         // chunks of other slots may still be copying into the caller's arrays: nothing of this call is left in flight on return
         for (int k = 0; k < Engine::NSLOT; ++k) cudaStreamSynchronize(e->slot_stream[k]);
@@ -514,15 +527,88 @@ int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t
     return rc;
 }
 
-static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
-                              const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
-                              int64_t cigar_cap, int64_t *cigar_off, int32_t *status)
+int db200_sw_batch_host(int device, const db200_sw_params *params, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
+                        const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,
+                        int64_t cigar_cap, int64_t *cigar_off, int32_t *status)
 {
     if (npairs < 0 || !params || !qoff || !toff || !results) { set_error("sw_batch_host: bad arguments"); return DB200_ERR_ARG; }
+    const HostSeqs Q{qbuf, qoff, nullptr, 0}, T{tbuf, toff, nullptr, 0};
+    return sw_batch_host_locked(device, params, Q, T, npairs, mask_len, results, cigar_buf, cigar_cap, cigar_off, status);
+}
+
+// Pre-packed form: both sides arrive in the engine's own pool format - 4-bit codes (A/U 0, C 1, G 2, T 3, other 4, padding 5),
+// eight bases per 32-bit word, every sequence padded to a 16-byte unit of 32 bases - as db200_sw_pack_host writes it.  The
+// reference's C boundary also takes encoded sequences (ssw_init / ssw_align read int8 codes, ssw.h:72-125; the wrapper
+// encodes, _ssw_wrapper.pyx:668-679); here the encoded form is half a byte per base, so a batch crosses PCIe at half the
+// bytes of ASCII and lands in the device pool without a pack kernel.  qunit_off / tunit_off [npairs + 1] count units and
+// must be dense: unit_off[i + 1] - unit_off[i] == ceil(len[i] / 32).
+int db200_sw_batch_host_packed(int device, const db200_sw_params *params, const uint32_t *qunits, const int64_t *qunit_off, const int32_t *qlen,
+                               const uint32_t *tunits, const int64_t *tunit_off, const int32_t *tlen, int64_t npairs, const int32_t *mask_len,
+                               db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap, int64_t *cigar_off, int32_t *status)
+{
+    if (npairs < 0 || !params || !qunit_off || !tunit_off || !qlen || !tlen || !results) { set_error("sw_batch_host_packed: bad arguments"); return DB200_ERR_ARG; }
+    for (int64_t i = 0; i < npairs; ++i)
+        if (qlen[i] < 0 || tlen[i] < 0 || qunit_off[i + 1] - qunit_off[i] != ((int64_t)qlen[i] + 31) / 32 || tunit_off[i + 1] - tunit_off[i] != ((int64_t)tlen[i] + 31) / 32) {
+            set_error("sw_batch_host_packed: unit offsets of pair %lld do not match its lengths", (long long)i);
+            return DB200_ERR_ARG;
+        }
+    HostSeqs Q{reinterpret_cast<const uint8_t *>(qunits), qunit_off, qlen, 0}, T{reinterpret_cast<const uint8_t *>(tunits), tunit_off, tlen, 0};
+    Q.packed = T.packed = true;
+    return sw_batch_host_locked(device, params, Q, T, npairs, mask_len, results, cigar_buf, cigar_cap, cigar_off, status);
+}
+
+// Slices form: sequences are (start, length) views of shared source buffers that travel to the device ONCE per call - the
+// shape dysgu's remapping really has: one reference region fetched per group of events (re_map.py:429-434) and many
+// windows cut out of it, overlapping freely.  A side whose length array is NULL is plain CSR (start = offsets[npairs + 1]).
+int db200_sw_batch_host_slices(int device, const db200_sw_params *params, const uint8_t *qsrc, int64_t qsrc_bytes, const int64_t *qstart,
+                               const int32_t *qlen, const uint8_t *tsrc, int64_t tsrc_bytes, const int64_t *tstart, const int32_t *tlen,
+                               int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap,
+                               int64_t *cigar_off, int32_t *status)
+{
+    if (npairs < 0 || !params || !qstart || !tstart || !results || qsrc_bytes < 0 || tsrc_bytes < 0) { set_error("sw_batch_host_slices: bad arguments"); return DB200_ERR_ARG; }
+    for (int side = 0; side < 2; ++side) {
+        const int64_t *st = side ? tstart : qstart;
+        const int32_t *ln = side ? tlen : qlen;
+        const int64_t cap = side ? tsrc_bytes : qsrc_bytes;
+        if (!ln) continue;
+        for (int64_t i = 0; i < npairs; ++i)
+            if (st[i] < 0 || ln[i] < 0 || st[i] + ln[i] > cap) { set_error("sw_batch_host_slices: slice %lld leaves its source buffer", (long long)i); return DB200_ERR_ARG; }
+    }
+    const HostSeqs Q{qsrc, qstart, qlen, qsrc_bytes}, T{tsrc, tstart, tlen, tsrc_bytes};
+    return sw_batch_host_locked(device, params, Q, T, npairs, mask_len, results, cigar_buf, cigar_cap, cigar_off, status);
+}
+
+// pairs `idx` of (Q, T) as two plain CSR batches (small groups only: the latency path, retries)
+static void append_sequence(const HostSeqs &S, int64_t i, std::vector<uint8_t> &out)
+{
+    const int64_t len = S.length(i);
+    if (!S.packed) { out.insert(out.end(), S.ptr(i), S.ptr(i) + len); return; }
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(S.buf) + S.off[i] * 4;   // pool units back to letters
+    for (int64_t k = 0; k < len; ++k) out.push_back((uint8_t)"ACGTNN??????????"[(w[k >> 3] >> ((k & 7) * 4)) & 15u]);
+}
+
+static void materialise(const HostSeqs &Q, const HostSeqs &T, const std::vector<int64_t> &idx, const int32_t *mask_len, std::vector<uint8_t> &qb,
+                        std::vector<int64_t> &qo, std::vector<uint8_t> &tb, std::vector<int64_t> &to, std::vector<int32_t> &ml)
+{
+    qo.assign(1, 0); to.assign(1, 0);
+    for (int64_t i : idx) {
+        append_sequence(Q, i, qb); qo.push_back((int64_t)qb.size());
+        append_sequence(T, i, tb); to.push_back((int64_t)tb.size());
+        if (mask_len) ml.push_back(mask_len[i]);
+    }
+    if (qb.empty()) qb.push_back(0);
+    if (tb.empty()) tb.push_back(0);
+}
+
+static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *params, const HostSeqs &Q, const HostSeqs &T, int64_t npairs,
+                              const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap, int64_t *cigar_off,
+                              int32_t *status)
+{
+    const uint8_t *qbuf = Q.buf, *tbuf = T.buf;
     if (cigar_off) cigar_off[0] = 0;
     // ---- latency path: a few short pairs run in one launch (sw_small.cuh); what it cannot hold goes through the pipeline below
     static thread_local bool small_inner = false;
-    if (!small_inner && npairs > 0 && npairs <= 64 && qbuf && tbuf) {
+    if (!small_inner && npairs > 0 && npairs <= 64 && qbuf && tbuf && Q.packed == T.packed) {
         std::vector<int32_t> st_local;
         int32_t *st = status;
         if (!st) { st_local.assign((size_t)npairs, 0); st = st_local.data(); }
@@ -530,7 +616,18 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
         int64_t *coff = cigar_off;
         if (!coff) { coff_local.assign((size_t)npairs + 1, 0); coff = coff_local.data(); }
         int handled = 0;
-        int rc = sw_small_host(e, params, qbuf, qoff, tbuf, toff, npairs, mask_len, results, cigar_buf, cigar_cap, coff, st, &handled);
+        std::vector<uint8_t> sq, stb;
+        std::vector<int64_t> sqo, sto;
+        std::vector<int32_t> sml;
+        const int64_t *qoff_csr = Q.off, *toff_csr = T.off;
+        const uint8_t *qbuf_csr = qbuf, *tbuf_csr = tbuf;
+        if (Q.len || T.len) {   // the small kernel reads CSR: a few short pairs are cheap to copy
+            std::vector<int64_t> all((size_t)npairs);
+            for (int64_t i = 0; i < npairs; ++i) all[(size_t)i] = i;
+            materialise(Q, T, all, nullptr, sq, sqo, stb, sto, sml);
+            qoff_csr = sqo.data(); toff_csr = sto.data(); qbuf_csr = sq.data(); tbuf_csr = stb.data();
+        }
+        int rc = sw_small_host(e, params, qbuf_csr, qoff_csr, tbuf_csr, toff_csr, npairs, mask_len, results, cigar_buf, cigar_cap, coff, st, &handled);
         if (rc) return rc;
         if (handled) {
             std::vector<int64_t> redo;
@@ -538,23 +635,20 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
             if (redo.empty()) return DB200_OK;
             // the pairs the small kernel could not hold: one call of the batch pipeline, results spliced back in pair order
             std::vector<uint8_t> qb, tb;
-            std::vector<int64_t> qo(1, 0), to(1, 0);
+            std::vector<int64_t> qo, to;
             std::vector<int32_t> ml;
-            for (int64_t i : redo) {
-                qb.insert(qb.end(), qbuf + qoff[i], qbuf + qoff[i + 1]); qo.push_back((int64_t)qb.size());
-                tb.insert(tb.end(), tbuf + toff[i], tbuf + toff[i + 1]); to.push_back((int64_t)tb.size());
-                if (mask_len) ml.push_back(mask_len[i]);
-            }
+            materialise(Q, T, redo, mask_len, qb, qo, tb, to, ml);
             const int64_t gn = (int64_t)redo.size();
             std::vector<db200_sw_result> r((size_t)gn);
             std::vector<int32_t> st2((size_t)gn);
             std::vector<int64_t> co((size_t)gn + 1);
             std::vector<uint32_t> cg(cigar_buf ? qb.size() + tb.size() + 2 * (size_t)gn + 16 : 1);
-            if (qb.empty()) qb.push_back(0);
-            if (tb.empty()) tb.push_back(0);
             small_inner = true;
-            rc = sw_batch_host_body(e, device, params, qb.data(), qo.data(), tb.data(), to.data(), gn, mask_len ? ml.data() : nullptr, r.data(),
-                                    cigar_buf ? cg.data() : nullptr, cigar_buf ? (int64_t)cg.size() : 0, co.data(), st2.data());
+            {
+                const HostSeqs Q2{qb.data(), qo.data(), nullptr, 0}, T2{tb.data(), to.data(), nullptr, 0};
+                rc = sw_batch_host_body(e, device, params, Q2, T2, gn, mask_len ? ml.data() : nullptr, r.data(),
+                                        cigar_buf ? cg.data() : nullptr, cigar_buf ? (int64_t)cg.size() : 0, co.data(), st2.data());
+            }
             small_inner = false;
             if (rc) return rc;
             std::vector<uint32_t> merged;
@@ -597,6 +691,24 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
         for (const char *q = sp; *q;) { char *end; const long long v = strtoll(q, &end, 10); if (end == q) break; if (v > 0) schedule.push_back(v); q = (*end == ',') ? end + 1 : end; }
         if (!schedule.empty()) { fixed_chunks = true; chunk_pairs = schedule[0]; }
     }
+    // slices form: the shared source buffers travel once, ahead of the first chunk (copy stream order puts them first)
+    const uint8_t *d_qsrc = nullptr, *d_tsrc = nullptr;
+    const bool packed = Q.packed && T.packed;
+    if (!packed && (Q.len || T.len)) {
+        e->src.reset();
+        if (Q.len) {
+            uint8_t *d = e->src.alloc<uint8_t>((size_t)Q.src_bytes + 16);
+            if (!d) { set_error("sw_batch_host_slices: device allocation failed"); return DB200_ERR_NOMEM; }
+            if (Q.src_bytes > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(d, Q.buf, (size_t)Q.src_bytes, cudaMemcpyHostToDevice, cst));
+            d_qsrc = d;
+        }
+        if (T.len) {
+            uint8_t *d = e->src.alloc<uint8_t>((size_t)T.src_bytes + 16);
+            if (!d) { set_error("sw_batch_host_slices: device allocation failed"); return DB200_ERR_NOMEM; }
+            if (T.src_bytes > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(d, T.buf, (size_t)T.src_bytes, cudaMemcpyHostToDevice, cst));
+            d_tsrc = d;
+        }
+    }
     int64_t cig_written = 0;
     SwSlot slots[NS];
     int iter = 0;
@@ -610,15 +722,16 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
     const double host0 = host_now();
     if (timeline) { cudaEventCreate(&tl0); cudaEventRecord(tl0, cst); }
     for (int64_t c0 = 0; c0 < npairs; ++iter) {
-        int64_t c1 = c0, bytes = 0;
+        int64_t c1 = c0, bytes = 0, qb = 0, tb = 0;
         int32_t maxq = 0, maxt = 0;
         int64_t want = chunk_pairs;
         if (npairs - (c0 + want) < want / 2) want = npairs - c0;   // no tiny trailing chunk
         while (c1 < npairs && c1 - c0 < want) {
-            const int64_t ql = qoff[c1 + 1] - qoff[c1], tl = toff[c1 + 1] - toff[c1];
+            const int64_t ql = Q.length(c1), tl = T.length(c1);
             if (ql < 0 || tl < 0 || ql > 0x7FFFFFF0 || tl > 0x7FFFFFF0) { set_error("sw_batch_host: bad offsets at pair %lld", (long long)c1); return DB200_ERR_ARG; }
             if (c1 > c0 && bytes + ql + tl > MAX_CHUNK_BYTES) break;
             bytes += ql + tl;
+            qb += ql; tb += tl;
             maxq = std::max<int32_t>(maxq, (int32_t)ql);
             maxt = std::max<int32_t>(maxt, (int32_t)tl);
             ++c1;
@@ -629,9 +742,8 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
         int rc = sw_finalize_slot(e, slot, sl, cigar_buf, cigar_cap, cigar_off, cig_written, st); // chunk iter-NS
         if (rc) return rc;
         const int64_t n = c1 - c0;
-        const int64_t qb = qoff[c1] - qoff[c0], tb = toff[c1] - toff[c0];
-        // pinned staging of the rebased offsets (+ the slot's cigar-total word in front)
-        const size_t stage_bytes = 64 + sizeof(int64_t) * (size_t)(2 * (n + 1));
+        // pinned staging of the rebased offsets / slice starts and lengths (+ the slot's cigar-total word in front)
+        const size_t stage_bytes = 64 + sizeof(int64_t) * (size_t)(2 * (n + 1)) + sizeof(int32_t) * (size_t)(2 * n);
         if (e->pinned_out_cap[slot] < stage_bytes) {
             if (e->pinned_out[slot]) cudaFreeHost(e->pinned_out[slot]);
             e->pinned_out[slot] = nullptr;
@@ -641,35 +753,50 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
         }
         int64_t *total_word = reinterpret_cast<int64_t *>(e->pinned_out[slot]);
         int64_t *offs = total_word + 8;
-        for (int64_t i = 0; i <= n; ++i) { offs[i] = qoff[c0 + i] - qoff[c0]; offs[n + 1 + i] = toff[c0 + i] - toff[c0]; }
+        int32_t *lens = reinterpret_cast<int32_t *>(offs + 2 * (n + 1));
+        if (Q.len) { for (int64_t i = 0; i < n; ++i) { offs[i] = Q.off[c0 + i]; lens[i] = Q.len[c0 + i]; } offs[n] = 0; }
+        else for (int64_t i = 0; i <= n; ++i) offs[i] = Q.off[c0 + i] - Q.off[c0];
+        if (T.len) { for (int64_t i = 0; i < n; ++i) { offs[n + 1 + i] = T.off[c0 + i]; lens[n + i] = T.len[c0 + i]; } offs[2 * n + 1] = 0; }
+        else for (int64_t i = 0; i <= n; ++i) offs[n + 1 + i] = T.off[c0 + i] - T.off[c0];
         Arena &io = e->io[slot];
         io.reset();
         e->arena[slot].reset();
         const int64_t cig_bound = cigar_buf ? std::min<int64_t>(cigar_cap, qb + tb + 2 * n) : 0;
-        uint8_t *d_q = io.alloc<uint8_t>((size_t)qb + 16), *d_t = io.alloc<uint8_t>((size_t)tb + 16);
-        int64_t *d_off = io.alloc<int64_t>((size_t)(2 * (n + 1)));
+        const uint8_t *d_q = d_qsrc, *d_t = d_tsrc;
+        const int64_t qu = packed ? Q.off[c1] - Q.off[c0] : 0, tu = packed ? T.off[c1] - T.off[c0] : 0;   // pool units of this chunk
+        uint32_t *d_pk = packed ? io.alloc<uint32_t>((size_t)(qu + tu) * 4 + 16) : nullptr;
+        if (packed && !d_pk) { set_error("sw_batch_host_packed: device allocation failed"); return DB200_ERR_NOMEM; }
+        uint8_t *d_qc = Q.len ? nullptr : io.alloc<uint8_t>((size_t)qb + 16), *d_tc = T.len ? nullptr : io.alloc<uint8_t>((size_t)tb + 16);
+        if (!Q.len) d_q = d_qc;
+        if (!T.len) d_t = d_tc;
+        int64_t *d_off = io.alloc<int64_t>((size_t)(2 * (n + 1)) + (size_t)n + 2);   // + the two int32 length arrays
+        int32_t *d_lens = reinterpret_cast<int32_t *>(d_off + 2 * (n + 1));
         int32_t *d_mask = mask_len ? io.alloc<int32_t>((size_t)n) : nullptr;
         db200_sw_result *d_res = io.alloc<db200_sw_result>((size_t)n);
         int32_t *d_status = io.alloc<int32_t>((size_t)n);
         int64_t *d_coff = io.alloc<int64_t>((size_t)n + 1);
         uint32_t *d_cig = cigar_buf ? io.alloc<uint32_t>((size_t)cig_bound + 16) : nullptr;
-        if (!d_q || !d_t || !d_off || (mask_len && !d_mask) || !d_res || !d_status || !d_coff || (cigar_buf && !d_cig)) {
+        if ((!Q.len && !d_qc) || (!T.len && !d_tc) || !d_off || (mask_len && !d_mask) || !d_res || !d_status || !d_coff || (cigar_buf && !d_cig)) {
             set_error("sw_batch_host: device allocation failed");
             return DB200_ERR_NOMEM;
         }
         TlRec rec{};
         if (timeline) { for (auto &ev : rec.ev) cudaEventCreate(&ev); rec.n = n; cudaEventRecord(rec.ev[0], cst); }
         // H2D on the copy stream
-        DB200_CUDA_CHECK(cudaMemcpyAsync(d_q, qbuf + qoff[c0], (size_t)qb, cudaMemcpyHostToDevice, cst));
-        DB200_CUDA_CHECK(cudaMemcpyAsync(d_t, tbuf + toff[c0], (size_t)tb, cudaMemcpyHostToDevice, cst));
-        DB200_CUDA_CHECK(cudaMemcpyAsync(d_off, offs, sizeof(int64_t) * (size_t)(2 * (n + 1)), cudaMemcpyHostToDevice, cst));
+        if (packed) {
+            if (qu > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(d_pk, qbuf + Q.off[c0] * 16, (size_t)qu * 16, cudaMemcpyHostToDevice, cst));
+            if (tu > 0) DB200_CUDA_CHECK(cudaMemcpyAsync(d_pk + qu * 4, tbuf + T.off[c0] * 16, (size_t)tu * 16, cudaMemcpyHostToDevice, cst));
+        }
+        if (!Q.len) DB200_CUDA_CHECK(cudaMemcpyAsync(d_qc, qbuf + Q.off[c0], (size_t)qb, cudaMemcpyHostToDevice, cst));
+        if (!T.len) DB200_CUDA_CHECK(cudaMemcpyAsync(d_tc, tbuf + T.off[c0], (size_t)tb, cudaMemcpyHostToDevice, cst));
+        DB200_CUDA_CHECK(cudaMemcpyAsync(d_off, offs, sizeof(int64_t) * (size_t)(2 * (n + 1)) + sizeof(int32_t) * (size_t)(2 * n), cudaMemcpyHostToDevice, cst));
         if (mask_len) DB200_CUDA_CHECK(cudaMemcpyAsync(d_mask, mask_len + c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, cst));
         DB200_CUDA_CHECK(cudaEventRecord(e->ev_copy[slot], cst));
         DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_copy[slot], 0));
         if (timeline) { cudaEventRecord(rec.ev[1], cst); cudaEventRecord(rec.ev[2], st); }
         e->aux_set = slot;
         rc = sw_batch_device_impl(e, e->arena[slot], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, maxt, d_mask, d_res, d_cig,
-                                  cig_bound, d_coff, d_status, nullptr, st);
+                                  cig_bound, d_coff, d_status, nullptr, st, nullptr, Q.len ? d_lens : nullptr, T.len ? d_lens + n : nullptr, d_pk, qu + tu);
         if (rc) return rc;
         DB200_CUDA_CHECK(cudaMemcpyAsync(results + c0, d_res, sizeof(db200_sw_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (status) DB200_CUDA_CHECK(cudaMemcpyAsync(status + c0, d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -715,22 +842,18 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
             for (size_t g0 = 0; g0 < redo.size(); g0 += GROUP) {
                 const size_t g1 = std::min(redo.size(), g0 + GROUP);
                 std::vector<uint8_t> qb, tb;
-                std::vector<int64_t> qo(1, 0), to(1, 0);
+                std::vector<int64_t> qo, to;
                 std::vector<int32_t> ml;
-                for (size_t k = g0; k < g1; ++k) {
-                    const int64_t i = redo[k];
-                    qb.insert(qb.end(), qbuf + qoff[i], qbuf + qoff[i + 1]); qo.push_back((int64_t)qb.size());
-                    tb.insert(tb.end(), tbuf + toff[i], tbuf + toff[i + 1]); to.push_back((int64_t)tb.size());
-                    if (mask_len) ml.push_back(mask_len[i]);
-                }
+                materialise(Q, T, std::vector<int64_t>(redo.begin() + (long)g0, redo.begin() + (long)g1), mask_len, qb, qo, tb, to, ml);
                 const int64_t gn = (int64_t)(g1 - g0);
                 std::vector<db200_sw_result> r((size_t)gn);
                 std::vector<int32_t> st2((size_t)gn);
                 std::vector<int64_t> co((size_t)gn + 1);
                 std::vector<uint32_t> cg(qb.size() + tb.size() + 2 * (size_t)gn + 16);
                 in_retry = true;
-                const int rc = db200_sw_batch_host(device, params, qb.data(), qo.data(), tb.data(), to.data(), gn, mask_len ? ml.data() : nullptr,
-                                                   r.data(), cg.data(), (int64_t)cg.size(), co.data(), st2.data());
+                const HostSeqs Q2{qb.data(), qo.data(), nullptr, 0}, T2{tb.data(), to.data(), nullptr, 0};
+                const int rc = sw_batch_host_body(e, device, params, Q2, T2, gn, mask_len ? ml.data() : nullptr,
+                                                  r.data(), cg.data(), (int64_t)cg.size(), co.data(), st2.data());
                 in_retry = false;
                 if (getenv("DB200_DEBUG")) { int nb = 0; for (auto v : st2) nb += v != 0; fprintf(stderr, "[db200] retry group of %lld: rc=%d still failing=%d\n", (long long)gn, rc, nb); }
                 if (rc) return rc;

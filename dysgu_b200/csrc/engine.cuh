@@ -66,6 +66,7 @@ struct Engine {
     cudaEvent_t ev_cig[NSLOT] = {};      // cigar block of the slot's previous chunk has left its io arena
     Arena arena[NSLOT];                  // compute workspace (one per in-flight chunk)
     Arena io[NSLOT];                     // device copies of host inputs / outputs (one per in-flight chunk)
+    Arena src;                           // slices form: the shared source buffers of a host call, uploaded once
     int64_t launches = 0;
     int sm_count = 0;
     void *pinned = nullptr;              // small pinned scratch (counters read back from the device)
@@ -113,7 +114,9 @@ struct SwLink {
 int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *params, const uint8_t *d_qbuf, const int64_t *d_qoff,
                          int64_t q_bytes, const uint8_t *d_tbuf, const int64_t *d_toff, int64_t t_bytes, int64_t npairs,
                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
-                         int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st, const SwLink *link = nullptr);
+                         int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st, const SwLink *link = nullptr,
+                         const int32_t *d_qlen = nullptr, const int32_t *d_tlen = nullptr,   // slices form: q_bytes / t_bytes are the sums of the lengths
+                         const uint32_t *d_packed = nullptr, int64_t packed_units = 0);   // pre-packed form: pool units of [all queries][all targets], lengths in d_qlen / d_tlen
 
 int sw_small_host(Engine *e, const db200_sw_params *prm, const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf,
                   const int64_t *toff, int64_t npairs, const int32_t *mask_len, db200_sw_result *results, uint32_t *cigar_buf,

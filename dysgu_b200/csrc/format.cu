@@ -125,3 +125,54 @@ int db200_ed_cigar_text(const uint8_t *path_buf, const int64_t *path_off, int64_
 }
 
 }  // extern "C"
+
+// ---- host-side packing into the engine's pool format (db200_sw_batch_host_packed) ------------------------------------------
+// ASCII -> 4-bit codes of _ssw_wrapper.pyx:60-68 (A/a/U/u 0, C/c 1, G/g 2, T/t 3, anything else 4), eight bases per 32-bit word,
+// every sequence padded with code 5 to a 16-byte unit of 32 bases.  What the device's sw_pack_kernel does, for callers that
+// prepare (or cache) their batches on the host: the packed form is what should cross PCIe.
+#include <thread>
+extern "C" int db200_sw_pack_host(const uint8_t *buf, const int64_t *off, const int32_t *len, int64_t nseq, uint32_t *units,
+                                  int64_t units_cap, int64_t *unit_off, int32_t *len_out, int32_t threads)
+{
+    if (nseq < 0 || !off || !unit_off) return DB200_ERR_ARG;
+    unit_off[0] = 0;
+    for (int64_t i = 0; i < nseq; ++i) {
+        const int64_t l = len ? (int64_t)len[i] : off[i + 1] - off[i];
+        if (l < 0 || l > 0x7FFFFFF0) return DB200_ERR_ARG;
+        unit_off[i + 1] = unit_off[i] + (l + 31) / 32;
+        if (len_out) len_out[i] = (int32_t)l;
+    }
+    if (!units) return DB200_OK;                       // sizing call
+    if (unit_off[nseq] > units_cap || !buf) return DB200_ERR_CAPACITY;
+    static uint8_t code[256];
+    static bool init = false;
+    if (!init) {
+        for (int c = 0; c < 256; ++c) code[c] = 4;
+        code[(int)'A'] = code[(int)'a'] = code[(int)'U'] = code[(int)'u'] = 0;
+        code[(int)'C'] = code[(int)'c'] = 1; code[(int)'G'] = code[(int)'g'] = 2; code[(int)'T'] = code[(int)'t'] = 3;
+        init = true;
+    }
+    auto work = [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; ++i) {
+            const uint8_t *src = buf + off[i];
+            const int64_t l = len ? (int64_t)len[i] : off[i + 1] - off[i];
+            uint32_t *dst = units + unit_off[i] * 4;
+            const int64_t nwords = (unit_off[i + 1] - unit_off[i]) * 4;
+            for (int64_t w = 0; w < nwords; ++w) {
+                uint32_t x = 0x55555555u;
+                const int64_t b0 = w * 8;
+                if (b0 < l) {
+                    x = 0;
+                    for (int k = 0; k < 8; ++k) x |= (uint32_t)(b0 + k < l ? code[src[b0 + k]] : 5u) << (4 * k);
+                }
+                dst[w] = x;
+            }
+        }
+    };
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(threads > 0 ? threads : 1, nseq / 4096 + 1));
+    if (nt == 1) { work(0, nseq); return DB200_OK; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work, nseq * t / nt, nseq * (t + 1) / nt);
+    for (auto &th : pool) th.join();
+    return DB200_OK;
+}

@@ -31,13 +31,16 @@ struct PairState {          // per-pair bookkeeping of the pipeline
 // ------------------------------------------------------------------------------------------------
 // 1. sequence units + packing (ASCII -> 4-bit codes, _ssw_wrapper.pyx:60-68)
 // ------------------------------------------------------------------------------------------------
-__global__ void sw_units_kernel(const int64_t *qoff, const int64_t *toff, int64_t npairs, int32_t *units)
+// A side of the batch is either CSR (len == nullptr: sequence p = buf[off[p], off[p + 1])) or slices of a shared source
+// buffer (sequence p = buf[off[p], off[p] + len[p]): overlapping windows of one reference region, re_map.py:429-434).
+__global__ void sw_units_kernel(const int64_t *qoff, const int64_t *toff, const int32_t *qlen, const int32_t *tlen, int64_t npairs, int32_t *units)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= 2 * npairs) return;
     const int64_t *off = i < npairs ? qoff : toff;
+    const int32_t *lens = i < npairs ? qlen : tlen;
     int64_t p = i < npairs ? i : i - npairs;
-    int64_t len = off[p + 1] - off[p];
+    int64_t len = lens ? (int64_t)lens[p] : off[p + 1] - off[p];
     units[i] = (int32_t)((len + 31) >> 5);
 }
 
@@ -76,6 +79,7 @@ __device__ __forceinline__ uint32_t nt_codes4(uint32_t x)
 // one warp per sequence; each lane turns 8 bases into one 32-bit word per iteration.  The bytes arrive through two
 // aligned 64-bit loads and a funnel shift (sequences start at arbitrary byte offsets of the CSR buffer).
 __global__ void __launch_bounds__(256) sw_pack_kernel(const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf, const int64_t *toff,
+                                                      const int32_t *qlen, const int32_t *tlen,
                                                       int64_t npairs, const int64_t *unit_off, uint32_t *pool, PairMeta *meta)
 {
     const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -84,8 +88,9 @@ __global__ void __launch_bounds__(256) sw_pack_kernel(const uint8_t *qbuf, const
     const bool isq = wid < npairs;
     const int64_t p = isq ? wid : wid - npairs;
     const int64_t *off = isq ? qoff : toff;
+    const int32_t *lens = isq ? qlen : tlen;
     const uint8_t *src = (isq ? qbuf : tbuf) + off[p];
-    const int64_t len = off[p + 1] - off[p];
+    const int64_t len = lens ? (int64_t)lens[p] : off[p + 1] - off[p];
     const int64_t u0 = unit_off[wid];
     const int64_t nwords = ((len + 31) >> 5) << 2;
     const int64_t fullw = (len + 7) >> 3;          // words holding at least one base
@@ -117,6 +122,17 @@ __global__ void __launch_bounds__(256) sw_pack_kernel(const uint8_t *qbuf, const
         if (isq) { meta[p].q_unit = (uint32_t)u0; meta[p].m = (int32_t)len; }
         else { meta[p].t_unit = (uint32_t)u0; meta[p].n = (int32_t)len; }
     }
+}
+
+// pre-packed input (db200_sw_batch_*_packed): the pool content arrived as is, only the pair records are built here
+__global__ void sw_meta_kernel(const int32_t *qlen, const int32_t *tlen, int64_t npairs, const int64_t *unit_off, PairMeta *meta)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    PairMeta pm;
+    pm.q_unit = (uint32_t)unit_off[p]; pm.m = qlen[p];
+    pm.t_unit = (uint32_t)unit_off[npairs + p]; pm.n = tlen[p];
+    meta[p] = pm;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -687,7 +703,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
                          int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len, db200_sw_result *d_results,
                          uint32_t *d_cigar_buf,
                          int64_t cigar_cap, int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, cudaStream_t st,
-                         const SwLink *link)
+                         const SwLink *link, const int32_t *d_qlen, const int32_t *d_tlen, const uint32_t *d_packed, int64_t packed_units)
 {
     if (npairs < 0 || !prm || !d_results) { set_error("sw_batch: bad arguments"); return DB200_ERR_ARG; }
     if (prm->gap_open <= 0 || prm->gap_extend <= 0 || prm->gap_open > 255 || prm->gap_extend > 255) {
@@ -821,10 +837,18 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
 
     // 1. pack ---------------------------------------------------------------------------------------
     prof_mark(e, st, ST_BEGIN);
-    sw_units_kernel<<<gseq, TB, 0, st>>>(d_qoff, d_toff, npairs, units);
+    sw_units_kernel<<<gseq, TB, 0, st>>>(d_qoff, d_toff, d_qlen, d_tlen, npairs, units);
     count_launch(e);
     exclusive_scan_i32_i64(e, units, unit_off, nseq, scan_tmp, st);
-    sw_pack_kernel<<<gwarp_seq, TB, 0, st>>>(d_qbuf, d_qoff, d_tbuf, d_toff, npairs, unit_off, pool, meta);
+    if (d_packed) {
+        // the caller's batch is already in pool format ([all queries][all targets], 32 bases per 16-byte unit): one device copy
+        // instead of the pack kernel; q_bytes / t_bytes are base counts, so the units are bounded by seq_units
+        if (packed_units < 0 || (size_t)packed_units > seq_units) { set_error("sw_batch: packed unit count does not match the lengths"); return DB200_ERR_ARG; }
+        DB200_CUDA_CHECK(cudaMemcpyAsync(pool, d_packed, (size_t)packed_units * 16, cudaMemcpyDeviceToDevice, st));
+        sw_meta_kernel<<<gpair, TB, 0, st>>>(d_qlen, d_tlen, npairs, unit_off, meta);
+    } else {
+        sw_pack_kernel<<<gwarp_seq, TB, 0, st>>>(d_qbuf, d_qoff, d_tbuf, d_toff, d_qlen, d_tlen, npairs, unit_off, pool, meta);
+    }
     count_launch(e);
 
     prof_mark(e, st, ST_PACK);

@@ -152,6 +152,37 @@ int db200_sw_batch_device(int device, const db200_sw_params *params,
                           int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, void *stream);
 
 /*
+ * Other host input forms of the same call (results, cigars and status exactly as db200_sw_batch_host):
+ *
+ * db200_sw_batch_host_slices - sequences are (start, length) views of shared source buffers that travel to the device once
+ *   per call: the shape dysgu's remapping has, one reference region fetched per group of events and many windows cut out
+ *   of it, overlapping freely (re_map.py:429-434, 192-199).  A side whose length array is NULL is plain CSR (its start
+ *   array is then offsets[npairs + 1]).
+ *
+ * db200_sw_batch_host_packed - both sides pre-encoded in the engine's pool format: 4-bit codes (A/a/U/u 0, C/c 1, G/g 2,
+ *   T/t 3, other 4; padding 5 - the table of _ssw_wrapper.pyx:60-68), eight bases per 32-bit word, every sequence padded
+ *   to a 16-byte unit of 32 bases.  The reference's C boundary takes encoded sequences too (int8 codes, ssw.h:72-125; the
+ *   wrapper encodes, _ssw_wrapper.pyx:668-679); this encoding is half a byte per base, so a batch crosses PCIe at half the
+ *   bytes of ASCII and lands in the device pool without a pack kernel.  unit_off[npairs + 1] count 16-byte units and must
+ *   be dense (unit_off[i + 1] - unit_off[i] == ceil(len[i] / 32)); db200_sw_pack_host writes this format from ASCII
+ *   (CSR when len == NULL, else slices; `units` == NULL only sizes: unit_off and len_out are filled).
+ */
+int db200_sw_batch_host_slices(int device, const db200_sw_params *params,
+                               const uint8_t *qsrc, int64_t qsrc_bytes, const int64_t *qstart, const int32_t *qlen,
+                               const uint8_t *tsrc, int64_t tsrc_bytes, const int64_t *tstart, const int32_t *tlen,
+                               int64_t npairs, const int32_t *mask_len,
+                               db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap,
+                               int64_t *cigar_off, int32_t *status);
+int db200_sw_batch_host_packed(int device, const db200_sw_params *params,
+                               const uint32_t *qunits, const int64_t *qunit_off, const int32_t *qlen,
+                               const uint32_t *tunits, const int64_t *tunit_off, const int32_t *tlen,
+                               int64_t npairs, const int32_t *mask_len,
+                               db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap,
+                               int64_t *cigar_off, int32_t *status);
+int db200_sw_pack_host(const uint8_t *buf, const int64_t *off, const int32_t *len, int64_t nseq,
+                       uint32_t *units, int64_t units_cap, int64_t *unit_off, int32_t *len_out, int32_t threads);
+
+/*
  * Legacy single-pair entry points with the reference's signatures (ssw.h:72-125), implemented as
  * "batch of one" so that an unmodified Cython wrapper can link against this library.
  * `read` / `ref` are already-encoded int8 codes (0..4) as produced by the wrapper.

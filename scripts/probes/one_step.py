@@ -1,5 +1,7 @@
+"""Two device-resident steps of the headline workload and nothing else (for ncu passes: scripts/forward_traffic.sh)."""
 import sys, ctypes as C
-sys.path.insert(0,'/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from dysgu_b200 import _lib
 import bench

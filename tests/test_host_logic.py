@@ -141,3 +141,21 @@ def test_install_routes_dysgu_imports(tmp_path, monkeypatch):
     finally:
         for name in [n for n in sys.modules if n == "dysgu" or n.startswith("dysgu.")]:
             sys.modules.pop(name, None)
+
+
+def test_host_packer_writes_the_pool_format():
+    """db200_sw_pack_host: codes of _ssw_wrapper.pyx:60-68 as nibbles, 8 per word, sequences padded with code 5 to 32 bases."""
+    from dysgu_b200 import batch
+    seqs = [b"ACGTNacgtnUu-xyz", b"", b"A", b"ACGT" * 8, b"ACGT" * 8 + b"C", b"T" * 70]
+    p = batch.pack_seqs(seqs, threads=3)
+    tab = np.full(256, 4, np.uint8)
+    for ch, c in zip(b"AaUuCcGgTt", [0, 0, 0, 0, 1, 1, 2, 2, 3, 3]):
+        tab[ch] = c
+    assert list(p.lengths) == [len(s) for s in seqs]
+    for i, s in enumerate(seqs):
+        nu = int(p.unit_off[i + 1] - p.unit_off[i])
+        assert nu == (len(s) + 31) // 32
+        w = p.units[p.unit_off[i] * 4:p.unit_off[i + 1] * 4]
+        nib = np.array([(int(w[k >> 3]) >> ((k & 7) * 4)) & 15 for k in range(nu * 32)], dtype=np.uint8)
+        exp = np.concatenate([tab[np.frombuffer(s, np.uint8)], np.full(nu * 32 - len(s), 5, np.uint8)]) if nu else np.zeros(0, np.uint8)
+        assert np.array_equal(nib, exp), i
