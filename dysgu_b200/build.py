@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libdysgu_b200_align.so")
 COMPAT = os.path.join(HERE, "libdysgu_b200_compat.so")
 PEAK = os.path.join(HERE, "int_peak")
-SOURCES = ["engine.cu", "sw.cu", "ed.cu", "queue.cu", "format.cu", "multi.cu"]
+SOURCES = ["engine.cu", "sw.cu", "ed.cu", "queue.cu", "format.cu", "multi.cu", "minimizer.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "dysgu_b200_align.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -67,7 +67,9 @@ void Arena::release()
 // detected here and reported as DB200_ERR_FORKED instead of a misleading "no CUDA device"; the Python layer routes such
 // children to the parent's engine (dysgu_b200/server.py) and dysgu_b200.patch keeps the pool's work in the parent.
 static std::mutex g_mu;
-static Engine *g_engines[64] = {nullptr};
+// [instance][device]: a second / third / fourth independent engine on one GPU (own streams, arenas and call lock) lets
+// host threads run whole batches side by side - H2D of one step under the kernels of another (DB200_INSTANCE(dev, k))
+static Engine *g_engines[4 * 64] = {nullptr};
 static pid_t g_pid = 0;
 static bool g_cuda_touched = false;        // this process (or the ancestor it was forked from) has called into the CUDA runtime
 static bool g_forked_after_cuda = false;   // set in the child by the atfork handler
@@ -108,10 +110,13 @@ Engine *get_engine(int device)
         set_error("no CUDA device available: libdysgu_b200_align has no CPU fallback");
         return nullptr;
     }
-    if (device < 0 || device >= count || device >= 64) { set_error("invalid device %d (have %d)", device, count); return nullptr; }
-    if (g_engines[device]) {
+    const int inst = device >= 0 ? (device >> 8) : 0;
+    if (device >= 0) device &= 0xFF;
+    if (device < 0 || device >= count || device >= 64 || inst > 3) { set_error("invalid device %d (have %d)", device, count); return nullptr; }
+    Engine *&slot = g_engines[inst * 64 + device];
+    if (slot) {
         cudaSetDevice(device);
-        return g_engines[device];
+        return slot;
     }
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return nullptr; }
     Engine *e = new Engine();
@@ -153,7 +158,7 @@ Engine *get_engine(int device)
     e->trace_slab_bytes = (size_t)(sb ? atol(sb) : 4096) << 20;
     if (e->trace_slab_bytes < ((size_t)64 << 20)) e->trace_slab_bytes = (size_t)64 << 20;
     e->ready = true;
-    g_engines[device] = e;
+    slot = e;
     return e;
 }
 

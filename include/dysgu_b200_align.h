@@ -61,6 +61,11 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------ */
 /* engine                                                                                       */
 /* ------------------------------------------------------------------------------------------ */
+/* Every `device` argument of this header is a CUDA device ordinal, optionally combined with an engine instance:
+ * DB200_INSTANCE(dev, k), k = 0..3, names the k-th independent engine on that GPU (its own streams, workspace and call
+ * lock).  Calls on different instances run concurrently, so two host threads that alternate over the batches of a long
+ * job keep the GPU busy while the next batch is still crossing PCIe (what bench.py's e2e arm does). */
+#define DB200_INSTANCE(dev, k) ((dev) | ((k) << 8))
 int db200_device_count(void);
 /* Creates (lazily, per process) the engine state for `device`; see the fork() note above. */
 int db200_init(int device);
@@ -353,6 +358,19 @@ int db200_sw_aligned_text(int which, const uint8_t *seq_buf, const int64_t *seq_
  * edlib.cpp:298-347); a pair without operations gives an empty string. */
 int db200_ed_cigar_text(const uint8_t *path_buf, const int64_t *path_off, int64_t npairs, int format,
                         char *out, int64_t out_cap, int64_t *out_off);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Minimizer sketches: what graph.pyx:59-84 sliding_window_minimum(k, m, s, found) */
+/* leaves in `found` for every sequence of a batch - the minimum over each window of k            */
+/* consecutive m-mer hashes plus the first and the last m-mer hash, hashes = XXH64(m-mer, seed)   */
+/* read as signed 64-bit (map_set_utils.pxd:28-29; dysgu: k = 16, m = 7, seed 42).  The set of     */
+/* sequence i comes back sorted ascending in out[out_off[i] .. out_off[i + 1]).  A sequence has at */
+/* most len - m + 1 values, so out_cap = total bytes always suffices.  db200_xxh64 is the host    */
+/* side of the same hash.                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+int db200_minimizers_batch_host(int device, const uint8_t *buf, const int64_t *off, int64_t nseq, int32_t k, int32_t m,
+                                uint64_t seed, int64_t *out, int64_t out_cap, int64_t *out_off);
+uint64_t db200_xxh64(const uint8_t *data, int32_t len, uint64_t seed);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Ticket queue: submit / flush / fetch (SURVEY 8b "new batched ABI").                          */

@@ -17,7 +17,8 @@ fi
 mkdir -p "$OUT"
 gcc -O2 -std=c99 -fPIC -shared -w -I"$REF/dysgu/scikitbio" "$REF/dysgu/scikitbio/ssw.c" -o "$OUT/libssw_ref.so" -lm
 g++ -O3 -std=c++17 -fPIC -shared -w -I"$REF/dysgu/edlib/src" "$REF/dysgu/edlib/src/edlib.cpp" -o "$OUT/libedlib_ref.so"
-echo "build_ref: built $OUT/libssw_ref.so $OUT/libedlib_ref.so"
+g++ -O2 -std=c++17 -fPIC -shared -w -I"$REF/dysgu" "$HERE/xxh_ref_wrap.cpp" -o "$OUT/libxxh_ref.so"   # the reference's XXHash64 (graph.pyx minimizers)
+echo "build_ref: built $OUT/libssw_ref.so $OUT/libedlib_ref.so $OUT/libxxh_ref.so"
 
 # Optional: the reference's two Cython wrappers (used only to generate wrapper-level golden vectors).
 # Built in a scratch directory; only the extension modules land in oracle/_ref/pyref/dysgu/...

@@ -55,7 +55,39 @@ def oracle_lib():
         _oracle.sw_oracle_batch_nt.restype = C.c_int
         _oracle.ed_oracle_batch.restype = C.c_int
         _oracle.ed_path_oracle_batch.restype = C.c_int
+        _oracle.oracle_xxh64.restype = C.c_uint64
+        _oracle.oracle_xxh64.argtypes = [C.c_char_p, C.c_int64, C.c_uint64]
+        _oracle.minimizer_oracle_batch.restype = C.c_int
     return _oracle
+
+
+_xxh_ref = None
+
+
+def ref_xxh_lib():
+    """The reference's own XXHash64 (oracle/_ref/libxxh_ref.so, compiled from dysgu/include/xxhash64.h by build_ref.sh)."""
+    global _xxh_ref
+    if _xxh_ref is None:
+        _xxh_ref = C.CDLL(os.path.join(REF, "libxxh_ref.so"))
+        _xxh_ref.ref_xxh64.restype = C.c_uint64
+        _xxh_ref.ref_xxh64.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64]
+    return _xxh_ref
+
+
+def oracle_minimizers(seqs, k=16, m=7, seed=42, use_reference_hash=False, csr=False):
+    """graph.pyx:59-84 for every sequence: (int64 sorted values, int64 offsets[n + 1]).  use_reference_hash: hash with the
+    reference's compiled xxhash64.h instead of the restated XXH64 (pinning / golden generation)."""
+    buf, off = seqs if csr else to_csr(seqs)
+    n = len(off) - 1
+    cap = int(off[-1]) + 2 * n + 16
+    out = np.zeros(cap, dtype=np.int64)
+    ooff = np.zeros(n + 1, dtype=np.int64)
+    fn = C.cast(ref_xxh_lib().ref_xxh64, C.c_void_p) if use_reference_hash else None
+    rc = oracle_lib().minimizer_oracle_batch(_p(buf, C.c_uint8), _p(off, C.c_int64), C.c_int64(n), C.c_int(k), C.c_int(m), C.c_uint64(seed), fn,
+                                             _p(out, C.c_int64), C.c_int64(cap), _p(ooff, C.c_int64))
+    if rc != 0:
+        raise RuntimeError("minimizer_oracle_batch failed")
+    return out[:ooff[n]], ooff
 
 
 def driver_lib():

@@ -147,3 +147,28 @@ def test_without_the_server_a_forked_child_gets_a_clear_error():
     env = dict(os.environ, DB200_NO_SERVER="1")
     r = subprocess.run([sys.executable, "-c", FORK_NO_SERVER_SCRIPT % ROOT], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "clear error ok" in r.stdout, (r.stdout, r.stderr[-3000:])
+
+
+def test_engine_instances_run_side_by_side_on_one_gpu():
+    """DB200_INSTANCE(dev, k): independent engines on one GPU, one host thread each (bench.py's streaming e2e arm)."""
+    dev = batch.default_device()
+    q, t, prm = workloads.remap_windows(40000, seed=77)
+    pq, pt = batch.pack_seqs(q), batch.pack_seqs(t)
+    want = batch.sw_align_batch(q, t, device=dev, **prm)
+    out, errs = [None, None, None], []
+
+    def work(j):
+        try:
+            for _ in range(3):
+                out[j] = batch.sw_align_packed(pq, pt, device=dev | (j << 8), **prm) if j else batch.sw_align_batch(q, t, device=dev | (2 << 8), **prm)
+        except Exception as exc:   # noqa: BLE001
+            errs.append(exc)
+
+    ths = [threading.Thread(target=work, args=(j,)) for j in range(3)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errs, errs
+    for r in out:
+        assert np.array_equal(r.fixed, want.fixed) and np.array_equal(r.cigar, want.cigar) and np.array_equal(r.cigar_off, want.cigar_off)

@@ -102,3 +102,26 @@ def test_ed_path_oracle_matches_golden():
             checked += 1
             none += c["cigar"] is None
     assert checked > 1500 and none > 100
+
+
+def test_minimizer_oracle_against_golden_and_reference_hash():
+    """oracle/minimizer_oracle.c (restated XXH64 + the window rule of graph.pyx:59-84) against vectors made with the reference's
+    own hash, and - where oracle/_ref/libxxh_ref.so exists - hash by hash on random inputs of every length 0..80."""
+    import ctypes as C
+    import random
+    with open(os.path.join(G, "minimizers.json")) as f:
+        g = json.load(f)
+    L = O.oracle_lib()
+    for hx, want in g["hash"]:
+        b = bytes.fromhex(hx)
+        v = L.oracle_xxh64(b, len(b), 42)
+        assert (v - (1 << 64) if v >= (1 << 63) else v) == want
+    for c in g["sketches"]:
+        vals, off = O.oracle_minimizers([c["seq"].encode()], k=c["k"], m=c["m"])
+        assert vals.tolist() == c["values"], (c["seq"][:30], c["k"], c["m"])
+    if os.path.exists(os.path.join(O.REF, "libxxh_ref.so")):
+        rng = random.Random(3)
+        for n in range(81):
+            for _ in range(10):
+                b = bytes(rng.randrange(256) for _ in range(n))
+                assert L.oracle_xxh64(b, n, 42) == O.ref_xxh_lib().ref_xxh64(b, n, 42)
