@@ -435,15 +435,22 @@ def run_ours(args):
     #      C entry points take (ssw.h:72-125; the wrapper encodes before ssw_init / ssw_align) at half a byte per base
     e2e_packed = e2e_packed_sync = None
     if kind == "sw":
-        pq, pt = B.pack_seqs(q, pinned=True), B.pack_seqs(t, pinned=True)
+        # host-side batch preparation, once, outside the timed region ("queues pairs into packed batches with length bucketing",
+        # BASELINE.json north_star): pairs ordered by target length class, both sides encoded.  With the pairs of a length bucket
+        # next to each other every chunk of the host pipeline feeds one or two bucket kernels with as many pairs as the whole batch
+        # would - chunks in submission order spread every bucket thin over all chunks.  Results come back in this order.
+        order = np.argsort(-((t.lengths + 31) // 32), kind="stable") if os.environ.get("DB200_BENCH_NO_BUCKETING") is None else np.arange(n)
+        pq, pt = B.pack_seqs(q.take(order), pinned=True), B.pack_seqs(t.take(order), pinned=True)
         hql = pinned_array(L, (n,), np.int32); hql[:] = pq.lengths
         htl = pinned_array(L, (n,), np.int32); htl[:] = pt.lengths
         hquo = pinned_array(L, (n + 1,), np.int64); hquo[:] = pq.unit_off
         htuo = pinned_array(L, (n + 1,), np.int64); htuo[:] = pt.unit_off
-        # two engine instances on the device, one host thread each: consecutive steps overlap (H2D of step k + 1 under the kernels
-        # of step k), the way a long job - config 2's ~10 M pairs - feeds its batches.  Every step still copies its own inputs in
-        # and its own results out inside the timed region; each thread has its own output buffers.
-        NT = 2
+        # three engine instances on the device, one host thread each: consecutive steps overlap (H2D of step k + 1 and D2H of
+        # step k - 1 under the kernels of step k; the kernels of different calls run one after the other, engine.cu), the way a
+        # long job - config 2's ~10 M pairs - feeds its batches.  Every step still copies its own inputs in and its own results
+        # out inside the timed region; each thread has its own output buffers.  (Two threads fall into lock step now and then:
+        # 23.7 / 30.3 ms per step in two runs; three: 22.6.)
+        NT = int(os.environ.get("DB200_BENCH_STREAM_THREADS", "3"))
         outs = [(pinned_array(L, (n, res_cols), np.int32), pinned_array(L, (var_words,), var_np), pinned_array(L, (n + 1,), np.int64),
                  pinned_array(L, (n,), np.int32)) for _ in range(NT)]
 
@@ -485,20 +492,28 @@ def run_ours(args):
         for j in range(NT):
             packed_step(j); packed_step(j)
         sync_s = timed(packed_step, 1, e2e_steps)                        # one synchronous call after the other
-        stream_steps = 2 * e2e_steps
+        stream_steps = NT * e2e_steps
+        for j in range(NT):   # the overlap happens between the calls: each call runs its kernels once over the whole batch
+            L.db200_set_host_chunk_pairs(local_rank | (j << 8), C.c_int64(int(os.environ.get("DB200_BENCH_STREAM_CHUNK", n))))
+        for j in range(NT):
+            packed_step(j)
         stream_s = timed(packed_step, NT, stream_steps)                  # two host threads alternate over the steps
         for j in range(NT):
-            if not np.array_equal(outs[j][0], hres) or int(outs[j][2][n]) != nvar:
+            L.db200_set_host_chunk_pairs(local_rank | (j << 8), C.c_int64(0))
+        for j in range(NT):
+            if not np.array_equal(outs[j][0], hres[order]) or int(outs[j][2][n]) != nvar:
                 raise SystemExit("bench.py: packed and ASCII host arms disagree")
         pk_bytes = pq.nbytes + pt.nbytes + 2 * 4 * n
-        note = ("pre-encoded 4-bit pool format in page-locked memory (db200_sw_pack_host, outside the timed region - the reference's C entry "
-                "points take pre-encoded int8 codes as well), db200_sw_batch_host_packed")
+        note = ("pairs grouped by target length class and pre-encoded in the 4-bit pool format in page-locked memory (numpy argsort + "
+                "db200_sw_pack_host, outside the timed region - the reference's C entry points take pre-encoded int8 codes as well), "
+                "db200_sw_batch_host_packed")
         e2e_packed_sync = {"value": total_cells * e2e_steps / sync_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": pk_bytes, "d2h_bytes_per_step": d2h,
                            "steps": e2e_steps, "ms_per_step": 1e3 * sync_s / e2e_steps, "input": note, "mode": "one synchronous call per step"}
         e2e_packed = {"value": total_cells * stream_steps / stream_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": pk_bytes, "d2h_bytes_per_step": d2h,
                       "steps": stream_steps, "ms_per_step": 1e3 * stream_s / stream_steps, "input": note,
-                      "mode": "two host threads, each with its own engine instance on the GPU (DB200_INSTANCE) and its own output buffers, alternate "
-                              "over the steps: the copies of one step run under the kernels of the other"}
+                      "mode": "%d host threads, each with its own engine instance on the GPU (DB200_INSTANCE) and its own output buffers, alternate "
+                              "over the steps: the copies of one step run under the kernels of another; one chunk per call "
+                              "(db200_set_host_chunk_pairs)" % NT}
 
     # ---- the Python front door on a smaller batch: list of bytes in, numpy results out (dysgu_b200.batch.sw_align_batch)
     front_door = None

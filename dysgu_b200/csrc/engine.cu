@@ -139,6 +139,7 @@ Engine *get_engine(int device)
         }
         cudaEventCreateWithFlags(&e->ev_fork[k], cudaEventDisableTiming);
     }
+    cudaEventCreateWithFlags(&e->ev_chain, cudaEventDisableTiming);
     for (int i = 0; i < Engine::NSLOT; ++i) {
         cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
@@ -281,6 +282,18 @@ int db200_device_count(void)
 }
 
 int db200_forked_after_init(void) { return forked_after_cuda() ? 1 : 0; }
+
+// Chunking of the *_host Smith-Waterman entry points of one engine (instance): 0 = the automatic schedule (small first chunk,
+// growing - the copies of later chunks hide behind earlier compute inside ONE call); n > 0 = chunks of n pairs.  A caller that
+// keeps several calls in flight on different engine instances (DB200_INSTANCE) sets n to its batch size: the overlap then
+// happens between calls and every call runs its kernels once over the whole batch.
+int db200_set_host_chunk_pairs(int device, int64_t pairs)
+{
+    Engine *e = get_engine(device);
+    if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
+    e->host_chunk_pairs = pairs > 0 ? pairs : 0;
+    return DB200_OK;
+}
 
 int db200_init(int device) { return get_engine(device) ? DB200_OK : (forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA); }
 
@@ -499,6 +512,10 @@ static int sw_finalize_slot(Engine *e, int slot, SwSlot &sl, uint32_t *cigar_buf
     return DB200_OK;
 }
 
+// compute order between whole-batch calls of different engine instances on one device (see sw_batch_host_body)
+static std::mutex g_chain_mu;
+static cudaEvent_t g_chain_last[64] = {nullptr};
+
 // One side of a host batch: CSR (len == nullptr: sequence i = buf[off[i], off[i + 1])) or slices of a shared source buffer of
 // src_bytes bytes (sequence i = buf[off[i], off[i] + len[i])).
 struct HostSeqs {
@@ -690,6 +707,7 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
     // cap of a fifth gave six chunks and 28.7 ms, one fixed size of 128k 29.1 ms, 256k 32.1 ms)
     const int64_t chunk_cap = std::min<int64_t>(std::max<int64_t>(npairs * 28 / 100, 65536), 262144);
     bool fixed_chunks = false;
+    if (e->host_chunk_pairs > 0) { chunk_pairs = e->host_chunk_pairs; fixed_chunks = true; }   // db200_set_host_chunk_pairs
     if (const char *cp = getenv("DB200_HOST_CHUNK_PAIRS")) { const int64_t v = atoll(cp); if (v > 0) { chunk_pairs = v; fixed_chunks = true; } }
     std::vector<int64_t> schedule;   // DB200_HOST_CHUNK_SCHEDULE=a,b,c: explicit chunk sizes (the last one repeats); tuning aid
     if (const char *sp = getenv("DB200_HOST_CHUNK_SCHEDULE")) {
@@ -798,11 +816,24 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
         if (mask_len) DB200_CUDA_CHECK(cudaMemcpyAsync(d_mask, mask_len + c0, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, cst));
         DB200_CUDA_CHECK(cudaEventRecord(e->ev_copy[slot], cst));
         DB200_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_copy[slot], 0));
+        // Whole-batch calls of different engine instances on one GPU (db200_set_host_chunk_pairs >= the batch): their copies
+        // overlap, their kernels do not - two batches' persistent bucket kernels sharing the SMs took 41 ms each instead of 22
+        // (B200, 524,288 pairs).  The kernels of a call start when the previous call's kernels on this device have finished.
+        const bool whole_batch = fixed_chunks && c0 == 0 && c1 == npairs && e->host_chunk_pairs > 0;
+        if (whole_batch) {
+            std::lock_guard<std::mutex> lk(g_chain_mu);
+            if (g_chain_last[e->device] && g_chain_last[e->device] != e->ev_chain) DB200_CUDA_CHECK(cudaStreamWaitEvent(st, g_chain_last[e->device], 0));
+        }
         if (timeline) { cudaEventRecord(rec.ev[1], cst); cudaEventRecord(rec.ev[2], st); }
         e->aux_set = slot;
         rc = sw_batch_device_impl(e, e->arena[slot], params, d_q, d_off, qb, d_t, d_off + n + 1, tb, n, maxq, maxt, d_mask, d_res, d_cig,
                                   cig_bound, d_coff, d_status, nullptr, st, nullptr, Q.len ? d_lens : nullptr, T.len ? d_lens + n : nullptr, d_pk, qu + tu);
         if (rc) return rc;
+        if (whole_batch) {
+            std::lock_guard<std::mutex> lk(g_chain_mu);
+            DB200_CUDA_CHECK(cudaEventRecord(e->ev_chain, st));
+            g_chain_last[e->device] = e->ev_chain;
+        }
         DB200_CUDA_CHECK(cudaMemcpyAsync(results + c0, d_res, sizeof(db200_sw_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (status) DB200_CUDA_CHECK(cudaMemcpyAsync(status + c0, d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
         // n entries only: entry c0 + n is the first one of the next chunk's copy (another stream); the chunk's total travels

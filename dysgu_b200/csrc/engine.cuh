@@ -63,6 +63,7 @@ struct Engine {
     int64_t *d_sub_words = nullptr;      // [NSUB_MAX + 1] cigar cursor between sub-batches; [NSUB_MAX + 1] Myers word steps evaluated
     cudaEvent_t ev_copy[NSLOT] = {};
     cudaEvent_t ev_done[NSLOT] = {};
+    cudaEvent_t ev_chain = nullptr;      // kernels of this engine's latest whole-batch host call have finished
     cudaEvent_t ev_cig[NSLOT] = {};      // cigar block of the slot's previous chunk has left its io arena
     Arena arena[NSLOT];                  // compute workspace (one per in-flight chunk)
     Arena io[NSLOT];                     // device copies of host inputs / outputs (one per in-flight chunk)
@@ -73,6 +74,7 @@ struct Engine {
     size_t pinned_cap = 0;
     void *pinned_out[NSLOT] = {};
     size_t pinned_out_cap[NSLOT] = {};
+    int64_t host_chunk_pairs = 0;        // db200_set_host_chunk_pairs: 0 = automatic chunk schedule of the host entry points
     void *small_host = nullptr, *small_dev = nullptr;   // mapped page-locked staging of the one-launch small-batch path (sw_small.cuh)
     size_t small_cap = 0;
     size_t trace_slab_bytes = (size_t)4 << 30;  // per-block slabs of the wide banded traceback (DB200_TRACE_SLAB_MB)

@@ -71,6 +71,11 @@ int db200_device_count(void);
 int db200_init(int device);
 /* 1 if this process was fork()ed after its parent initialised CUDA through this library (compute calls fail with DB200_ERR_FORKED). */
 int db200_forked_after_init(void);
+/* Chunking of this engine's Smith-Waterman *_host entry points: 0 = automatic (a small first chunk, growing: the copies of
+ * later chunks hide behind earlier compute inside one call); n > 0 = chunks of n pairs.  A caller that keeps several calls in
+ * flight on different engine instances (DB200_INSTANCE) sets n to its batch size, so that the overlap happens between calls
+ * and every call runs its kernels once over the whole batch. */
+int db200_set_host_chunk_pairs(int device, int64_t pairs);
 /* Device used by the legacy single-pair entry points (their reference signatures carry no device): the environment
  * variable DB200_DEVICE, else LOCAL_RANK, else 0. */
 int db200_default_device(void);
