@@ -262,6 +262,80 @@ def run_reference(args):
     return 0
 
 
+
+def merge_shape_figure(L, B, torch, dev, dist, local_rank, rank, world, steps=3, pairs=8192):
+    """BASELINE configs 4/5 beside the headline, so that the driver's 1/2/4/8-GPU sweep covers the merge shape as well: long-read
+    contig pairs 1-10 kb (ONT error) through check_contig_match's scoring (2,-3,10,1), score + coordinates + cigar, pairs sharded
+    by rank.  Device-timed GCUPS (inputs resident) and end to end through db200_sw_batch_host_packed (one synchronous call per
+    step).  Max over ranks, whole-job aggregate."""
+    from dysgu_b200 import _lib
+    q, t, prm, cells = make_workload(pairs, 20261121 + rank, "long_contigs")
+    n = len(q)
+    prm_c = _lib.SwParams()
+    prm_c.match, prm_c.mismatch, prm_c.gap_open, prm_c.gap_extend = prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"]
+    prm_c.score_size, prm_c.flag = 2, 1
+    qb, tb = int(q.off[-1]), int(t.off[-1])
+    cap = qb + tb + 2 * n + 16
+    d_q, d_t = torch.from_numpy(q.buf).to(dev), torch.from_numpy(t.buf).to(dev)
+    d_qo, d_to = torch.from_numpy(q.off).to(dev), torch.from_numpy(t.off).to(dev)
+    d_res = torch.zeros((n, 8), dtype=torch.int32, device=dev)
+    d_cig = torch.zeros(cap, dtype=torch.int32, device=dev)
+    d_co = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def dstep():
+        _lib.check(L.db200_sw_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qo.data_ptr(), qb, d_t.data_ptr(), d_to.data_ptr(), tb, n,
+                                           int(q.lengths.max()), int(t.lengths.max()), None, d_res.data_ptr(), d_cig.data_ptr(), cap,
+                                           d_co.data_ptr(), d_st.data_ptr(), None, C.c_void_p(stream.cuda_stream)), "db200_sw_batch_device")
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(2):
+        dstep()
+    barrier()
+    if int((d_st != 0).sum().item()):
+        raise SystemExit("bench.py: merge shape reported a non-zero status")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        dstep()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    tc = torch.tensor([cells], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+    pq, pt = B.pack_seqs(q, pinned=True), B.pack_seqs(t, pinned=True)
+    hres = pinned_array(L, (n, 8), np.int32); hcig = pinned_array(L, (cap,), np.uint32)
+    hco = pinned_array(L, (n + 1,), np.int64); hst = pinned_array(L, (n,), np.int32)
+    ql, tl = np.ascontiguousarray(pq.lengths), np.ascontiguousarray(pt.lengths)
+
+    def hstep():
+        _lib.check(L.db200_sw_batch_host_packed(local_rank, C.byref(prm_c), pq.units.ctypes.data, pq.unit_off.ctypes.data, ql.ctypes.data,
+                                                pt.units.ctypes.data, pt.unit_off.ctypes.data, tl.ctypes.data, n, None, hres.ctypes.data,
+                                                hcig.ctypes.data, cap, hco.ctypes.data, hst.ctypes.data), "db200_sw_batch_host_packed")
+    hstep()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hstep()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if not np.array_equal(hres[:, :7], d_res.cpu().numpy()[:, :7]):
+        raise SystemExit("bench.py: merge shape: host and device arms disagree")
+    return {"workload": WORKLOADS["long_contigs"][4], "pairs_per_step_per_gpu": n, "value": float(tc.item()) * steps / (float(ms.item()) * 1e-3) / 1e9,
+            "unit": UNIT, "ms_per_step": float(ms.item()) / steps,
+            "e2e": {"value": float(tc.item()) * steps / float(dt.item()) / 1e9, "unit": UNIT, "ms_per_step": 1e3 * float(dt.item()) / steps,
+                    "h2d_bytes_per_step": pq.nbytes + pt.nbytes + 8 * n, "d2h_bytes_per_step": int(32 * n + 12 * n + 4 * int(hco[n]))}}
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -309,6 +383,17 @@ def run_ours(args):
     want_path = kind == "ed" and prm["task"] == "path"
     path_cap = q_bytes + t_bytes + 16
 
+    # ---- host-side batch preparation for the Smith-Waterman workloads, once, outside every timed region: pairs ordered by target
+    #      length class and both sides encoded in the 4-bit pool format (db200_sw_pack_host)
+    order = pq = pt = None
+    if kind == "sw":
+        order = np.argsort(-((t.lengths + 31) // 32), kind="stable") if os.environ.get("DB200_BENCH_NO_BUCKETING") is None else np.arange(n)
+        pq, pt = B.pack_seqs(q.take(order), pinned=True), B.pack_seqs(t.take(order), pinned=True)
+        d_units = torch.from_numpy(np.concatenate([pq.units[:int(pq.unit_off[-1]) * 4], pt.units[:int(pt.unit_off[-1]) * 4]]).view(np.int32)).to(dev)
+        d_qlen = torch.from_numpy(np.ascontiguousarray(pq.lengths)).to(dev)
+        d_tlen = torch.from_numpy(np.ascontiguousarray(pt.lengths)).to(dev)
+        n_units = int(pq.unit_off[-1] + pt.unit_off[-1])
+
     # ---- device-resident arm --------------------------------------------------------------------------
     d_q = torch.from_numpy(q.buf).to(dev)
     d_t = torch.from_numpy(t.buf).to(dev)
@@ -323,10 +408,10 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
 
     def device_step():
-        if kind == "sw":
-            rc = L.db200_sw_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
-                                         d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_var.data_ptr(), var_cap,
-                                         d_voff.data_ptr(), d_status.data_ptr(), None, C.c_void_p(stream.cuda_stream))
+        if kind == "sw":   # the batch resident in HBM in pool format (north_star: "device-resident packed batches")
+            rc = L.db200_sw_batch_device_packed(local_rank, C.byref(prm_c), d_units.data_ptr(), n_units, d_qlen.data_ptr(), d_tlen.data_ptr(),
+                                                q_bytes, t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_var.data_ptr(), var_cap,
+                                                d_voff.data_ptr(), d_status.data_ptr(), None, C.c_void_p(stream.cuda_stream))
         elif want_path:
             rc = L.db200_ed_path_batch_device(local_rank, C.byref(prm_c), d_q.data_ptr(), d_qoff.data_ptr(), q_bytes, d_t.data_ptr(),
                                               d_toff.data_ptr(), t_bytes, n, max_q, max_t, None, d_res.data_ptr(), d_var.data_ptr(), var_cap,
@@ -439,8 +524,7 @@ def run_ours(args):
         # BASELINE.json north_star): pairs ordered by target length class, both sides encoded.  With the pairs of a length bucket
         # next to each other every chunk of the host pipeline feeds one or two bucket kernels with as many pairs as the whole batch
         # would - chunks in submission order spread every bucket thin over all chunks.  Results come back in this order.
-        order = np.argsort(-((t.lengths + 31) // 32), kind="stable") if os.environ.get("DB200_BENCH_NO_BUCKETING") is None else np.arange(n)
-        pq, pt = B.pack_seqs(q.take(order), pinned=True), B.pack_seqs(t.take(order), pinned=True)
+        # (order, pq, pt: prepared before the device arm, see above)
         hql = pinned_array(L, (n,), np.int32); hql[:] = pq.lengths
         htl = pinned_array(L, (n,), np.int32); htl[:] = pt.lengths
         hquo = pinned_array(L, (n + 1,), np.int64); hquo[:] = pq.unit_off
@@ -529,6 +613,10 @@ def run_ours(args):
             raise SystemExit("bench.py: Python front door and C ABI disagree")
         front_door = {"value": fcells / dtf / 1e9, "unit": UNIT, "pairs": nf, "ms": 1e3 * dtf,
                       "call": "dysgu_b200.batch.sw_align_batch(list[bytes], list[bytes]) -> numpy (pageable buffers, CSR built in Python)"}
+
+    merge_shape = None
+    if name == "remap_windows" and not args.no_merge_shape:
+        merge_shape = merge_shape_figure(L, B, torch, dev, dist, local_rank, rank, world)
 
     if rank != 0:
         if dist is not None:
@@ -627,13 +715,17 @@ def run_ours(args):
         "dtype": "int16" if kind == "sw" else "u64", "data": "synthetic",
         "config": {"workload": WORKLOADS[name][4],
                    "pairs_per_step_per_gpu": n, "cells_per_step_per_gpu": cells, "input_bytes_per_step_per_gpu": q_bytes + t_bytes,
-                   "l2": "inputs larger than L2 (%.0f MB per step)" % ((q_bytes + t_bytes) / 1e6), "sharding": "pairs by rank, no collective",
+                   "l2": "inputs larger than L2 (%.0f MB per step%s)" % (
+                       ((pq.nbytes + pt.nbytes) if kind == "sw" else (q_bytes + t_bytes)) / 1e6, ", 4-bit pool format" if kind == "sw" else ""),
+                   "device_arm_input": "length-bucketed batch resident in HBM in the 4-bit pool format (db200_sw_batch_device_packed)" if kind == "sw"
+                   else "ASCII CSR batch resident in HBM", "sharding": "pairs by rank, no collective",
                    "host": numa_note},
         "clocks": clocks,
         "e2e": e2e_packed if e2e_packed else e2e_ascii,
         "e2e_single_call": e2e_packed_sync,
         "e2e_ascii": e2e_ascii,
         "python_front_door": front_door,
+        "merge_shape": merge_shape,
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
@@ -660,6 +752,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=0, help="pairs per step of the CPU reference sample (0: the workload's default)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-merge-shape", action="store_true", help="skip the long-contig (configs 4/5) figure that rides on the default line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -64,6 +64,10 @@ def lib():
     L.db200_sw_batch_host_packed.restype = C.c_int
     L.db200_sw_batch_host_packed.argtypes = [C.c_int, C.POINTER(SwParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.db200_sw_batch_device_packed.restype = C.c_int
+    L.db200_sw_batch_device_packed.argtypes = [C.c_int, C.POINTER(SwParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                               C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]
     L.db200_sw_pack_host.restype = C.c_int
     L.db200_sw_pack_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
     L.db200_sw_batch_host_multi.restype = C.c_int

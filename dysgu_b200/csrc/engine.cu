@@ -474,6 +474,25 @@ int db200_sw_batch_device(int device, const db200_sw_params *params, const uint8
     return DB200_OK;
 }
 
+// Device-resident batch already in pool format: d_units holds [all queries][all targets] (dense, 16-byte units of 32 bases),
+// d_qlen / d_tlen the lengths in bases.  No pack kernel: one device copy puts the units next to the engine's reversed-prefix
+// area.  q_bases / t_bases are the sums of the lengths (they size the workspace).
+int db200_sw_batch_device_packed(int device, const db200_sw_params *params, const uint32_t *d_units, int64_t n_units, const int32_t *d_qlen,
+                                 const int32_t *d_tlen, int64_t q_bases, int64_t t_bases, int64_t npairs, int32_t max_query_len,
+                                 int32_t max_target_len, const int32_t *d_mask_len, db200_sw_result *d_results, uint32_t *d_cigar_buf,
+                                 int64_t cigar_cap, int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, void *stream)
+{
+    Engine *e = get_engine(device);
+    if (!e) return forked_after_cuda() ? DB200_ERR_FORKED : DB200_ERR_CUDA;
+    std::lock_guard<std::recursive_mutex> call_lock(e->call_mu);
+    if (!d_units || !d_qlen || !d_tlen || n_units < 0) { set_error("sw_batch_device_packed: bad arguments"); return DB200_ERR_ARG; }
+    e->arena[0].reset();
+    e->aux_set = 0;
+    return sw_batch_device_impl(e, e->arena[0], params, nullptr, nullptr, q_bases, nullptr, nullptr, t_bases, npairs, max_query_len, max_target_len,
+                                d_mask_len, d_results, d_cigar_buf, cigar_cap, d_cigar_off, d_status, cigar_total, (cudaStream_t)stream, nullptr,
+                                d_qlen, d_tlen, d_units, n_units);
+}
+
 // Host entry point.  The batch is cut into chunks that flow through a pipeline of Engine::NSLOT slots: while chunk i is being
 // aligned on the compute stream, chunk i+1 is copied to the device on the copy stream (pinned host buffers make
 // the copies asynchronous).  Fixed-size results travel back right behind the kernels; the variable-size cigar

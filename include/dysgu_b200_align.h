@@ -189,6 +189,13 @@ int db200_sw_batch_host_packed(int device, const db200_sw_params *params,
                                int64_t npairs, const int32_t *mask_len,
                                db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap,
                                int64_t *cigar_off, int32_t *status);
+/* The pre-packed form with everything resident in device memory: d_units = [all queries][all targets], dense; q_bases /
+ * t_bases the sums of the lengths; otherwise as db200_sw_batch_device. */
+int db200_sw_batch_device_packed(int device, const db200_sw_params *params, const uint32_t *d_units, int64_t n_units,
+                                 const int32_t *d_qlen, const int32_t *d_tlen, int64_t q_bases, int64_t t_bases, int64_t npairs,
+                                 int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len,
+                                 db200_sw_result *d_results, uint32_t *d_cigar_buf, int64_t cigar_cap,
+                                 int64_t *d_cigar_off, int32_t *d_status, int64_t *cigar_total, void *stream);
 int db200_sw_pack_host(const uint8_t *buf, const int64_t *off, const int32_t *len, int64_t nseq,
                        uint32_t *units, int64_t units_cap, int64_t *unit_off, int32_t *len_out, int32_t threads);
 
