@@ -77,6 +77,7 @@ struct Engine {
     int64_t host_chunk_pairs = 0;        // db200_set_host_chunk_pairs: 0 = automatic chunk schedule of the host entry points
     void *small_host = nullptr, *small_dev = nullptr;   // mapped page-locked staging of the one-launch small-batch path (sw_small.cuh)
     size_t small_cap = 0;
+    int32_t small_epoch = 0;
     size_t trace_slab_bytes = (size_t)4 << 30;  // per-block slabs of the wide banded traceback (DB200_TRACE_SLAB_MB)
     // optional stage profiling (CUDA events recorded on the launching stream between pipeline stages)
     bool profiling = false;

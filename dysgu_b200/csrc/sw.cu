@@ -475,7 +475,7 @@ int sw_small_host(Engine *e, const db200_sw_params *prm, const uint8_t *qbuf, co
     if (eligible * 2 < npairs) return DB200_OK;   // mostly long pairs: one trip through the batch pipeline
     // staging area in page-locked memory mapped into the device address space
     const size_t in_bytes = (size_t)(qbytes + tbytes) + sizeof(int32_t) * (size_t)(3 * npairs + 2) + 64;
-    const size_t out_bytes = (size_t)npairs * (sizeof(db200_sw_result) + sizeof(int32_t) + sizeof(uint32_t) * SW_SMALL_CIGAR_STRIDE) + 64;
+    const size_t out_bytes = (size_t)npairs * (sizeof(db200_sw_result) + 2 * sizeof(int32_t) + sizeof(uint32_t) * SW_SMALL_CIGAR_STRIDE) + 64;
     const size_t need = ((in_bytes + 255) & ~(size_t)255) + out_bytes;
     if (e->small_cap < need) {
         if (e->small_host) cudaFreeHost(e->small_host);
@@ -508,13 +508,18 @@ int sw_small_host(Engine *e, const db200_sw_params *prm, const uint8_t *qbuf, co
     const size_t out0 = (in_bytes + 255) & ~(size_t)255;
     db200_sw_result *h_res = reinterpret_cast<db200_sw_result *>(h + out0);
     int32_t *h_status = reinterpret_cast<int32_t *>(h_res + npairs);
-    uint32_t *h_cig = reinterpret_cast<uint32_t *>(h_status + npairs);
+    volatile int32_t *h_done = reinterpret_cast<volatile int32_t *>(h_status + npairs);
+    uint32_t *h_cig = reinterpret_cast<uint32_t *>(h_status + 2 * npairs);
     SmallArgs a;
     a.seq = d + (h_seq - h);
     a.qoff = reinterpret_cast<const int32_t *>(d); a.toff = a.qoff + npairs + 1; a.mask_len = a.toff + npairs + 1;
     a.results = reinterpret_cast<db200_sw_result *>(d + out0);
     a.status = reinterpret_cast<int32_t *>(a.results + npairs);
-    a.cigar = reinterpret_cast<uint32_t *>(a.status + npairs);
+    a.done = reinterpret_cast<volatile int32_t *>(a.status + npairs);
+    a.cigar = reinterpret_cast<uint32_t *>(a.status + 2 * npairs);
+    a.epoch = ++e->small_epoch;
+    if (a.epoch == 0) a.epoch = ++e->small_epoch;
+    for (int64_t i = 0; i < npairs; ++i) h_done[i] = 0;
     a.maxq = (maxq + 15) & ~15;
     int bias = 0;
     for (int x = 0; x < 6; ++x)
@@ -538,7 +543,24 @@ int sw_small_host(Engine *e, const db200_sw_params *prm, const uint8_t *qbuf, co
     sw_small_kernel<<<(unsigned)npairs, 32, smem, e->stream>>>(a);
     count_launch(e);
     DB200_CUDA_CHECK(cudaGetLastError());
-    DB200_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    {
+        // wait on the per-pair flags the kernel writes into mapped memory after its results (cheaper than a stream
+        // synchronisation for a call of a few tens of microseconds); the driver call remains the fallback and the error path
+        timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
+        int64_t i = 0;
+        unsigned spins = 0;
+        while (i < npairs) {
+            if (h_done[i] == a.epoch) { ++i; continue; }
+            if ((++spins & 1023u) == 0) {
+                timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
+                if ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6 > 2.0) break;   // long pairs: let the driver wait
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (i < npairs) DB200_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    }
     int64_t cpos = 0;
     for (int64_t i = 0; i < npairs; ++i) {
         const int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];

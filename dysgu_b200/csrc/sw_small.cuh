@@ -36,6 +36,8 @@ struct SmallArgs {
     db200_sw_result *results;    // [n]
     int32_t *status;             // [n]
     uint32_t *cigar;             // [n][SW_SMALL_CIGAR_STRIDE]
+    volatile int32_t *done;      // [n] mapped host memory: receives `epoch` once pair p's outputs are visible to the host
+    int32_t epoch;
     int32_t maxq;                // shared-memory layout: bytes reserved for the query codes (multiple of 16)
     int32_t bias, score_size, flag;
     SwScoring sc;
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(32) sw_small_kernel(SmallArgs a)
         if ((long long)mm * min(m, n) > 30000) status = DB200_PAIR_SCORE_RANGE;
     }
     if (status != DB200_PAIR_OK) {
-        if (lane == 0) { a.results[p] = r; a.status[p] = status; }
+        if (lane == 0) { a.results[p] = r; a.status[p] = status; __threadfence_system(); a.done[p] = a.epoch; }
         return;
     }
     // ---- encode (_ssw_wrapper.pyx:60-68) ---------------------------------------------------------------
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(32) sw_small_kernel(SmallArgs a)
     const bool overflow8 = score + a.bias >= 255;
     const bool use_word = (a.score_size == 1) || (a.score_size == 2 && overflow8);
     if (a.score_size == 0 && overflow8) {
-        if (lane == 0) { a.results[p] = r; a.status[p] = DB200_PAIR_OVERFLOW; }
+        if (lane == 0) { a.results[p] = r; a.status[p] = DB200_PAIR_OVERFLOW; __threadfence_system(); a.done[p] = a.epoch; }
         return;
     }
     r.score1 = score;
@@ -323,7 +325,8 @@ __global__ void __launch_bounds__(32) sw_small_kernel(SmallArgs a)
         for (int k = lane; k < ncig; k += 32) out[k] = runs[k];
         r.cigar_len = ncig;
     }
-    if (lane == 0) { a.results[p] = r; a.status[p] = status; }
+    __syncwarp();
+    if (lane == 0) { a.results[p] = r; a.status[p] = status; __threadfence_system(); a.done[p] = a.epoch; }
 }
 
 }  // namespace db200
