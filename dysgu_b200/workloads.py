@@ -55,12 +55,12 @@ class SeqBatch:
 
     @staticmethod
     def from_list(seqs) -> "SeqBatch":
-        bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+        bs = [s.encode("latin-1") if isinstance(s, str) else (s if isinstance(s, bytes) else bytes(s)) for s in seqs]
         off = np.zeros(len(bs) + 1, dtype=np.int64)
         if bs:
-            np.cumsum([len(b) for b in bs], out=off[1:])
-        buf = np.frombuffer(b"".join(bs), dtype=np.uint8).copy()
-        return SeqBatch(buf, off)
+            np.cumsum(np.fromiter(map(len, bs), dtype=np.int64, count=len(bs)), out=off[1:])
+        # one join, no second copy: the engine only reads the buffer (the array is a read-only view of the joined bytes)
+        return SeqBatch.__new_pinned__(np.frombuffer(b"".join(bs), dtype=np.uint8), off)
 
 
 def _offsets(lens: np.ndarray) -> np.ndarray:

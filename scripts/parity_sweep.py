@@ -135,7 +135,8 @@ def cmp_path(r, ref):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--tasks", default="all", choices=["all", "path", "nopath"], help="path: only the edlib task 'path' settings")
+    ap.add_argument("--tasks", default="all", choices=["all", "path", "nopath", "ed"], help="path: only the edlib task 'path' settings; ed: edit distance only (long sequences)")
+    ap.add_argument("--forms", action="store_true", help="Smith-Waterman: also through the pre-packed input form and, for a sample, the one-launch path in batches of at most 64 pairs")
     ap.add_argument("--pairs", type=int, default=100000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-len", type=int, default=600)
@@ -154,6 +155,8 @@ def main():
     if a.tasks == "path":
         sw_settings = []
         ed_settings = [e for e in ed_settings if e[1] == "path"]
+    if a.tasks == "ed":
+        sw_settings = []
     total = bad_total = ops_total = 0
     t0 = time.time()
     fams = list(families(rng, a.pairs, a.max_len))
@@ -169,6 +172,24 @@ def main():
             bad = cmp_sw(r, ref) & ok | ((r.status != 0) != (ref.status != 0))
             total += len(q); bad_total += int(bad.sum())
             print("SW  %-14s (%d,%d,%d,%d) size=%d flag=%d  pairs=%d  diffs=%d" % (name, ma, mi, go, ge, ss, fl, len(q), int(bad.sum())), flush=True)
+            if a.forms:
+                # the same pairs through the pre-packed form, and a sample through the one-launch path (batches of <= 64 pairs)
+                rp = batch.sw_align_packed(batch.pack_seqs(q), batch.pack_seqs(t), ma, mi, go, ge, score_size=ss, flag=fl)
+                badp = cmp_sw(rp, ref) & ok | ((rp.status != 0) != (ref.status != 0))
+                nsm, bads, pos = min(len(q), 4096), 0, 0
+                while pos < nsm:
+                    k = int(rng.integers(1, 65))
+                    idx = np.arange(pos, min(pos + k, nsm))
+                    rs = batch.sw_align_batch(q.take(idx), t.take(idx), ma, mi, go, ge, score_size=ss, flag=fl)
+                    sub_ok = ok[idx]
+                    same = (rs.fixed[:, :7] == ref.fixed[idx, :7]).all(axis=1) & (np.diff(rs.cigar_off) == np.diff(ref.cigar_off)[idx])
+                    for j, i in enumerate(idx):
+                        if same[j] and sub_ok[j] and not np.array_equal(rs.cigar_of(j), ref.cigar_of(i)):
+                            same[j] = False
+                    bads += int((~same & sub_ok).sum()) + int(((rs.status != 0) != (ref.status[idx] != 0)).sum())
+                    pos += k
+                total += len(q) + nsm; bad_total += int(badp.sum()) + bads
+                print("SW  %-14s   ... pre-packed form: pairs=%d diffs=%d; one-launch path: pairs=%d diffs=%d" % (name, len(q), int(badp.sum()), nsm, bads), flush=True)
         for (mode, task, k) in ed_settings:
             r = batch.ed_align_batch(q, t, mode=mode, task=task, k=-1 if k is None else k)
             if use_ref:
