@@ -18,7 +18,8 @@ OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libdysgu_b200_align.so")
 COMPAT = os.path.join(HERE, "libdysgu_b200_compat.so")
 PEAK = os.path.join(HERE, "int_peak")
-SOURCES = ["engine.cu", "sw.cu", "ed.cu", "queue.cu", "format.cu", "multi.cu", "minimizer.cu"]
+SOURCES = ["engine.cu", "sw.cu", "ed.cu", "queue.cu", "format.cu", "multi.cu", "minimizer.cu",
+           "sw_fine_g1.cu", "sw_fine_g2.cu", "sw_fine_g4.cu", "sw_fine_g8.cu", "sw_fine_g16.cu", "sw_fine_g32.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "dysgu_b200_align.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -51,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if force or _newer(o, [s] + deps):
             jobs.append([NVCC] + ARCH + FLAGS + ["-c", s, "-o", o])
     if jobs:
-        with ThreadPoolExecutor(len(jobs)) as ex:
+        with ThreadPoolExecutor(min(len(jobs), os.cpu_count() or 4)) as ex:
             for out in ex.map(_run, jobs):
                 if verbose and out:
                     print(out)

@@ -5,16 +5,17 @@
 // Reference behaviour being reproduced (dysgu v1.9.0):
 //   _ssw_wrapper.pyx:60-68 (encoding), 583-588 (mask length), ssw.c:772-857 (driver),
 //   ssw.c:124-346 / 372-548 (scoring passes), ssw.c:550-728 (banded traceback).
-#include "sw_kernels.cuh"
+#include "sw_launch.cuh"
 
 namespace db200 {
 
-// ------------------------------------------------------------------------------------------------
-// kernel configurations: index -> (K columns per virtual lane, G threads per pair)
-// ------------------------------------------------------------------------------------------------
-// columns per pass = 2*G*K; the last configuration tiles longer targets in passes of 2048 columns
-static const int CFG_CAP[SW_NCFG] = {32, 64, 96, 128, 160, 192, 224, 256, 320, 512, 1024, 2048};
-__device__ __constant__ int d_cfg_cap[SW_NCFG] = {32, 64, 96, 128, 160, 192, 224, 256, 320, 512, 1024, 2048};
+// per-call view of the configuration table (sw_launch.cuh) for the bucketing kernels
+struct CfgSel {
+    uint16_t cap[SW_NCFG];    // columns per pass
+    uint16_t cost[SW_NCFG];   // relative issue cost of one row of one pair; 0 = not usable in this call
+    uint8_t skew[SW_NCFG];    // 2G - 1: wavefront steps beyond the rows
+};
+constexpr int SW_SINGLE_PASS_MAX = 1024;   // widest single-pass configuration (K = 16, G = 32); longer targets are column-tiled
 
 struct PairState {          // per-pair bookkeeping of the pipeline
     int32_t mask_len;
@@ -138,16 +139,23 @@ __global__ void sw_meta_kernel(const int32_t *qlen, const int32_t *tlen, int64_t
 // ------------------------------------------------------------------------------------------------
 // 2. bucketing: counting sort of pairs by (config, needs column maxima, descending length bin)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sw_cfg_for(int n)
+// cheapest usable configuration whose pass holds n columns: cost per row x (rows + wavefront skew).  With the fine
+// configurations switched off the costs grow with the capacity, so this is "smallest capacity that fits" as before.
+__device__ __forceinline__ int sw_cfg_for(const CfgSel &s, int m, int n)
 {
-    int c = 0;
-    while (c < SW_NCFG - 1 && d_cfg_cap[c] < n) ++c;
-    return c;
+    int best = SW_CFG_MULTI;
+    unsigned long long bw = ~0ull;
+    for (int c = 0; c < SW_CFG_MULTI; ++c) {
+        if (s.cost[c] == 0 || (int)s.cap[c] < n) continue;
+        const unsigned long long w = (unsigned long long)s.cost[c] * (unsigned long long)(m + (int)s.skew[c]);
+        if (w < bw) { bw = w; best = c; }
+    }
+    return best;
 }
 
-__device__ __forceinline__ int sw_bin_key(int m, int n, int need_colmax)
+__device__ __forceinline__ int sw_bin_key(const CfgSel &sel, int m, int n, int need_colmax)
 {
-    const int c = sw_cfg_for(n);
+    const int c = sw_cfg_for(sel, m, n);
     const int lb = min(m >> 5, SW_LBINS - 1);
     return ((c * 2 + need_colmax) * SW_LBINS) + (SW_LBINS - 1 - lb);
 }
@@ -159,6 +167,7 @@ struct InitArgs {
     int64_t npairs;
     int32_t max_match;         // largest matrix entry
     int32_t flag;
+    CfgSel sel;
 };
 
 // per pair: status, mask length, colmax need, histogram of forward bins
@@ -176,21 +185,25 @@ __global__ void sw_init_kernel(InitArgs a, int32_t *hist)
     // column maxima are only needed when a column can fall outside the mask window (ssw.c:326-341)
     s.need_colmax = (s.mask_len >= 15 && pm.n > s.mask_len - 1) ? 1 : 0;
     a.state[p] = s;
-    if (s.status == DB200_PAIR_OK) atomicAdd(&hist[sw_bin_key(pm.m, pm.n, s.need_colmax)], 1);
+    if (s.status == DB200_PAIR_OK) atomicAdd(&hist[sw_bin_key(a.sel, pm.m, pm.n, s.need_colmax)], 1);
 }
 
 // single block: exclusive scan of the bin histogram, segment ranges
-// one warp per segment: totals by warp reduction, bin starts by a warp scan over 32 bins at a time
-__global__ void __launch_bounds__(SW_NSEG * 32) sw_binscan_kernel(const int32_t *hist, int32_t *bin_start, int32_t *seg_begin, int32_t *seg_count)
+// a warp per segment at a time: totals by warp reduction, bin starts by a warp scan over 32 bins at a time
+constexpr int SW_BINSCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SW_BINSCAN_THREADS) sw_binscan_kernel(const int32_t *hist, int32_t *bin_start, int32_t *seg_begin, int32_t *seg_count)
 {
     __shared__ int32_t seg_tot[SW_NSEG];
     __shared__ int32_t seg_off[SW_NSEG + 1];
-    const int seg = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int32_t *h = hist + seg * SW_LBINS;
-    int s = 0;
-    for (int b = lane; b < SW_LBINS; b += 32) s += h[b];
-    s = __reduce_add_sync(0xFFFFFFFFu, s);
-    if (lane == 0) seg_tot[seg] = s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = SW_BINSCAN_THREADS / 32;
+    for (int seg = warp; seg < SW_NSEG; seg += NW) {
+        const int32_t *h = hist + seg * SW_LBINS;
+        int s = 0;
+        for (int b = lane; b < SW_LBINS; b += 32) s += h[b];
+        s = __reduce_add_sync(0xFFFFFFFFu, s);
+        if (lane == 0) seg_tot[seg] = s;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
@@ -198,19 +211,23 @@ __global__ void __launch_bounds__(SW_NSEG * 32) sw_binscan_kernel(const int32_t 
         seg_off[SW_NSEG] = acc;
     }
     __syncthreads();
-    if (lane == 0) { seg_begin[seg] = seg_off[seg]; seg_count[seg] = seg_tot[seg]; }
-    int acc = seg_off[seg];
-    for (int b0 = 0; b0 < SW_LBINS; b0 += 32) {
-        const int v = h[b0 + lane];
-        int inc = v;
+    for (int seg = warp; seg < SW_NSEG; seg += NW) {
+        if (lane == 0) { seg_begin[seg] = seg_off[seg]; seg_count[seg] = seg_tot[seg]; }
+        if (seg_tot[seg] == 0) continue;   // nothing is scattered into an empty segment
+        const int32_t *h = hist + seg * SW_LBINS;
+        int acc = seg_off[seg];
+        for (int b0 = 0; b0 < SW_LBINS; b0 += 32) {
+            const int v = h[b0 + lane];
+            int inc = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
-        bin_start[seg * SW_LBINS + b0 + lane] = acc + inc - v;
-        acc += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+            bin_start[seg * SW_LBINS + b0 + lane] = acc + inc - v;
+            acc += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
     }
 }
 
-__global__ void sw_scatter_kernel(const PairMeta *meta, const PairState *state, int64_t npairs, int which,
+__global__ void sw_scatter_kernel(const PairMeta *meta, const PairState *state, int64_t npairs, int which, const CfgSel sel,
                                   const int32_t *bin_start, int32_t *bin_fill, int32_t *tasks)
 {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -219,7 +236,7 @@ __global__ void sw_scatter_kernel(const PairMeta *meta, const PairState *state, 
     if (s.status != DB200_PAIR_OK) return;
     if (which == 1 && !s.want_rev) return;
     const PairMeta pm = meta[p];
-    const int key = sw_bin_key(pm.m, pm.n, which == 0 ? s.need_colmax : 0);
+    const int key = sw_bin_key(sel, pm.m, pm.n, which == 0 ? s.need_colmax : 0);
     const int pos = bin_start[key] + atomicAdd(&bin_fill[key], 1);
     tasks[pos] = (int32_t)p;
 }
@@ -238,6 +255,7 @@ struct MidArgs {
     int32_t max_match, gap_open, gap_extend;
     uint32_t *unit_cursor;   // bump allocator for reversed sequences (units)
     uint32_t unit_base;
+    CfgSel sel;
 };
 
 __global__ void sw_mid_kernel(MidArgs a, int32_t *hist)
@@ -269,7 +287,7 @@ __global__ void sw_mid_kernel(MidArgs a, int32_t *hist)
     PairMeta r;
     r.q_unit = u0; r.t_unit = u0 + uq; r.m = rows; r.n = tspan;
     a.rmeta[p] = r;
-    atomicAdd(&hist[sw_bin_key(r.m, r.n, 0)], 1);
+    atomicAdd(&hist[sw_bin_key(a.sel, r.m, r.n, 0)], 1);
 }
 
 // one warp per pair: write reversed prefixes as packed codes
@@ -623,7 +641,6 @@ __global__ void sw_cigar_gather_kernel(const PairState *state, int64_t npairs, c
 // ------------------------------------------------------------------------------------------------
 // pipelined column tiles: the tasks of a column-tiled segment are expanded into (pair, pass) units
 // ------------------------------------------------------------------------------------------------
-constexpr int SW_MULTI_COLS = 2048;   // columns per pass of the column-tiled kernel (K = 32, G = 32)
 
 __global__ void sw_npass_kernel(const int32_t *tasks, const int32_t *seg_begin, const int32_t *seg_count, int seg, const PairMeta *meta,
                                 int64_t npairs, int32_t *lens)
@@ -677,28 +694,6 @@ __global__ void sw_expand_kernel(ExpandArgs a)
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
-template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG, bool PIPE = false>
-static int launch_pass(Engine *e, const PassArgs &a, cudaStream_t st)
-{
-    constexpr int NCH = K / 8, ROW = 2 * NCH * 32;
-    const size_t smem = (size_t)(SW_PASS_THREADS / 32) * 6 * ROW * sizeof(uint4);
-    static int blocks_cached[16] = {0};
-    int &blocks = blocks_cached[e->device & 15];
-    if (blocks == 0) {
-        DB200_CUDA_CHECK(cudaFuncSetAttribute(sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG, PIPE>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        DB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG, PIPE>, SW_PASS_THREADS, smem));
-        if (per_sm < 1) per_sm = 1;
-        if (MULTI && per_sm * (SW_PASS_THREADS / 32) > SW_MULTI_MAX_WARPS_PER_SM) per_sm = SW_MULTI_MAX_WARPS_PER_SM / (SW_PASS_THREADS / 32);
-        blocks = e->sm_count * per_sm;
-    }
-    sw_pass_kernel<K, G, COLMAX, MULTI, WATCH, TAG, PIPE><<<blocks, SW_PASS_THREADS, smem, st>>>(a);
-    count_launch(e);
-    DB200_CUDA_CHECK(cudaGetLastError());
-    return DB200_OK;
-}
-
 template <bool COLMAX, bool WATCH, bool TAG>
 static int launch_cfg(Engine *e, int cfg, const PassArgs &a, cudaStream_t st)
 {
@@ -714,10 +709,26 @@ static int launch_cfg(Engine *e, int cfg, const PassArgs &a, cudaStream_t st)
         case 8: return launch_pass<16, 10, COLMAX, false, WATCH, TAG>(e, a, st);
         case 9: return launch_pass<16, 16, COLMAX, false, WATCH, TAG>(e, a, st);
         case 10: return launch_pass<16, 32, COLMAX, false, WATCH, TAG>(e, a, st);
-        default:
+        case SW_CFG_MULTI:
             if constexpr (TAG) return DB200_ERR_INTERNAL;
             else return launch_pass<32, 32, COLMAX, true, WATCH, false>(e, a, st);
+        default: break;
     }
+    // fine configurations: tagged kernels only, one translation unit per group size
+    if constexpr (TAG && !WATCH) {
+        const SwCfg f = sw_cfg_table()[cfg];
+        switch (f.G) {
+            case 1: return sw_launch_fine_g1(e, f.K, COLMAX, a, st);
+            case 2: return sw_launch_fine_g2(e, f.K, COLMAX, a, st);
+            case 4: return sw_launch_fine_g4(e, f.K, COLMAX, a, st);
+            case 8: return sw_launch_fine_g8(e, f.K, COLMAX, a, st);
+            case 16: return sw_launch_fine_g16(e, f.K, COLMAX, a, st);
+            case 32: return sw_launch_fine_g32(e, f.K, COLMAX, a, st);
+            default: break;
+        }
+    }
+    set_error("sw_batch: configuration %d has no kernel for this variant", cfg);
+    return DB200_ERR_INTERNAL;
 }
 
 int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const uint8_t *d_qbuf, const int64_t *d_qoff,
@@ -753,13 +764,50 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
             sc.mat[a * 6 + b] = (a < 5 && b < 5) ? (int16_t)m5[a * 5 + b] : (int16_t)SW_NEG;
     sc.gap_open = prm->gap_open;
     sc.gap_extend = prm->gap_extend;
-    // tagged kernels run on scores scaled by 16 (K = 16 columns per virtual lane -> 4 tag bits)
-    SwScoring sc16 = sc;
-    for (int i = 0; i < 36; ++i) if (sc.mat[i] != SW_NEG) sc16.mat[i] = (int16_t)(sc.mat[i] * 16);
-    sc16.gap_open = sc.gap_open * 16;
-    sc16.gap_extend = sc.gap_extend * 16;
+    // tagged kernels run on scores scaled by 2^TAGB: 16 for K <= 16 columns per virtual lane (4 tag bits), 32 above
+    SwScoring sc16 = sc, sc32 = sc;
+    for (int i = 0; i < 36; ++i) if (sc.mat[i] != SW_NEG) { sc16.mat[i] = (int16_t)(sc.mat[i] * 16); sc32.mat[i] = (int16_t)(sc.mat[i] * 32); }
+    sc16.gap_open = sc.gap_open * 16; sc16.gap_extend = sc.gap_extend * 16;
+    sc32.gap_open = sc.gap_open * 32; sc32.gap_extend = sc.gap_extend * 32;
+    // ---- configurations usable in this call ------------------------------------------------------------
+    // Fine configurations (sw_launch.cuh) pay for themselves when the buckets are large; a small batch would only see
+    // their extra (mostly empty) launches, so it keeps the eleven classic ones.
+    const SwCfg *cfgs = sw_cfg_table();
+    int64_t fine_min_pairs = 16384;
+    if (const char *fm = getenv("DB200_SW_FINE_MIN_PAIRS")) fine_min_pairs = atoll(fm);
+    const bool fine = npairs >= fine_min_pairs && !getenv("DB200_SW_NO_FINE");
+    int ovh = 21;   // ALU-pipe instructions per row outside the recurrence (hand-over, strict-improvement test, query decode)
+    if (const char *ov = getenv("DB200_SW_ROW_OVERHEAD")) ovh = atoi(ov);
+    int force_k = 0, force_g = 0;   // measurement aid: DB200_SW_FORCE_CFG=K,G leaves that configuration alone in the table
+    if (const char *fc = getenv("DB200_SW_FORCE_CFG")) sscanf(fc, "%d,%d", &force_k, &force_g);
     bool tag_ok[SW_NCFG];
-    for (int c = 0; c < SW_NCFG; ++c) tag_ok[c] = (c < SW_NCFG - 1) && ((int64_t)max_match * CFG_CAP[c] <= 2047) && max_match > 0;
+    CfgSel sel;
+    memset(&sel, 0, sizeof(sel));
+    for (int c = 0; c < SW_NCFG; ++c) {
+        const int K = cfgs[c].K, G = cfgs[c].G, cap = 2 * K * G;
+        const bool is_fine = c >= SW_NCLASSIC && c < SW_CFG_MULTI;
+        tag_ok[c] = c < SW_CFG_MULTI && max_match > 0 && (int64_t)max_match * cap <= (K <= 16 ? 2047 : 1023);
+        sel.cap[c] = (uint16_t)cap;
+        sel.skew[c] = (uint8_t)(2 * G - 1);
+        // issue slots of one row of one pair: (6 K + overhead) per warp row, 32 / G pairs per warp
+        const bool usable = c < SW_CFG_MULTI && (!is_fine || (fine && tag_ok[c])) && (force_k == 0 || (K == force_k && G == force_g));
+        sel.cost[c] = usable ? (uint16_t)((64 * (6 * K + ovh) + (32 / G) / 2) / (32 / G)) : 0;
+    }
+    // a configuration is never chosen when another one that holds every target of this batch is cheaper in both terms
+    bool launchable[SW_NCFG];
+    for (int c = 0; c < SW_NCFG; ++c) {
+        launchable[c] = c == SW_CFG_MULTI || sel.cost[c] != 0;
+        if (c == SW_CFG_MULTI || !launchable[c] || max_target_len <= 0) continue;
+        for (int d = 0; d < SW_CFG_MULTI && launchable[c]; ++d) {
+            if (d == c || sel.cost[d] == 0 || (int)sel.cap[d] < max_target_len || sel.skew[d] > sel.skew[c]) continue;
+            if (sel.cost[d] < sel.cost[c] || (sel.cost[d] == sel.cost[c] && d < c)) launchable[c] = false;
+        }
+    }
+    if (max_target_len > 0 && max_target_len <= SW_SINGLE_PASS_MAX) launchable[SW_CFG_MULTI] = false;
+    // launch order: widest passes first, their drain overlaps the narrower buckets
+    int order[SW_NCFG];
+    for (int c = 0; c < SW_NCFG; ++c) order[c] = c;
+    std::stable_sort(order, order + SW_NCFG, [&](int x, int y) { return 2 * cfgs[x].K * cfgs[x].G * (x == SW_CFG_MULTI ? 64 : 1) > 2 * cfgs[y].K * cfgs[y].G * (y == SW_CFG_MULTI ? 64 : 1); });
 
     // ---- workspace ---------------------------------------------------------------------------------
     const int64_t nseq = 2 * npairs;
@@ -804,7 +852,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     // than the PIPE instantiation running one warp per pair: 16,000 long-read contigs 52.5 vs 58.3 ms forward).
     int pipe_max_tasks = 6144;
     if (const char *pt = getenv("DB200_SW_PIPE_MAX_TASKS")) pipe_max_tasks = atoi(pt);
-    const bool pipe = max_query_len > 0 && max_target_len > CFG_CAP[SW_NCFG - 2] && npairs <= pipe_max_tasks && !getenv("DB200_SW_NO_PIPE");
+    const bool pipe = max_query_len > 0 && max_target_len > SW_SINGLE_PASS_MAX && npairs <= pipe_max_tasks && !getenv("DB200_SW_NO_PIPE");
     const size_t vt_cap = pipe ? (size_t)(t_bytes / SW_MULTI_COLS + npairs + 16) : 0;
     constexpr int NPIPE = 3;   // forward without / with column maxima, reverse
     int32_t *vt_len = nullptr, *vt_pair = nullptr, *vt_pass = nullptr, *vt_prog = nullptr, *pair_done = nullptr;
@@ -845,8 +893,8 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     int32_t *segs = bins + 6 * nb;
     int32_t *seg_begin_f = segs, *seg_count_f = segs + SW_NSEG, *seg_begin_r = segs + 2 * SW_NSEG, *seg_count_r = segs + 3 * SW_NSEG;
     int32_t *amb_count_f = segs + 4 * SW_NSEG, *amb_count_r = segs + 5 * SW_NSEG;
-    // counters: [0..127] work counters of pass launches, [128] unit cursor, [130..131] trace cursor (u64),
-    // [132..133] cigar cursor (u64), [134] overflow flag
+    // counters: [128] unit cursor, [130..131] trace cursor (u64), [132..133] cigar cursor (u64), [134] overflow flag, ...;
+    // [256 ..] work counters of the pass launches (at most 5 per configuration)
     DB200_CUDA_CHECK(cudaMemsetAsync(bins, 0, (nb * 6 + 1024) * sizeof(int32_t), st));
     DB200_CUDA_CHECK(cudaMemsetAsync(counters, 0, 4096 * sizeof(int32_t), st));
     uint32_t *unit_cursor = reinterpret_cast<uint32_t *>(counters + 128);
@@ -876,10 +924,10 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     prof_mark(e, st, ST_PACK);
     // 2. bucket -------------------------------------------------------------------------------------
     InitArgs ia;
-    ia.meta = meta; ia.mask_len = d_mask_len; ia.state = state; ia.npairs = npairs; ia.max_match = max_match; ia.flag = prm->flag;
+    ia.meta = meta; ia.mask_len = d_mask_len; ia.state = state; ia.npairs = npairs; ia.max_match = max_match; ia.flag = prm->flag; ia.sel = sel;
     sw_init_kernel<<<gpair, TB, 0, st>>>(ia, hist_f);
-    sw_binscan_kernel<<<1, SW_NSEG * 32, 0, st>>>(hist_f, start_f, seg_begin_f, seg_count_f);
-    sw_scatter_kernel<<<gpair, TB, 0, st>>>(meta, state, npairs, 0, start_f, fill_f, tasks_f);
+    sw_binscan_kernel<<<1, SW_BINSCAN_THREADS, 0, st>>>(hist_f, start_f, seg_begin_f, seg_count_f);
+    sw_scatter_kernel<<<gpair, TB, 0, st>>>(meta, state, npairs, 0, sel, start_f, fill_f, tasks_f);
     sw_colmax_len_kernel<<<gpair, TB, 0, st>>>(meta, state, npairs, lens);
     count_launch(e, 4);
     exclusive_scan_i32_i64(e, lens, colmax_off, npairs, scan_tmp, st);
@@ -897,7 +945,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     pa.bnd_off = bnd_off;
     pa.k65536 = 65536u;
     pa.sc = sc;
-    int counter_idx = 0;
+    int counter_idx = 256;
     const bool can_multi = max_query_len > 0;
 
     // column-tiled segment `seg` of the task list in `pa`, pipelined: expand it into (pair, pass) units, then one warp per unit
@@ -925,19 +973,21 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     // 3. forward pass per segment, then the exact re-run of pairs with an ambiguous end row -----------
     { const int rc = aux_fork(e, st); if (rc) return rc; }
     int aux_i = 0;
-    for (int seg = SW_NSEG - 1; seg >= 0; --seg) {   // widest buckets first: their drain overlaps the narrower ones
-        const int cfg = seg >> 1, cmx = seg & 1;
-        if (cfg == SW_NCFG - 1 && !can_multi) continue;
+    auto tag_sc = [&](int cfg) -> const SwScoring & { return cfgs[cfg].K <= 16 ? sc16 : sc32; };
+    for (int oi = 0; oi < 2 * SW_NCFG; ++oi) {
+        const int cfg = order[oi >> 1], cmx = 1 - (oi & 1), seg = 2 * cfg + cmx;
+        if (!launchable[cfg]) continue;
+        if (cfg == SW_CFG_MULTI && !can_multi) continue;
         cudaStream_t ls = e->aux[e->aux_set][(aux_i++) % Engine::NAUX];
         pa.meta = meta; pa.tasks = tasks_f; pa.seg_begin = seg_begin_f; pa.seg_count = seg_count_f; pa.seg = seg;
         pa.counter = counters + (counter_idx++);
         pa.out = fwd;
         pa.amb_list = amb_f; pa.amb_count = amb_count_f + 2 * cfg; pa.amb_base_seg = 2 * cfg;
         int rc;
-        if (cfg == SW_NCFG - 1 && pipe) { pa.sc = sc; rc = launch_piped(cmx, cmx != 0, pa, ls); }
-        else if (cmx && tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<true, false, true>(e, cfg, pa, ls); }
+        if (cfg == SW_CFG_MULTI && pipe) { pa.sc = sc; rc = launch_piped(cmx, cmx != 0, pa, ls); }
+        else if (cmx && tag_ok[cfg]) { pa.sc = tag_sc(cfg); rc = launch_cfg<true, false, true>(e, cfg, pa, ls); }
         else if (cmx) { pa.sc = sc; rc = launch_cfg<true, false, false>(e, cfg, pa, ls); }
-        else if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
+        else if (tag_ok[cfg]) { pa.sc = tag_sc(cfg); rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
         else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, ls); }
         if (rc) return rc;
     }
@@ -945,7 +995,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     pa.sc = sc;
     prof_mark(e, st, ST_FORWARD);
     for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
-        if (cfg == SW_NCFG - 1 && !can_multi) continue;
+        if (!launchable[cfg] || (cfg == SW_CFG_MULTI && !can_multi)) continue;
         pa.meta = meta; pa.tasks = amb_f; pa.seg_begin = seg_begin_f; pa.seg_count = amb_count_f; pa.seg = 2 * cfg;
         pa.counter = counters + (counter_idx++);
         pa.out = fwd;
@@ -960,32 +1010,33 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     ma.fwd = fwd; ma.meta = meta; ma.rmeta = rmeta; ma.state = state; ma.npairs = npairs;
     ma.bias = bias; ma.score_size = prm->score_size; ma.flag = prm->flag; ma.filters = prm->filters;
     ma.max_match = max_match; ma.gap_open = prm->gap_open; ma.gap_extend = prm->gap_extend;
-    ma.unit_cursor = unit_cursor; ma.unit_base = (uint32_t)seq_units;
+    ma.unit_cursor = unit_cursor; ma.unit_base = (uint32_t)seq_units; ma.sel = sel;
     sw_mid_kernel<<<gpair, TB, 0, st>>>(ma, hist_r);
     sw_reverse_extract_kernel<<<gwarp_pair, TB, 0, st>>>(meta, rmeta, state, fwd, npairs, pool);
-    sw_binscan_kernel<<<1, SW_NSEG * 32, 0, st>>>(hist_r, start_r, seg_begin_r, seg_count_r);
-    sw_scatter_kernel<<<gpair, TB, 0, st>>>(rmeta, state, npairs, 1, start_r, fill_r, tasks_r);
+    sw_binscan_kernel<<<1, SW_BINSCAN_THREADS, 0, st>>>(hist_r, start_r, seg_begin_r, seg_count_r);
+    sw_scatter_kernel<<<gpair, TB, 0, st>>>(rmeta, state, npairs, 1, sel, start_r, fill_r, tasks_r);
     count_launch(e, 4);
     prof_mark(e, st, ST_REVERSE_PREP);
     pa.bnd_off = bnd_off + npairs;   // the reversed problems keep their own boundary columns
     { const int rc = aux_fork(e, st); if (rc) return rc; }
-    for (int cfg = SW_NCFG - 1; cfg >= 0; --cfg) {
-        if (cfg == SW_NCFG - 1 && !can_multi) continue;
+    for (int oi = 0; oi < SW_NCFG; ++oi) {
+        const int cfg = order[oi];
+        if (!launchable[cfg] || (cfg == SW_CFG_MULTI && !can_multi)) continue;
         cudaStream_t ls = e->aux[e->aux_set][(aux_i++) % Engine::NAUX];
         pa.meta = rmeta; pa.tasks = tasks_r; pa.seg_begin = seg_begin_r; pa.seg_count = seg_count_r; pa.seg = 2 * cfg;
         pa.counter = counters + (counter_idx++);
         pa.out = rev;
         pa.amb_list = amb_r; pa.amb_count = amb_count_r + 2 * cfg; pa.amb_base_seg = 2 * cfg;
         int rc;
-        if (cfg == SW_NCFG - 1 && pipe) { pa.sc = sc; rc = launch_piped(2, false, pa, ls); }
-        else if (tag_ok[cfg]) { pa.sc = sc16; rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
+        if (cfg == SW_CFG_MULTI && pipe) { pa.sc = sc; rc = launch_piped(2, false, pa, ls); }
+        else if (tag_ok[cfg]) { pa.sc = tag_sc(cfg); rc = launch_cfg<false, false, true>(e, cfg, pa, ls); }
         else { pa.sc = sc; rc = launch_cfg<false, false, false>(e, cfg, pa, ls); }
         if (rc) return rc;
     }
     { const int rc = aux_join(e, st); if (rc) return rc; }
     prof_mark(e, st, ST_REVERSE);
     for (int cfg = 0; cfg < SW_NCFG; ++cfg) {
-        if (cfg == SW_NCFG - 1 && !can_multi) continue;
+        if (!launchable[cfg] || (cfg == SW_CFG_MULTI && !can_multi)) continue;
         pa.meta = rmeta; pa.tasks = amb_r; pa.seg_begin = seg_begin_r; pa.seg_count = amb_count_r; pa.seg = 2 * cfg;
         pa.counter = counters + (counter_idx++);
         pa.out = rev;
@@ -1001,7 +1052,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     fa.fwd = fwd; fa.rev = rev; fa.meta = meta; fa.state = state; fa.colmax = colmax; fa.colmax_off = colmax_off;
     fa.results = d_results; fa.status_out = nullptr; fa.npairs = npairs;
     fa.flag = prm->flag; fa.filters = prm->filters; fa.filterd = prm->filterd;
-    fa.pipe_abort = pipe ? counters + 148 : nullptr; fa.tiled_from = CFG_CAP[SW_NCFG - 2];
+    fa.pipe_abort = pipe ? counters + 148 : nullptr; fa.tiled_from = SW_SINGLE_PASS_MAX;
     fa.defer_second_from = max_target_len > 512 ? 512 : 0;
     sw_finalize_kernel<<<gpair, TB, 0, st>>>(fa);
     if (fa.defer_second_from > 0) { sw_second_best_kernel<<<gwarp_pair, TB, 0, st>>>(fa); count_launch(e); }

@@ -24,7 +24,7 @@ namespace db200 {
 
 constexpr int SW_PAD_CODE = 5;       // nibble used for padding; scores SW_NEG against everything
 constexpr int SW_NEG = -16384;
-constexpr int SW_NCFG = 12;          // kernel configurations (K, G)
+constexpr int SW_NCFG = 60;          // kernel configurations (K, G): 11 classic (K = 16), 48 fine, the column-tiled one (sw_launch.cuh)
 constexpr int SW_LBINS = 512;        // length bins per (config, colmax) segment, 32 rows each
 constexpr int SW_NSEG = SW_NCFG * 2; // (config, needs column maxima)
 constexpr int SW_MULTI_MAX_WARPS_PER_SM = 8;
@@ -34,6 +34,9 @@ constexpr int SW_MULTI_MAX_WARPS_PER_SM = 8;
 #ifndef SW_PASS_MIN_BLOCKS
 #define SW_PASS_MIN_BLOCKS 4
 #endif // bounds the per-warp boundary scratch of the column-tiled kernel
+#ifndef SW_FINE_KMAX
+#define SW_FINE_KMAX 20           // largest K that still runs four blocks per SM (registers and 768*K bytes of profile per warp)
+#endif
 
 struct PairMeta {      // one alignment problem on packed sequences
     uint32_t q_unit;   // offset of the streamed sequence in the nibble pool, in 16-byte units (32 bases)
@@ -109,12 +112,11 @@ __device__ __forceinline__ int pool_code(const uint4 *pool, uint32_t unit, int i
 // so the tiles of a 10 kb x 10 kb pair run as a pipeline of five warps instead of one warp after the other.  Units are
 // dispensed in list order and a pass only ever waits for the unit right before it, which a resident warp already holds.
 template <int K, int G, bool COLMAX, bool MULTI, bool WATCH, bool TAG, bool PIPE = false>
-__global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS_MIN_BLOCKS : 1) sw_pass_kernel(PassArgs a)
+__global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI) ? SW_PASS_MIN_BLOCKS : 1) sw_pass_kernel(PassArgs a)
 {
     static_assert(!PIPE || (MULTI && !WATCH), "pipelined passes are the column-tiled scoring kernel");
     constexpr int V = 2 * G;          // virtual lanes per group
     constexpr int C = V * K;          // columns per pass
-    constexpr int NCH = K / 8;        // 16-byte units per half strip (sizing only)
     constexpr int GROUPS = 32 / G;    // pairs per warp (G need not divide 32: the remaining lanes idle)
     // profile row of one streamed code, per warp: 32-bit word [k][lane] = (score of the low-half column k) |
     // (score of the high-half column k) << 16.  Every lane owns one bank, so the 16-bit loads below never conflict
@@ -122,9 +124,10 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
     constexpr int ROW16 = 2 * K * 32; // uint16 entries per row
     constexpr int TAGB = (K <= 16) ? 4 : 5;
     constexpr bool VMAX = !TAG || COLMAX;
-    constexpr int ROW = 2 * NCH * 32; // uint4 per profile row (one streamed code) per warp
-    constexpr int UNITS = (2 * K) / 32;
-    static_assert(K % 16 == 0, "K must be a multiple of 16");
+    constexpr bool ALIGNED = (K % 16 == 0);   // a lane's 2K columns are whole 16-byte units of the pool
+    constexpr int UNITS = ALIGNED ? (2 * K) / 32 : 1;
+    constexpr int TW = (2 * K + 7) / 8 + 1;   // !ALIGNED: 32-bit words that can hold a lane's 2K codes at any nibble offset
+    static_assert(K >= 2 && K <= 32, "columns per virtual lane");
     static_assert(!MULTI || G == 32, "column tiling runs one pair per warp");
     static_assert(!(TAG && (WATCH || MULTI)), "the tagged variant is a single-pass kernel");
 
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
     __shared__ int16_t mat_s[36];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lig = lane % G, grp = lane / G;
-    uint16_t *prof = reinterpret_cast<uint16_t *>(smem + warp * (6 * ROW));
+    uint16_t *prof = reinterpret_cast<uint16_t *>(smem) + warp * (6 * ROW16);
     if (threadIdx.x < 36) mat_s[threadIdx.x] = a.sc.mat[threadIdx.x];
     __syncthreads();
 
@@ -209,23 +212,47 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= 16 && !MULTI) ? SW_PASS
             __syncwarp();
             {
                 const int j0 = ps * C + lig * 2 * K;
-                uint4 tu[UNITS];
+                if constexpr (ALIGNED) {
+                    uint4 tu[UNITS];
 #pragma unroll
-                for (int u = 0; u < UNITS; ++u) {
-                    const int jb = j0 + u * 32;
-                    if (jb < n) tu[u] = a.pool[pm.t_unit + (jb >> 5)];
-                    else tu[u] = make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);
-                }
+                    for (int u = 0; u < UNITS; ++u) {
+                        const int jb = j0 + u * 32;
+                        if (jb < n) tu[u] = a.pool[pm.t_unit + (jb >> 5)];
+                        else tu[u] = make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);
+                    }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int jj = h * K + k; // position inside this lane's 2K columns
-                        int tc = (int)((unit_word(tu[jj >> 5], (jj >> 3) & 3) >> ((jj & 7) * 4)) & 15u);
-                        tc = min(tc, SW_PAD_CODE) * 6;
+                        for (int k = 0; k < K; ++k) {
+                            const int jj = h * K + k; // position inside this lane's 2K columns
+                            int tc = (int)((unit_word(tu[jj >> 5], (jj >> 3) & 3) >> ((jj & 7) * 4)) & 15u);
+                            tc = min(tc, SW_PAD_CODE) * 6;
 #pragma unroll
-                        for (int c = 0; c < 6; ++c)
-                            prof[c * ROW16 + (k * 32 + lane) * 2 + h] = (uint16_t)mat_s[tc + c];
+                            for (int c = 0; c < 6; ++c)
+                                prof[c * ROW16 + (k * 32 + lane) * 2 + h] = (uint16_t)mat_s[tc + c];
+                        }
+                    }
+                } else {
+                    // any K: the lane's codes start at nibble j0 of the target; words past the sequence's last unit read as padding
+                    const uint32_t *tw = reinterpret_cast<const uint32_t *>(a.pool + pm.t_unit);
+                    const int t_words = ((n + 31) >> 5) << 2;
+                    const int w0 = j0 >> 3;
+                    const int sh = (j0 & 7) * 4;
+                    uint32_t raw[TW];
+#pragma unroll
+                    for (int u = 0; u < TW; ++u) raw[u] = (w0 + u < t_words) ? tw[w0 + u] : 0x55555555u;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const int jj = h * K + k;
+                            const uint32_t w = __funnelshift_r(raw[jj >> 3], raw[(jj >> 3) + 1], sh);
+                            int tc = (int)((w >> ((jj & 7) * 4)) & 15u);
+                            tc = min(tc, SW_PAD_CODE) * 6;
+#pragma unroll
+                            for (int c = 0; c < 6; ++c)
+                                prof[c * ROW16 + (k * 32 + lane) * 2 + h] = (uint16_t)mat_s[tc + c];
+                        }
                     }
                 }
             }

@@ -193,3 +193,57 @@ def test_device_entry_point_sub_batches_share_one_cigar_csr():
         assert outs[nsub][4] == ref[4]
     oracle = O.oracle_sw((q.buf, q.off), (t.buf, t.off), prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"], csr=True)
     assert np.array_equal(ref[0].numpy(), oracle.fixed)
+
+
+# ---- fine-grained kernel configurations (K = 8..18 columns per virtual lane, sw_launch.cuh) --------------------------
+# Large batches choose them per pair by cost; the tests switch them on for small batches (DB200_SW_FINE_MIN_PAIRS=0)
+# and compare with the oracle and with the classic configurations.
+
+@pytest.mark.parametrize("scoring", SCORINGS)
+def test_fine_configurations_random_classes(scoring, monkeypatch):
+    monkeypatch.setenv("DB200_SW_FINE_MIN_PAIRS", "0")
+    qs, ts = pairgen.sw_pairs(9000 + sum(scoring), 3000, 700)
+    m, x, go, ge = scoring
+    res = batch.sw_align_batch(qs, ts, m, x, go, ge)
+    ref = O.oracle_sw(qs, ts, m, x, go, ge)
+    compare(qs, ts, res, ref, "fine " + str(scoring))
+
+
+def test_fine_configurations_every_target_length(monkeypatch):
+    # one related and one unrelated pair for every target length 1..1024: every (K, G) and every padding remainder;
+    # a fixed short mask asks for the column maxima variants (second best) as well, flag 0 for the score-only route
+    import random
+    rng = random.Random(31)
+    qs, ts = [], []
+    for n in range(1, 1025):
+        t = pairgen.rand_dna(rng, n)
+        q = pairgen.rand_dna(rng, rng.randint(0, 30)) + pairgen.mutate(rng, t, 0.03, 0.01, 0.01) + pairgen.rand_dna(rng, rng.randint(0, 30))
+        qs.append(q.encode()); ts.append(t.encode())
+        qs.append(pairgen.rand_dna(rng, rng.randint(20, 200)).encode()); ts.append(t.lower().encode())
+    monkeypatch.setenv("DB200_SW_FINE_MIN_PAIRS", "0")
+    for kw in (dict(), dict(mask_len=15), dict(flag=0)):
+        res = batch.sw_align_batch(qs, ts, 2, -8, 6, 1, **kw)
+        okw = dict(kw)
+        if "mask_len" in okw:
+            okw["mask_len"] = np.full(len(qs), okw["mask_len"], np.int32)
+        ref = O.oracle_sw(qs, ts, 2, -8, 6, 1, **okw)
+        compare(qs, ts, res, ref, "fine lengths %r" % (kw,))
+    monkeypatch.setenv("DB200_SW_NO_FINE", "1")
+    classic = batch.sw_align_batch(qs, ts, 2, -8, 6, 1)
+    monkeypatch.delenv("DB200_SW_NO_FINE")
+    fine = batch.sw_align_batch(qs, ts, 2, -8, 6, 1)
+    assert np.array_equal(classic.fixed, fine.fixed) and np.array_equal(classic.cigar, fine.cigar)
+
+
+def test_fine_configurations_headline_shape_and_large_match_scores(monkeypatch):
+    # 40,000 window / clip pairs take the fine configurations by default (>= 16,384 pairs); match = 5 leaves the tag bits
+    # only to the narrower configurations, the others fall back to the classic ones inside the same call
+    q, t, prm = workloads.remap_windows(40000, seed=23)
+    res = batch.sw_align_batch(q, t, **prm)
+    ref = O.oracle_sw((q.buf, q.off), (t.buf, t.off), prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"], csr=True)
+    assert np.array_equal(res.fixed, ref.fixed) and np.array_equal(res.cigar, ref.cigar) and np.array_equal(res.cigar_off, ref.cigar_off)
+    monkeypatch.setenv("DB200_SW_FINE_MIN_PAIRS", "0")
+    qs, ts = pairgen.sw_pairs(515, 3000, 600)
+    res = batch.sw_align_batch(qs, ts, 5, -4, 8, 2)
+    ref = O.oracle_sw(qs, ts, 5, -4, 8, 2)
+    compare(qs, ts, res, ref, "fine match=5")
