@@ -878,9 +878,9 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     const size_t slab_bytes = (e->trace_slab_bytes / (size_t)wide_blocks) & ~(size_t)255;
     uint8_t *slab = ws.alloc<uint8_t>(slab_bytes * (size_t)wide_blocks);
     int32_t *narrow_list = ws.alloc<int32_t>(npairs);
-    int32_t *medium_list = ws.alloc<int32_t>(npairs);
-    int32_t *wide_list = ws.alloc<int32_t>(npairs);
-    int32_t *slab_scalar_list = ws.alloc<int32_t>(npairs);
+    int32_t *medium_list = ws.alloc<int32_t>((size_t)npairs * TRACE_MEDIUM_CLASSES);
+    int32_t *wide_list = ws.alloc<int32_t>((size_t)npairs * TRACE_MEDIUM_CLASSES);
+    int32_t *slab_scalar_list = ws.alloc<int32_t>((size_t)npairs * TRACE_MEDIUM_CLASSES);
     if (!units || !unit_off || !scan_tmp || !pool || !meta || !rmeta || !state || !fwd || !rev || !tasks_f || !tasks_r || !amb_f ||
         !amb_r || !colmax_off || !cig_off_tmp || !lens || !colmax || !bins || !cigar_pool || !counters || !boundary || !slab ||
         !bnd_pool || !bnd_off ||
@@ -1068,6 +1068,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     ta.list[0] = narrow_list; ta.list[1] = medium_list; ta.list[2] = wide_list; ta.list[3] = slab_scalar_list;
     for (int l = 0; l < 3; ++l) { ta.count[l] = counters + 136 + l; ta.counter[l] = counters + 140 + l; }
     ta.count[3] = counters + 139;
+    ta.class_count = counters + 160;   // [4][TRACE_MEDIUM_CLASSES]
     const int warp_blocks = e->sm_count * 24;
     ta.coop_blocks[0] = 0; ta.coop_blocks[1] = warp_blocks; ta.coop_blocks[2] = wide_blocks;
     sw_trace_classify_kernel<<<gpair, TB, 0, st>>>(ta);
@@ -1082,12 +1083,13 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         const unsigned gn = (unsigned)((npairs + TRACE_NARROW_THREADS - 1) / TRACE_NARROW_THREADS);
         sw_trace_narrow_kernel<<<gn, TRACE_NARROW_THREADS, sm0, st>>>(ta, 0);
         // the same kernel over the jobs of up to TRACE_MEDIUM_CELLS cells, directions in private regions of the slab
-        sw_trace_narrow_kernel<<<gn, TRACE_NARROW_THREADS, sm0, st>>>(ta, 3);
+        const size_t sm3 = (size_t)TRACE_NARROW_THREADS * TRACE_MEDIUM_WORDS * sizeof(uint32_t);
+        sw_trace_narrow_kernel<<<gn, TRACE_NARROW_THREADS, sm3, st>>>(ta, 3);
         count_launch(e);
     }
     {
         // level 1: one warp per pair (state for 2*62+1 diagonals, 8 KB of walk staging)
-        constexpr int W1 = 254, S1 = 8192;
+        constexpr int W1 = 126, S1 = 8192;
         const size_t sm1 = (((size_t)3 * (W1 + 2) * sizeof(int16_t) + 15) & ~(size_t)15) + S1;
         sw_trace_coop_kernel<32, 1, W1, 0, S1><<<warp_blocks, 32, sm1, st>>>(ta);
         // level 2: one block per pair (4094 diagonals, both sub-sequences staged, 48 KB of walk staging shared with nothing)

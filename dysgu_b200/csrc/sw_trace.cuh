@@ -33,6 +33,7 @@ struct TraceArgs {
     int32_t coop_blocks[3];        // grid size per level (slab = slab_total / blocks)
     unsigned long long slab_total;
     unsigned long long *medium_cursor;   // level 0, jobs too large for the shared-memory slice: regions of the slab handed out so far
+    int32_t *class_count;                // [4][TRACE_MEDIUM_CLASSES] fill of the sub-lists of lists 1..3 (count[l] is their sum)
     int32_t debug;
 };
 
@@ -43,20 +44,51 @@ constexpr int TRACE_NARROW_CELLS = 768;
 // 300-row contig with a band of 3-17 columns is still a job for one thread - the warp-per-pair sweep of level 1 would run
 // it with 3-17 of its 32 lanes and a barrier per anti-diagonal (paired-end contigs: traceback stage 9.5 -> see DESIGN.md)
 constexpr int TRACE_MEDIUM_CELLS = 3072;
+constexpr int TRACE_MEDIUM_REGION = 4096;      // bytes of slab per such job: nibbles, rows padded to 8 cells (<= 1024 rows of one word)
+constexpr int TRACE_MEDIUM_CLASSES = 8;        // sub-lists of list 3 by job size, so that the 32 jobs of a warp are of similar length
+constexpr int TRACE_MEDIUM_CLASS_CELLS = TRACE_MEDIUM_CELLS / TRACE_MEDIUM_CLASSES;
 constexpr int TRACE_MEDIUM_MIN_JOBS = 16384;   // below this many such jobs in a batch the warp-per-pair kernel is quicker
 constexpr int TRACE_NARROW_WIDTH = 30;   // widest band row the scalar kernel keeps in its shared-memory slice
-constexpr int TRACE_WARP_BW = 62;
+constexpr int TRACE_WARP_BW = 62;      // 125 band diagonals, at most 63 cells on an anti-diagonal: two per lane
+// (bands up to 126 either side at this level measured slower: long_contigs traceback 44.7 -> 59.6 ms; the block level
+// sweeps a wide anti-diagonal in one slot)
 // per-thread slice of the scalar kernel: direction nibbles of TRACE_NARROW_CELLS cells + four rolling int16 rows,
 // padded to an odd word count so that the 32 slices of a warp start in 32 different banks
 constexpr int TRACE_NARROW_DIR_WORDS = TRACE_NARROW_CELLS / 8;
 constexpr int TRACE_NARROW_ROW = TRACE_NARROW_WIDTH + 2;
 constexpr int TRACE_NARROW_WORDS = (TRACE_NARROW_DIR_WORDS + 4 * TRACE_NARROW_ROW / 2) | 1;
+constexpr int TRACE_MEDIUM_WORDS = (4 * TRACE_NARROW_ROW / 2) | 1;   // list 3 keeps its directions in the slab: rolling rows only
 constexpr int TRACE_NARROW_THREADS = 128;
+// Work lists 1..3 are TRACE_MEDIUM_CLASSES sub-lists of `stride` entries each, by job size, taken largest class first:
+// the 32 jobs of a warp of the scalar kernel are of similar length, and the cooperative kernels start their longest
+// pairs first instead of leaving one for the end of the launch (a 6 kb contig pair sweeps for milliseconds).
+__device__ __forceinline__ int trace_class(int lvl, int readLen, int refLen, int width)
+{
+    if (lvl == 3) return min(TRACE_MEDIUM_CLASSES - 1, (readLen * width) / TRACE_MEDIUM_CLASS_CELLS);
+    return max(0, min(TRACE_MEDIUM_CLASSES - 1, 24 - __clz(readLen + refLen)));   // < 256 steps: 0 ... >= 16384: 7
+}
+__device__ __forceinline__ void trace_push(int32_t *const *list, int32_t *const *count, int32_t *ccount, long long stride, int lvl, int p,
+                                           int readLen, int refLen, int width)
+{
+    if (lvl == 0) { list[0][atomicAdd(count[0], 1)] = p; return; }
+    const int c = trace_class(lvl, readLen, refLen, width);
+    atomicAdd(count[lvl], 1);
+    list[lvl][(long long)c * stride + atomicAdd(ccount + lvl * TRACE_MEDIUM_CLASSES + c, 1)] = p;
+}
+// task r of a classed list, largest class first (the classes are complete before the consuming launch starts)
+__device__ __forceinline__ int trace_task(const int32_t *list, const int32_t *ccount, long long stride, int lvl, long long r)
+{
+    const int32_t *cc = ccount + lvl * TRACE_MEDIUM_CLASSES;
+    int c = TRACE_MEDIUM_CLASSES - 1;
+    while (c > 0 && r >= cc[c]) { r -= cc[c]; --c; }
+    return list[(long long)c * stride + r];
+}
 __device__ __forceinline__ int trace_level(int readLen, int refLen, int bw)
 {
     const int width = min(2 * bw + 1, refLen);
     if (width <= TRACE_NARROW_WIDTH && (long long)readLen * width <= TRACE_NARROW_CELLS) return 0;
-    if (width <= TRACE_NARROW_WIDTH && (long long)readLen * width <= TRACE_MEDIUM_CELLS) return 3;
+    if (width <= TRACE_NARROW_WIDTH && (long long)readLen * width <= TRACE_MEDIUM_CELLS &&
+        (long long)readLen * ((width + 7) >> 3) * 4 <= TRACE_MEDIUM_REGION) return 3;
     return bw <= TRACE_WARP_BW ? 1 : 2;
 }
 constexpr int TRACE_WMAX = 4094;       // wide kernel: band diagonals held in shared memory (3 x int16 each)
@@ -123,7 +155,7 @@ __global__ void __launch_bounds__(256) sw_trace_classify_kernel(TraceArgs a)
     const int bw = abs(refLen - readLen) + 1;
     const int lvl = trace_level(readLen, refLen, bw);
     s.trace_bw = bw;
-    a.list[lvl][atomicAdd(a.count[lvl], 1)] = (int32_t)p;
+    trace_push(a.list, a.count, a.class_count, a.npairs, lvl, (int)p, readLen, refLen, min(2 * bw + 1, refLen));
 }
 
 // direction nibble: bits 0-1 = H source (0 diagonal, 1 vertical state E, 2 horizontal state F),
@@ -144,7 +176,12 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
     __syncthreads();
     const int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (li >= *a.count[self]) return;
-    const int p = a.list[self][li];
+    int p;
+    if (self == 3) {
+        p = trace_task(a.list[3], a.class_count, a.npairs, 3, li);
+    } else {
+        p = a.list[self][li];
+    }
     PairState &s = a.state[p];
     db200_sw_result &res = a.results[p];
     const PairMeta pm = a.meta[p];
@@ -157,12 +194,13 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
     if (self == 3 && *a.count[3] < TRACE_MEDIUM_MIN_JOBS) {
         // few of these jobs: one thread each would only add its latency (~0.3 ms) to the batch - the warp-per-pair
         // kernel runs them side by side (what happens to the chunks of the host pipeline on the soft-clip workload)
-        a.list[bw <= TRACE_WARP_BW ? 1 : 2][atomicAdd(a.count[bw <= TRACE_WARP_BW ? 1 : 2], 1)] = p;
+        trace_push(a.list, a.count, a.class_count, a.npairs, bw <= TRACE_WARP_BW ? 1 : 2, p, readLen, refLen, 0);
         return;
     }
-    uint32_t *slice = narrow_sm + threadIdx.x * TRACE_NARROW_WORDS;
+    uint32_t *slice = narrow_sm + threadIdx.x * (self == 3 ? TRACE_MEDIUM_WORDS : TRACE_NARROW_WORDS);
     uint8_t *dir = reinterpret_cast<uint8_t *>(slice);
-    uint8_t *gdir = nullptr;   // medium jobs: one byte per cell in a private region of the slab
+    uint32_t *gdir = nullptr;  // medium jobs: direction nibbles in a private region of the slab, rows padded to whole words -
+    int wpr = 0;               // one 32-bit store per eight cells (a byte per cell was one partial-sector write per cell)
     int width = 0;
     while (true) {
         width = min(2 * bw + 1, refLen);
@@ -170,18 +208,20 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
             int lvl = trace_level(readLen, refLen, bw);
             if (lvl == 3 && self == 3 && !gdir) {
                 const unsigned long long region = atomicAdd(a.medium_cursor, 1ull);
-                if ((region + 1ull) * (unsigned long long)TRACE_MEDIUM_CELLS <= a.slab_total) gdir = a.slab + region * (unsigned long long)TRACE_MEDIUM_CELLS;
+                if ((region + 1ull) * (unsigned long long)TRACE_MEDIUM_REGION <= a.slab_total)
+                    gdir = reinterpret_cast<uint32_t *>(a.slab + region * (unsigned long long)TRACE_MEDIUM_REGION);
                 else lvl = bw <= TRACE_WARP_BW ? 1 : 2;   // no room left: a cooperative kernel takes the pair
             }
             if (lvl != self) { // the band outgrew this launch: hand the pair (and the band to try next) to a later one
                 s.trace_bw = bw;
-                a.list[lvl][atomicAdd(a.count[lvl], 1)] = p;
+                trace_push(a.list, a.count, a.class_count, a.npairs, lvl, p, readLen, refLen, width);
                 return;
             }
         }
         const bool use_g = self == 3;
+        wpr = (width + 7) >> 3;
         // this attempt's direction nibbles and the two rolling rows of (H, E), band-relative, live in the thread's slice
-        int16_t *Hp = reinterpret_cast<int16_t *>(slice + TRACE_NARROW_DIR_WORDS);
+        int16_t *Hp = reinterpret_cast<int16_t *>(slice + (self == 3 ? 0 : TRACE_NARROW_DIR_WORDS));
         int16_t *Ep = Hp + TRACE_NARROW_ROW, *Hc = Ep + TRACE_NARROW_ROW, *Ec = Hc + TRACE_NARROW_ROW;
         int best = 0;
         int pbeg = 0, pend = -1;
@@ -190,6 +230,7 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
             const int qc = pool_code(a.pool, pm.q_unit, rbeg + i);
             NibReader rt(a.pool, pm.t_unit, tbeg + beg);
             int f = 0, hleft = 0;
+            uint32_t acc = 0;
             const unsigned long long rowbase = (unsigned long long)i * (unsigned long long)width;
             for (int j = beg; j <= end; ++j) {
                 const bool up_in = (i > 0 && j >= pbeg && j <= pend);
@@ -213,8 +254,11 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
                 const int src = (g <= d) ? 0 : (e1 > f1 ? 1 : 2);
                 const uint8_t nib = (uint8_t)(src | (e_open << 2) | (f_open << 3));
                 const unsigned long long cell = rowbase + (unsigned long long)(j - beg);
-                if (use_g) gdir[cell] = nib;
-                else {
+                if (use_g) {
+                    const int c = j - beg;
+                    acc |= (uint32_t)nib << ((c & 7) * 4);
+                    if ((c & 7) == 7 || j == end) { gdir[i * wpr + (c >> 3)] = acc; acc = 0; }
+                } else {
                     uint8_t &byte = dir[cell >> 1];
                     byte = (cell & 1) ? (uint8_t)((byte & 0x0F) | (nib << 4)) : (uint8_t)((byte & 0xF0) | nib);
                 }
@@ -242,7 +286,7 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
             const int x = j - beg;
             if (x < 0 || x >= width || j < 0) { bad = true; break; } // the reference would read out of bounds here
             const unsigned long long cell = (unsigned long long)i * (unsigned long long)width + (unsigned long long)x;
-            const int nib = walk_g ? (int)gdir[cell] : ((dir[cell >> 1] >> ((cell & 1) * 4)) & 15);
+            const int nib = walk_g ? (int)((gdir[i * wpr + (x >> 3)] >> ((x & 7) * 4)) & 15u) : ((dir[cell >> 1] >> ((cell & 1) * 4)) & 15);
             switch (trace_step_code(nib, state)) {
                 case 1: --i; --j; state = 2; op = 0; break;
                 case 2: --i; state = 0; op = 1; break;
@@ -343,7 +387,10 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
         const int ti = sh_task;
         coop_sync<T>();
         if (ti >= *a.count[LEVEL]) break;
-        const int p = a.list[LEVEL][ti];
+        if (threadIdx.x == 0) sh_task = trace_task(a.list[LEVEL], a.class_count, a.npairs, LEVEL, ti);
+        coop_sync<T>();
+        const int p = sh_task;
+        coop_sync<T>();
         PairState &s = a.state[p];
         db200_sw_result &res = a.results[p];
         const PairMeta pm = a.meta[p];
@@ -380,9 +427,12 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
             if (LEVEL == 1 && bw > TRACE_WARP_BW) { escalate = true; break; }
             const int OFF = min(bw, readLen - 1);
             const int XW = OFF + min(bw, refLen - 1) + 1;            // band diagonals with at least one cell
-            const int width = min(2 * bw + 1, refLen);
-            wst = (width + 15) & ~15;                                 // one byte per cell, 16-byte aligned rows
-            const unsigned long long dir_bytes = (unsigned long long)readLen * (unsigned long long)wst;
+            // Direction codes are stored anti-diagonal by anti-diagonal, one byte per cell at half its band diagonal (the
+            // cells of an anti-diagonal sit on every other band diagonal): the threads of a sweep step write
+            // neighbouring bytes - one or two 32-byte sectors per warp store, where row-major storage touched 32.
+            // (Two cells per byte, paired up by a shuffle, measured slower: long contigs 44.7 -> 51.8 ms.)
+            wst = ((XW >> 1) + 1 + 15) & ~15;                         // 16-byte aligned
+            const unsigned long long dir_bytes = (unsigned long long)(readLen + refLen - 1) * (unsigned long long)wst;
             const unsigned long long runs_bytes = (unsigned long long)(readLen + refLen + 4) * 4ull;
             if (XW > WMAX || dir_bytes + runs_bytes + 64 > slab_bytes) {
                 if (LEVEL == 1) escalate = true; else failed = true;   // level 2 has the larger slabs
@@ -422,7 +472,7 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
                     const int src = (g <= d) ? 0 : (e1 > f1 ? 1 : 2);
                     const uint8_t nib = (uint8_t)(src | (e_open << 2) | (f_open << 3));
 #ifndef DB200_TRACE_NOSTORE
-                    slab[(unsigned long long)i * (unsigned long long)wst + (unsigned long long)(j - max(0, i - bw))] = nib;
+                    slab[(unsigned long long)tau * (unsigned long long)wst + (unsigned long long)(x >> 1)] = nib;
 #else
                     if (h == -12345) slab[0] = nib;
 #endif
@@ -438,7 +488,7 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
             bw *= 2;
         }
         if (escalate) {
-            if (threadIdx.x == 0) { s.trace_bw = bw; a.list[2][atomicAdd(a.count[2], 1)] = p; }
+            if (threadIdx.x == 0) { s.trace_bw = bw; trace_push(a.list, a.count, a.class_count, a.npairs, 2, p, readLen, refLen, 0); }
             coop_sync<T>();
             continue;
         }
@@ -450,36 +500,39 @@ __global__ void __launch_bounds__(T) sw_trace_coop_kernel(TraceArgs a)
             coop_sync<T>();
             continue;
         }
-        // ---- walk: rows are staged through shared memory in chunks (coalesced 16-byte copies), one thread follows
+        // ---- walk: anti-diagonals are staged through shared memory in chunks (one bulk copy each), one thread follows
         //      the directions inside the chunk; runs are collected behind the direction bytes, then copied reversed
-        uint32_t *runs = reinterpret_cast<uint32_t *>(slab + (((unsigned long long)readLen * (unsigned long long)wst + 15) & ~15ull));
+        const unsigned long long dir_total = (unsigned long long)(readLen + refLen - 1) * (unsigned long long)wst;
+        uint32_t *runs = reinterpret_cast<uint32_t *>(slab + ((dir_total + 15) & ~15ull));
         {
             uint8_t *stage = reinterpret_cast<uint8_t *>(sm) + (((3u * (WMAX + 2) * sizeof(int16_t) + SEQW * 4u) + 15u) & ~15u);
-            const int stage_rows = max(1, (int)((unsigned)STAGEB / (unsigned)wst));
+            const int stage_taus = max(2, (int)((unsigned)STAGEB / (unsigned)wst));
+            const int OFFW = min(bw, readLen - 1);
             const int width = min(2 * bw + 1, refLen);
             __shared__ int w_i, w_j, w_run, w_prev, w_op, w_state, w_l, w_bad;
             if (threadIdx.x == 0) { w_i = readLen - 1; w_j = refLen - 1; w_run = 0; w_prev = 0; w_op = 0; w_state = 2; w_l = 0; w_bad = 0; }
             coop_sync<T>();
             while (true) {
-                const int i_hi = w_i;
-                if (i_hi <= 0 || w_bad) break;
-                const int i_lo = max(1, i_hi - stage_rows + 1);
-                // one bulk copy (TMA) brings the rows of this chunk; the direction bytes were written with ordinary
-                // stores by this block, hence the proxy fence after the block-wide barrier
+                if (w_i <= 0 || w_bad) break;
+                const int tau_hi = w_i + w_j;
+                const int tau_lo = max(0, tau_hi - stage_taus + 1);
+                // one bulk copy (TMA) brings the anti-diagonals of this chunk; the direction bytes were written with
+                // ordinary stores by this block, hence the proxy fence after the block-wide barrier
                 if (threadIdx.x == 0) {
-                    const uint32_t bytes = (uint32_t)(i_hi - i_lo + 1) * (uint32_t)wst;
+                    const uint32_t bytes = (uint32_t)(tau_hi - tau_lo + 1) * (uint32_t)wst;
                     fence_proxy_async();
                     mbar_expect_tx(&tma_bar, bytes);
-                    tma_bulk_g2s(stage, slab + (unsigned long long)i_lo * (unsigned long long)wst, bytes, &tma_bar);
+                    tma_bulk_g2s(stage, slab + (unsigned long long)tau_lo * (unsigned long long)wst, bytes, &tma_bar);
                 }
                 mbar_wait(&tma_bar, tma_phase);
                 tma_phase ^= 1u;
                 if (threadIdx.x == 0) {
                     int i = w_i, j = w_j, run = w_run, prev = w_prev, op = w_op, state = w_state, l = w_l;
-                    while (i >= i_lo) {
+                    while (i > 0 && i + j >= tau_lo) {
                         const int x = j - max(0, i - bw);
                         if (x < 0 || x >= width || j < 0) { w_bad = 1; break; } // the reference would read out of bounds here
-                        const int nib = stage[(i - i_lo) * wst + x];
+                        if (j - i > bw) { w_bad = 1; break; }   // a cell the sweep never evaluated
+                        const int nib = stage[(i + j - tau_lo) * wst + ((j - i + OFFW) >> 1)];
                         switch (trace_step_code(nib, state)) {
                             case 1: --i; --j; state = 2; op = 0; break;
                             case 2: --i; state = 0; op = 1; break;
