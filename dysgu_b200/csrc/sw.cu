@@ -256,7 +256,35 @@ struct MidArgs {
     uint32_t *unit_cursor;   // bump allocator for reversed sequences (units)
     uint32_t unit_base;
     CfgSel sel;
+    const uint32_t *pool;    // packed codes (perfect-diagonal shortcut)
+    PassOut *rev;
+    int32_t uniform_match;   // the matrix is match / mismatch with zeros for N (no custom matrix): shortcut allowed
 };
+
+// eight packed codes ending at position p >= 7 of the sequence starting at word array w (position p in the top nibble)
+__device__ __forceinline__ uint32_t codes_window(const uint32_t *w, int p)
+{
+    const int a = p - 7;
+    return __funnelshift_r(w[a >> 3], w[p >> 3], (a & 7) * 4);
+}
+
+// Does the alignment ending at (end_q, end_t) consist of L identical A/C/G/T pairs?  Then its score is L x match, no
+// alignment over fewer target columns or fewer query rows can reach that score, and the reverse pass of ssw.c:827-835
+// (first reversed column whose maximum reaches the score, smallest row in it) must stop at (L - 1, L - 1).
+__device__ __forceinline__ bool perfect_diagonal(const uint32_t *qw, const uint32_t *tw, int end_q, int end_t, int L)
+{
+    int eq = end_q, et = end_t, left = L;
+    while (left >= 8) {
+        const uint32_t a = codes_window(qw, eq), b = codes_window(tw, et);
+        if ((a ^ b) != 0u || (a & 0x44444444u) != 0u) return false;
+        eq -= 8; et -= 8; left -= 8;
+    }
+    for (; left > 0; --left, --eq, --et) {
+        const uint32_t a = (qw[eq >> 3] >> ((eq & 7) * 4)) & 15u, b = (tw[et >> 3] >> ((et & 7) * 4)) & 15u;
+        if (a != b || a >= 4u) return false;
+    }
+    return true;
+}
 
 __global__ void sw_mid_kernel(MidArgs a, int32_t *hist)
 {
@@ -275,6 +303,16 @@ __global__ void sw_mid_kernel(MidArgs a, int32_t *hist)
     s.want_cigar = 0;
     if (!want_begin) return;
     if (score == 0) return; // degenerate: handled in finalize (no cells to walk)
+    if (a.uniform_match && score % a.max_match == 0) {
+        const int L = score / a.max_match;
+        if (L <= fw.end_q + 1 && L <= fw.end_t + 1 &&
+            perfect_diagonal(a.pool + (size_t)pm.q_unit * 4, a.pool + (size_t)pm.t_unit * 4, fw.end_q, fw.end_t, L)) {
+            PassOut r;
+            r.score = score; r.end_t = L - 1; r.end_q = L - 1; r.amb = 0;
+            a.rev[p] = r;      // what the reverse pass would report; no reversed problem is built
+            return;
+        }
+    }
     s.want_rev = 1;
     // rows the reverse pass can possibly need: the alignment spans at most tspan columns and
     // g query-only gap bases with  score <= max_match*tspan - (gap_open + (g-1)*gap_extend)
@@ -1011,6 +1049,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     ma.bias = bias; ma.score_size = prm->score_size; ma.flag = prm->flag; ma.filters = prm->filters;
     ma.max_match = max_match; ma.gap_open = prm->gap_open; ma.gap_extend = prm->gap_extend;
     ma.unit_cursor = unit_cursor; ma.unit_base = (uint32_t)seq_units; ma.sel = sel;
+    ma.pool = pool; ma.rev = rev; ma.uniform_match = (!prm->mat && prm->match > 0 && prm->mismatch < prm->match && !getenv("DB200_SW_NO_DIAG_SHORTCUT")) ? 1 : 0;
     sw_mid_kernel<<<gpair, TB, 0, st>>>(ma, hist_r);
     sw_reverse_extract_kernel<<<gwarp_pair, TB, 0, st>>>(meta, rmeta, state, fwd, npairs, pool);
     sw_binscan_kernel<<<1, SW_BINSCAN_THREADS, 0, st>>>(hist_r, start_r, seg_begin_r, seg_count_r);

@@ -1,0 +1,16 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+python -m pytest tests/test_sw_gpu.py tests/test_golden_gpu.py tests/test_callers_gpu.py tests/test_small_path_gpu.py tests/test_input_forms_gpu.py -m gpu -x -q 2>&1 | tail -6 > gpurun_out/p21_pytest.txt
+cat gpurun_out/p21_pytest.txt
+summ() { python -c "
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+r=d['roofline']; s=r['stage_ms_per_step']
+print(sys.argv[2], 'GCUPS', round(d['value']), 'ms', round(d['ms_per_step'],2), 'frac', round(r['frac'],3), 'whole', round(r.get('frac_whole_step') or 0,3), {k: round(v,2) for k,v in s.items() if v > 0.005})
+" "$1" "$2"; }
+B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-merge-shape --e2e-steps 2"
+$B > gpurun_out/p21_on.json 2> gpurun_out/p21_on.err; summ gpurun_out/p21_on.json shortcut_on
+DB200_SW_NO_DIAG_SHORTCUT=1 $B > gpurun_out/p21_off.json 2> gpurun_out/p21_off.err; summ gpurun_out/p21_off.json shortcut_off
+python bench.py --workload pe_contigs --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/p21_pe.json 2> gpurun_out/p21_pe.err; summ gpurun_out/p21_pe.json pe_contigs
+python scripts/parity_sweep.py --pairs 60000 --max-len 600 --seed 12 2>&1 | grep "^SW\|TOTAL" | tail -12
