@@ -93,6 +93,15 @@ __device__ __forceinline__ uint32_t pack16(int v) { return (uint32_t)(v & 0xFFFF
 __device__ __forceinline__ int lo16(uint32_t x) { return (int)(int16_t)(x & 0xFFFF); }
 __device__ __forceinline__ int hi16(uint32_t x) { return (int)(int16_t)(x >> 16); }
 
+// PTX prmt in its generic form: selector nibbles 0..7 pick a byte of {a (0..3), b (4..7)}, bit 3 of a nibble replicates
+// that byte's sign bit instead (0x00 for a non-negative value) - __byte_perm documents three selector bits only
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t unit_word(const uint4 &u, int w)
 {
     return w == 0 ? u.x : (w == 1 ? u.y : (w == 2 ? u.z : u.w));
@@ -124,6 +133,7 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
     constexpr int ROW16 = 2 * K * 32; // uint16 entries per row
     constexpr int TAGB = (K <= 16) ? 4 : 5;
     constexpr bool VMAX = !TAG || COLMAX;
+    constexpr bool LAZY = (G > 1);    // strict-improvement test once per SW_UNR rows instead of every row
     constexpr bool ALIGNED = (K % 16 == 0);   // a lane's 2K columns are whole 16-byte units of the pool
     constexpr int UNITS = ALIGNED ? (2 * K) / 32 : 1;
     constexpr int TW = (2 * K + 7) / 8 + 1;   // !ALIGNED: 32-bit words that can hold a lane's 2K codes at any nibble offset
@@ -140,6 +150,11 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
     __syncthreads();
 
     const uint32_t nGE2 = pack16(-a.sc.gap_extend), nGO2 = pack16(-a.sc.gap_open);
+    // lane hand-over: low half <- previous lane's high half, high half <- own low half, as one byte permute.  The first
+    // lane of a group takes "sign of the high byte of its own low half" instead of the neighbour's bytes: 0 for H (never
+    // negative), 0 or -1 for the horizontal gap state - any non-positive value entering column 0 gives the same H
+    // everywhere (a gap state only matters once it is positive, and then it was re-opened from H).  No select per row.
+    const uint32_t selIn = (lig == 0) ? 0x54DDu : 0x5432u;
     const int seg_begin = a.seg_begin[a.seg], seg_count = a.seg_count[a.seg];
     const unsigned FULL = 0xFFFFFFFFu;
     uint32_t *bnd = nullptr;
@@ -328,10 +343,15 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
                     bchunk = (ps > 0 && t + lane < m) ? src[t + lane] : 0u;
                 }
               }
-#pragma unroll UNR
-              for (int b = 0; b < 8; ++b) {
+#pragma unroll 1
+              for (int hb = 0; hb < 8 / UNR; ++hb) {
+              uint32_t m2r[UNR];
+#pragma unroll
+              for (int bb = 0; bb < UNR; ++bb) {
+                const int b = hb * UNR + bb;
                 const int t = t8 * 8 + b;
-                const int c_lo = (int)((cur >> (4 * b)) & 15u); // the pool only holds codes 0..5
+                // the pool only holds codes 0..5; shift left (an IMAD on the FMA pipe) then right instead of shift + mask
+                const int c_lo = (int)((cur << (28 - 4 * b)) >> 28);
                 const uint16_t *row_lo = prof + c_lo * ROW16 + lane * 2;
 
                 // ---- inputs from the preceding virtual lane ---------------------------------------
@@ -340,14 +360,19 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
                     sh = __shfl_sync(FULL, OH, lane - 1);
                     sv = __shfl_sync(FULL, OV, lane - 1);
                 }
+                uint32_t inH, inV;
                 if (MULTI) {
                     const uint32_t y = __shfl_sync(FULL, bchunk, t & 31);
                     if (lig == 0) { sh = y << 16; sv = y & 0xFFFF0000u; }
+                    inH = __funnelshift_l(sh, OH, 16); // lo <- previous lane's hi, hi <- own lo
+                    inV = __funnelshift_l(sv, OV, 16);
+                } else if (G == 1) {
+                    inH = OH << 16;   // no neighbour: two IMAD.SHL on the FMA pipe
+                    inV = OV << 16;
                 } else {
-                    if (lig == 0) { sh = 0; sv = 0; }
+                    inH = prmt(sh, OH, selIn);
+                    inV = prmt(sv, OV, selIn);
                 }
-                const uint32_t inH = __funnelshift_l(sh, OH, 16); // lo <- previous lane's hi, hi <- own lo
-                const uint32_t inV = __funnelshift_l(sv, OV, 16);
 
                 uint32_t Vv = inV;
                 uint32_t diag = prevIn;
@@ -374,15 +399,14 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
                 OH = H[K - 1];
                 OV = Vv;
                 row_hi = row_lo + 1;
-
-                // ---- running maximum of each virtual lane (strict improvement -> step) ------------
-                // (__vibmax_s16x2's predicate outputs would save four instructions here, but the variant built with
-                //  it produced wrong rows on B200 with CUDA 12.9, so the strict-improvement test stays explicit)
-                const uint32_t nb = __vmaxs2(best2, m2);
-                const uint32_t chg = nb ^ best2;
-                if (chg & 0x0000FFFFu) bstep_lo = t;
-                if (chg & 0xFFFF0000u) bstep_hi = t;
-                best2 = nb;
+                if (LAZY) m2r[bb] = m2;   // running maximum of each virtual lane: examined once per UNR rows, below
+                else {
+                    const uint32_t nb = __vmaxs2(best2, m2);
+                    const uint32_t chg = nb ^ best2;
+                    if (chg & 0x0000FFFFu) bstep_lo = t;
+                    if (chg & 0xFFFF0000u) bstep_hi = t;
+                    best2 = nb;
+                }
 
                 if (WATCH) {
                     uint32_t hs_lo = 0xFFFFFFFFu, hs_hi = 0xFFFFFFFFu;
@@ -421,6 +445,30 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
                         }
                     }
                 }
+              }
+              // ---- running maximum of each virtual lane (strict improvement -> step) ------------
+              // One three-way maximum per two rows finds out whether any of the UNR rows improved a lane's maximum; only
+              // then (a warp-uniform branch) the rows are examined one by one for the first step of strict improvement.
+              // With 32 pairs in a warp (G = 1) some pair improves in most row groups and the per-row test is cheaper
+              // (B200, 32-column targets: 110 issue slots per row against 121).
+              // (__vibmax_s16x2's predicate outputs would do it per row in one instruction, but the variant built with
+              //  it produced wrong rows on B200 with CUDA 12.9.)
+              if (LAZY) {
+                uint32_t nb = best2;
+#pragma unroll
+                for (int bb = 0; bb + 1 < UNR; bb += 2) nb = __vimax3_s16x2(nb, m2r[bb], m2r[bb + 1]);
+                if (UNR & 1) nb = __vmaxs2(nb, m2r[UNR - 1]);
+                if (__any_sync(FULL, nb != best2)) {
+#pragma unroll
+                    for (int bb = 0; bb < UNR; ++bb) {
+                        const uint32_t x = __vmaxs2(best2, m2r[bb]);
+                        const uint32_t chg = x ^ best2;
+                        if (chg & 0x0000FFFFu) bstep_lo = t8 * 8 + hb * UNR + bb;
+                        if (chg & 0xFFFF0000u) bstep_hi = t8 * 8 + hb * UNR + bb;
+                        best2 = x;
+                    }
+                }
+              }
               }
             }
 
