@@ -915,7 +915,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     const int wide_blocks = std::min(e->sm_count * 4, 1024);
     const size_t slab_bytes = (e->trace_slab_bytes / (size_t)wide_blocks) & ~(size_t)255;
     uint8_t *slab = ws.alloc<uint8_t>(slab_bytes * (size_t)wide_blocks);
-    int32_t *narrow_list = ws.alloc<int32_t>(npairs);
+    int32_t *narrow_list = ws.alloc<int32_t>((size_t)npairs * TRACE_MEDIUM_CLASSES);
     int32_t *medium_list = ws.alloc<int32_t>((size_t)npairs * TRACE_MEDIUM_CLASSES);
     int32_t *wide_list = ws.alloc<int32_t>((size_t)npairs * TRACE_MEDIUM_CLASSES);
     int32_t *slab_scalar_list = ws.alloc<int32_t>((size_t)npairs * TRACE_MEDIUM_CLASSES);
@@ -1108,6 +1108,8 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     for (int l = 0; l < 3; ++l) { ta.count[l] = counters + 136 + l; ta.counter[l] = counters + 140 + l; }
     ta.count[3] = counters + 139;
     ta.class_count = counters + 160;   // [4][TRACE_MEDIUM_CLASSES]
+    ta.medium_min_jobs = TRACE_MEDIUM_MIN_JOBS;
+    if (const char *mj = getenv("DB200_TRACE_MEDIUM_MIN_JOBS")) ta.medium_min_jobs = atoi(mj);
     const int warp_blocks = e->sm_count * 24;
     ta.coop_blocks[0] = 0; ta.coop_blocks[1] = warp_blocks; ta.coop_blocks[2] = wide_blocks;
     sw_trace_classify_kernel<<<gpair, TB, 0, st>>>(ta);

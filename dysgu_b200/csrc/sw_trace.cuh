@@ -33,7 +33,8 @@ struct TraceArgs {
     int32_t coop_blocks[3];        // grid size per level (slab = slab_total / blocks)
     unsigned long long slab_total;
     unsigned long long *medium_cursor;   // level 0, jobs too large for the shared-memory slice: regions of the slab handed out so far
-    int32_t *class_count;                // [4][TRACE_MEDIUM_CLASSES] fill of the sub-lists of lists 1..3 (count[l] is their sum)
+    int32_t *class_count;                // [4][TRACE_MEDIUM_CLASSES] fill of the sub-lists of every list (count[l] is their sum)
+    int32_t medium_min_jobs;             // fewer slab-backed scalar jobs than this go to the warp-per-pair kernel instead
     int32_t debug;
 };
 
@@ -59,18 +60,18 @@ constexpr int TRACE_NARROW_ROW = TRACE_NARROW_WIDTH + 2;
 constexpr int TRACE_NARROW_WORDS = (TRACE_NARROW_DIR_WORDS + 4 * TRACE_NARROW_ROW / 2) | 1;
 constexpr int TRACE_MEDIUM_WORDS = (4 * TRACE_NARROW_ROW / 2) | 1;   // list 3 keeps its directions in the slab: rolling rows only
 constexpr int TRACE_NARROW_THREADS = 128;
-// Work lists 1..3 are TRACE_MEDIUM_CLASSES sub-lists of `stride` entries each, by job size, taken largest class first:
+// The work lists are TRACE_MEDIUM_CLASSES sub-lists of `stride` entries each, by job size, taken largest class first:
 // the 32 jobs of a warp of the scalar kernel are of similar length, and the cooperative kernels start their longest
 // pairs first instead of leaving one for the end of the launch (a 6 kb contig pair sweeps for milliseconds).
 __device__ __forceinline__ int trace_class(int lvl, int readLen, int refLen, int width)
 {
     if (lvl == 3) return min(TRACE_MEDIUM_CLASSES - 1, (readLen * width) / TRACE_MEDIUM_CLASS_CELLS);
+    if (lvl == 0) return min(TRACE_MEDIUM_CLASSES - 1, (readLen * width) / (TRACE_NARROW_CELLS / TRACE_MEDIUM_CLASSES));
     return max(0, min(TRACE_MEDIUM_CLASSES - 1, 24 - __clz(readLen + refLen)));   // < 256 steps: 0 ... >= 16384: 7
 }
 __device__ __forceinline__ void trace_push(int32_t *const *list, int32_t *const *count, int32_t *ccount, long long stride, int lvl, int p,
                                            int readLen, int refLen, int width)
 {
-    if (lvl == 0) { list[0][atomicAdd(count[0], 1)] = p; return; }
     const int c = trace_class(lvl, readLen, refLen, width);
     atomicAdd(count[lvl], 1);
     list[lvl][(long long)c * stride + atomicAdd(ccount + lvl * TRACE_MEDIUM_CLASSES + c, 1)] = p;
@@ -176,12 +177,7 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
     __syncthreads();
     const int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (li >= *a.count[self]) return;
-    int p;
-    if (self == 3) {
-        p = trace_task(a.list[3], a.class_count, a.npairs, 3, li);
-    } else {
-        p = a.list[self][li];
-    }
+    const int p = trace_task(a.list[self], a.class_count, a.npairs, self, li);
     PairState &s = a.state[p];
     db200_sw_result &res = a.results[p];
     const PairMeta pm = a.meta[p];
@@ -191,7 +187,7 @@ __global__ void __launch_bounds__(TRACE_NARROW_THREADS) sw_trace_narrow_kernel(T
     const int rbeg = res.read_begin1, tbeg = res.ref_begin1; // local copies: the byte stores below may alias `res`
     const int gapO = a.sc.gap_open, gapE = a.sc.gap_extend;
     int bw = self == 0 ? abs(refLen - readLen) + 1 : s.trace_bw;
-    if (self == 3 && *a.count[3] < TRACE_MEDIUM_MIN_JOBS) {
+    if (self == 3 && *a.count[3] < a.medium_min_jobs) {
         // few of these jobs: one thread each would only add its latency (~0.3 ms) to the batch - the warp-per-pair
         // kernel runs them side by side (what happens to the chunks of the host pipeline on the soft-clip workload)
         trace_push(a.list, a.count, a.class_count, a.npairs, bw <= TRACE_WARP_BW ? 1 : 2, p, readLen, refLen, 0);
