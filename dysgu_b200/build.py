@@ -23,7 +23,7 @@ SOURCES = ["engine.cu", "sw.cu", "ed.cu", "queue.cu", "format.cu", "multi.cu", "
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "dysgu_b200_align.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--diag-suppress", "177"]
+FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--diag-suppress", "177"] + os.environ.get("DB200_NVCC_FLAGS", "").split()
 
 
 def _newer(target, deps):

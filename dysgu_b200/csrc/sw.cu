@@ -286,31 +286,30 @@ __device__ __forceinline__ bool perfect_diagonal(const uint32_t *qw, const uint3
     return true;
 }
 
-__global__ void sw_mid_kernel(MidArgs a, int32_t *hist)
+// what a pair still needs after the forward pass; returns the 16-byte units its reversed problem takes (0: none)
+__device__ __forceinline__ uint32_t sw_mid_pair(const MidArgs &a, int64_t p, PairMeta &r, uint32_t &uq)
 {
-    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= a.npairs) return;
     PairState &s = a.state[p];
-    if (s.status != DB200_PAIR_OK) return;
+    if (s.status != DB200_PAIR_OK) return 0;
     const PairMeta pm = a.meta[p];
     const PassOut fw = a.fwd[p];
     const int score = fw.score;
     const bool overflow8 = score + a.bias >= 255;
     s.use_word = (a.score_size == 1) || (a.score_size == 2 && overflow8);
-    if (a.score_size == 0 && overflow8) { s.status = DB200_PAIR_OVERFLOW; return; }
+    if (a.score_size == 0 && overflow8) { s.status = DB200_PAIR_OVERFLOW; return 0; }
     const bool want_begin = !(a.flag == 0 || (a.flag == 2 && score < a.filters));
     s.want_rev = 0;
     s.want_cigar = 0;
-    if (!want_begin) return;
-    if (score == 0) return; // degenerate: handled in finalize (no cells to walk)
+    if (!want_begin) return 0;
+    if (score == 0) return 0; // degenerate: handled in finalize (no cells to walk)
     if (a.uniform_match && score % a.max_match == 0) {
         const int L = score / a.max_match;
         if (L <= fw.end_q + 1 && L <= fw.end_t + 1 &&
             perfect_diagonal(a.pool + (size_t)pm.q_unit * 4, a.pool + (size_t)pm.t_unit * 4, fw.end_q, fw.end_t, L)) {
-            PassOut r;
-            r.score = score; r.end_t = L - 1; r.end_q = L - 1; r.amb = 0;
-            a.rev[p] = r;      // what the reverse pass would report; no reversed problem is built
-            return;
+            PassOut o;
+            o.score = score; o.end_t = L - 1; o.end_q = L - 1; o.amb = 0;
+            a.rev[p] = o;      // what the reverse pass would report; no reversed problem is built
+            return 0;
         }
     }
     s.want_rev = 1;
@@ -320,17 +319,72 @@ __global__ void sw_mid_kernel(MidArgs a, int32_t *hist)
     int g = (a.max_match * tspan - score - a.gap_open) / a.gap_extend + 1;
     if (a.max_match * tspan - score - a.gap_open < 0) g = 0;
     const int rows = min(fw.end_q + 1, tspan + max(g, 0));
-    const uint32_t uq = (uint32_t)((rows + 31) >> 5), ut = (uint32_t)((tspan + 31) >> 5);
-    const uint32_t u0 = a.unit_base + atomicAdd(a.unit_cursor, uq + ut);
-    PairMeta r;
-    r.q_unit = u0; r.t_unit = u0 + uq; r.m = rows; r.n = tspan;
-    a.rmeta[p] = r;
-    atomicAdd(&hist[sw_bin_key(a.sel, r.m, r.n, 0)], 1);
+    uq = (uint32_t)((rows + 31) >> 5);
+    const uint32_t ut = (uint32_t)((tspan + 31) >> 5);
+    r.m = rows; r.n = tspan;
+    return uq + ut;
 }
 
-// one warp per pair: write reversed prefixes as packed codes
+// The units of the reversed sequences come from one bump cursor: a warp adds up what its pairs need and takes it with one
+// atomic (one returning atomic per pair on a single address took 0.2 ms per 524,288 pairs - as long as the rest of the stage).
+__global__ void sw_mid_kernel(MidArgs a, int32_t *hist)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    PairMeta r;
+    r.q_unit = 0; r.t_unit = 0; r.m = 0; r.n = 0;
+    uint32_t uq = 0;
+    const uint32_t need = p < a.npairs ? sw_mid_pair(a, p, r, uq) : 0u;
+    uint32_t incl = need;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(a.unit_cursor, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+    if (need) {
+        const uint32_t u0 = a.unit_base + base + (incl - need);
+        r.q_unit = u0; r.t_unit = u0 + uq;
+        a.rmeta[p] = r;
+        atomicAdd(&hist[sw_bin_key(a.sel, r.m, r.n, 0)], 1);
+    }
+}
+
+// the eight codes of x in reversed order (byte reversal, then the two codes of every byte swapped)
+__device__ __forceinline__ uint32_t codes_reversed(uint32_t x)
+{
+    x = __byte_perm(x, 0u, 0x0123);
+    return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+}
+
+// words of R[i] = S[end - i], i < len (positions past len hold the padding code), written to dst
+__device__ __forceinline__ void reverse_prefix_words(const uint32_t *src, int end, int len, uint32_t *dst, int lane)
+{
+    const int nwords = ((len + 31) >> 5) << 2;
+    for (int w = lane; w < nwords; w += 32) {
+        const int p = end - 8 * w;          // source position of the word's first code
+        const int cnt = len - 8 * w;        // codes of this word that exist
+        uint32_t x;
+        if (cnt <= 0) x = 0x55555555u;
+        else if (p >= 7) {
+            x = codes_reversed(codes_window(src, p));
+            if (cnt < 8) { const uint32_t keep = (1u << (4 * cnt)) - 1u; x = (x & keep) | (0x55555555u & ~keep); }
+        } else {
+            x = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int i = p - e;
+                const uint32_t c = (e < cnt && i >= 0) ? ((src[i >> 3] >> ((i & 7) * 4)) & 15u) : (uint32_t)SW_PAD_CODE;
+                x |= c << (4 * e);
+            }
+        }
+        dst[w] = x;
+    }
+}
+
+// one warp per pair: write reversed prefixes as packed codes, a 32-bit word (eight codes) at a time
 __global__ void sw_reverse_extract_kernel(const PairMeta *meta, const PairMeta *rmeta, const PairState *state,
-                                          const PassOut *fwd, int64_t npairs, uint32_t *pool)
+                                          const PassOut *fwd, int64_t npairs, const uint32_t *src_pool, uint32_t *pool)
 {
     const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -339,35 +393,10 @@ __global__ void sw_reverse_extract_kernel(const PairMeta *meta, const PairMeta *
     if (s.status != DB200_PAIR_OK || !s.want_rev) return;
     const PairMeta pm = meta[p], r = rmeta[p];
     const PassOut fw = fwd[p];
-    const uint4 *pool4 = reinterpret_cast<const uint4 *>(pool);
-    {   // reversed query prefix: R[i] = Q[end_q - i], i < r.m
-        uint32_t *dst = pool + (size_t)r.q_unit * 4;
-        const int nwords = ((r.m + 31) >> 5) << 2;
-        for (int w = lane; w < nwords; w += 32) {
-            uint32_t x = 0;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int i = w * 8 + e;
-                const uint32_t c = i < r.m ? (uint32_t)pool_code(pool4, pm.q_unit, fw.end_q - i) : (uint32_t)SW_PAD_CODE;
-                x |= c << (4 * e);
-            }
-            dst[w] = x;
-        }
-    }
-    {   // reversed target prefix: R[j] = T[end_t - j], j < r.n
-        uint32_t *dst = pool + (size_t)r.t_unit * 4;
-        const int nwords = ((r.n + 31) >> 5) << 2;
-        for (int w = lane; w < nwords; w += 32) {
-            uint32_t x = 0;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int j = w * 8 + e;
-                const uint32_t c = j < r.n ? (uint32_t)pool_code(pool4, pm.t_unit, fw.end_t - j) : (uint32_t)SW_PAD_CODE;
-                x |= c << (4 * e);
-            }
-            dst[w] = x;
-        }
-    }
+    // the forward sequences may be the caller's packed batch; reversed query prefix R[i] = Q[end_q - i], i < r.m, and
+    // reversed target prefix R[j] = T[end_t - j], j < r.n
+    reverse_prefix_words(src_pool + (size_t)pm.q_unit * 4, fw.end_q, r.m, pool + (size_t)r.q_unit * 4, lane);
+    reverse_prefix_words(src_pool + (size_t)pm.t_unit * 4, fw.end_t, r.n, pool + (size_t)r.t_unit * 4, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -814,7 +843,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     int64_t fine_min_pairs = 16384;
     if (const char *fm = getenv("DB200_SW_FINE_MIN_PAIRS")) fine_min_pairs = atoll(fm);
     const bool fine = npairs >= fine_min_pairs && !getenv("DB200_SW_NO_FINE");
-    int ovh = 21;   // ALU-pipe instructions per row outside the recurrence (hand-over, strict-improvement test, query decode)
+    int ovh = 8;    // ALU-pipe instructions per row outside the recurrence (hand-over, query decode; measured optimum on the headline step)
     if (const char *ov = getenv("DB200_SW_ROW_OVERHEAD")) ovh = atoi(ov);
     int force_k = 0, force_g = 0;   // measurement aid: DB200_SW_FORCE_CFG=K,G leaves that configuration alone in the table
     if (const char *fc = getenv("DB200_SW_FORCE_CFG")) sscanf(fc, "%d,%d", &force_k, &force_g);
@@ -944,6 +973,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     const unsigned gwarp_seq = (unsigned)((nseq * 32 + TB - 1) / TB), gwarp_pair = (unsigned)((npairs * 32 + TB - 1) / TB);
 
     // 1. pack ---------------------------------------------------------------------------------------
+    const uint32_t *pool_f = pool;   // where the forward sequences live
     prof_mark(e, st, ST_BEGIN);
     sw_units_kernel<<<gseq, TB, 0, st>>>(d_qoff, d_toff, d_qlen, d_tlen, npairs, units);
     count_launch(e);
@@ -952,7 +982,10 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
         // the caller's batch is already in pool format ([all queries][all targets], 32 bases per 16-byte unit): one device copy
         // instead of the pack kernel; q_bytes / t_bytes are base counts, so the units are bounded by seq_units
         if (packed_units < 0 || (size_t)packed_units > seq_units) { set_error("sw_batch: packed unit count does not match the lengths"); return DB200_ERR_ARG; }
-        DB200_CUDA_CHECK(cudaMemcpyAsync(pool, d_packed, (size_t)packed_units * 16, cudaMemcpyDeviceToDevice, st));
+        // 16-byte aligned: the kernels read the caller's batch in place (the forward sequences are never written; reversed
+        // sequences go to the workspace pool); otherwise one device copy into the workspace pool
+        if ((reinterpret_cast<uintptr_t>(d_packed) & 15u) == 0 && !getenv("DB200_SW_COPY_PACKED")) pool_f = d_packed;
+        else DB200_CUDA_CHECK(cudaMemcpyAsync(pool, d_packed, (size_t)packed_units * 16, cudaMemcpyDeviceToDevice, st));
         sw_meta_kernel<<<gpair, TB, 0, st>>>(d_qlen, d_tlen, npairs, unit_off, meta);
     } else {
         sw_pack_kernel<<<gwarp_seq, TB, 0, st>>>(d_qbuf, d_qoff, d_tbuf, d_toff, d_qlen, d_tlen, npairs, unit_off, pool, meta);
@@ -975,7 +1008,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     prof_mark(e, st, ST_BUCKET);
     PassArgs pa;
     memset(&pa, 0, sizeof(pa));
-    pa.pool = reinterpret_cast<const uint4 *>(pool);
+    pa.pool = reinterpret_cast<const uint4 *>(pool_f);
     pa.colmax = colmax; pa.colmax_off = colmax_off;
     pa.boundary = boundary; pa.boundary_stride = bstride;
     pa.bnd_pool = bnd_pool; pa.bnd_cap = (unsigned long long)bnd_cap;
@@ -1049,14 +1082,15 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     ma.bias = bias; ma.score_size = prm->score_size; ma.flag = prm->flag; ma.filters = prm->filters;
     ma.max_match = max_match; ma.gap_open = prm->gap_open; ma.gap_extend = prm->gap_extend;
     ma.unit_cursor = unit_cursor; ma.unit_base = (uint32_t)seq_units; ma.sel = sel;
-    ma.pool = pool; ma.rev = rev; ma.uniform_match = (!prm->mat && prm->match > 0 && prm->mismatch < prm->match && !getenv("DB200_SW_NO_DIAG_SHORTCUT")) ? 1 : 0;
+    ma.pool = pool_f; ma.rev = rev; ma.uniform_match = (!prm->mat && prm->match > 0 && prm->mismatch < prm->match && !getenv("DB200_SW_NO_DIAG_SHORTCUT")) ? 1 : 0;
     sw_mid_kernel<<<gpair, TB, 0, st>>>(ma, hist_r);
-    sw_reverse_extract_kernel<<<gwarp_pair, TB, 0, st>>>(meta, rmeta, state, fwd, npairs, pool);
+    sw_reverse_extract_kernel<<<gwarp_pair, TB, 0, st>>>(meta, rmeta, state, fwd, npairs, pool_f, pool);
     sw_binscan_kernel<<<1, SW_BINSCAN_THREADS, 0, st>>>(hist_r, start_r, seg_begin_r, seg_count_r);
     sw_scatter_kernel<<<gpair, TB, 0, st>>>(rmeta, state, npairs, 1, sel, start_r, fill_r, tasks_r);
     count_launch(e, 4);
     prof_mark(e, st, ST_REVERSE_PREP);
     pa.bnd_off = bnd_off + npairs;   // the reversed problems keep their own boundary columns
+    pa.pool = reinterpret_cast<const uint4 *>(pool);   // ... and live in the workspace pool
     { const int rc = aux_fork(e, st); if (rc) return rc; }
     for (int oi = 0; oi < SW_NCFG; ++oi) {
         const int cfg = order[oi];
@@ -1097,7 +1131,7 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     if (fa.defer_second_from > 0) { sw_second_best_kernel<<<gwarp_pair, TB, 0, st>>>(fa); count_launch(e); }
     prof_mark(e, st, ST_FINALIZE);
     TraceArgs ta;
-    ta.pool = reinterpret_cast<const uint4 *>(pool); ta.meta = meta; ta.state = state; ta.results = d_results; ta.npairs = npairs;
+    ta.pool = reinterpret_cast<const uint4 *>(pool_f); ta.meta = meta; ta.state = state; ta.results = d_results; ta.npairs = npairs;
     ta.sc = sc;
     ta.cigar_pool = cigar_pool; ta.cigar_cursor = cigar_cursor; ta.cigar_cap = (unsigned long long)cig_pool_cap;
     ta.overflow_flag = overflow_flag;
