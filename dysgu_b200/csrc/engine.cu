@@ -839,8 +839,12 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
         // overlap, their kernels do not - two batches' persistent bucket kernels sharing the SMs took 41 ms each instead of 22
         // (B200, 524,288 pairs).  The kernels of a call start when the previous call's kernels on this device have finished.
         const bool whole_batch = fixed_chunks && c0 == 0 && c1 == npairs && e->host_chunk_pairs > 0;
+        // The lock is held from the wait to the record: a call that looked at the last event while another call was still
+        // enqueuing its kernels would wait for the call before that one and run side by side with it (seen with three
+        // threads starting together: their first calls took 64 ms of kernel time each instead of 19.7).
+        std::unique_lock<std::mutex> chain_lk(g_chain_mu, std::defer_lock);
         if (whole_batch) {
-            std::lock_guard<std::mutex> lk(g_chain_mu);
+            chain_lk.lock();
             if (g_chain_last[e->device] && g_chain_last[e->device] != e->ev_chain) DB200_CUDA_CHECK(cudaStreamWaitEvent(st, g_chain_last[e->device], 0));
         }
         if (timeline) { cudaEventRecord(rec.ev[1], cst); cudaEventRecord(rec.ev[2], st); }
@@ -849,9 +853,9 @@ static int sw_batch_host_body(Engine *e, int device, const db200_sw_params *para
                                   cig_bound, d_coff, d_status, nullptr, st, nullptr, Q.len ? d_lens : nullptr, T.len ? d_lens + n : nullptr, d_pk, qu + tu);
         if (rc) return rc;
         if (whole_batch) {
-            std::lock_guard<std::mutex> lk(g_chain_mu);
             DB200_CUDA_CHECK(cudaEventRecord(e->ev_chain, st));
             g_chain_last[e->device] = e->ev_chain;
+            chain_lk.unlock();
         }
         DB200_CUDA_CHECK(cudaMemcpyAsync(results + c0, d_res, sizeof(db200_sw_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (status) DB200_CUDA_CHECK(cudaMemcpyAsync(status + c0, d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
