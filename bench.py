@@ -750,7 +750,7 @@ def main():
     ap.add_argument("--workload", default="remap_windows", choices=sorted(WORKLOADS), help="default: the headline (BASELINE configs[1])")
     ap.add_argument("--pairs", type=int, default=0, help="pairs per step per GPU (0: the workload's default)")
     ap.add_argument("--ref-pairs", type=int, default=0, help="pairs per step of the CPU reference sample (0: the workload's default)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10, help="steps per host thread of the end-to-end arms (the streaming arm runs 3 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-merge-shape", action="store_true", help="skip the long-contig (configs 4/5) figure that rides on the default line")
     args = ap.parse_args()

@@ -837,10 +837,12 @@ int sw_batch_device_impl(Engine *e, Arena &ws, const db200_sw_params *prm, const
     sc16.gap_open = sc.gap_open * 16; sc16.gap_extend = sc.gap_extend * 16;
     sc32.gap_open = sc.gap_open * 32; sc32.gap_extend = sc.gap_extend * 32;
     // ---- configurations usable in this call ------------------------------------------------------------
-    // Fine configurations (sw_launch.cuh) pay for themselves when the buckets are large; a small batch would only see
-    // their extra (mostly empty) launches, so it keeps the eleven classic ones.
+    // Fine configurations (sw_launch.cuh) pay for themselves when the buckets are large: ~60 usable configurations split a
+    // batch (or a chunk of the host pipeline) into as many persistent launches.  The ASCII host call, whose 32k-147k-pair
+    // chunks arrive in submission order, went from 27.4 to 34 ms per 524,288 pairs with them (500-2,500 pairs per launch);
+    // whole batches of that size gain 6 %.  Smaller calls keep the eleven classic configurations.
     const SwCfg *cfgs = sw_cfg_table();
-    int64_t fine_min_pairs = 16384;
+    int64_t fine_min_pairs = 196608;
     if (const char *fm = getenv("DB200_SW_FINE_MIN_PAIRS")) fine_min_pairs = atoll(fm);
     const bool fine = npairs >= fine_min_pairs && !getenv("DB200_SW_NO_FINE");
     int ovh = 8;    // ALU-pipe instructions per row outside the recurrence (hand-over, query decode; measured optimum on the headline step)

@@ -196,7 +196,7 @@ def test_device_entry_point_sub_batches_share_one_cigar_csr():
 
 
 # ---- fine-grained kernel configurations (K = 8..18 columns per virtual lane, sw_launch.cuh) --------------------------
-# Large batches choose them per pair by cost; the tests switch them on for small batches (DB200_SW_FINE_MIN_PAIRS=0)
+# Calls of >= 196,608 pairs choose them per pair by cost; the tests switch them on for small batches (DB200_SW_FINE_MIN_PAIRS=0)
 # and compare with the oracle and with the classic configurations.
 
 @pytest.mark.parametrize("scoring", SCORINGS)
@@ -236,13 +236,14 @@ def test_fine_configurations_every_target_length(monkeypatch):
 
 
 def test_fine_configurations_headline_shape_and_large_match_scores(monkeypatch):
-    # 40,000 window / clip pairs take the fine configurations by default (>= 16,384 pairs); match = 5 leaves the tag bits
-    # only to the narrower configurations, the others fall back to the classic ones inside the same call
+    # 40,000 window / clip pairs through the fine configurations (by default only calls of >= 196,608 pairs take them);
+    # match = 5 leaves the tag bits only to the narrower configurations, the others fall back to the classic ones
+    # inside the same call
+    monkeypatch.setenv("DB200_SW_FINE_MIN_PAIRS", "0")
     q, t, prm = workloads.remap_windows(40000, seed=23)
     res = batch.sw_align_batch(q, t, **prm)
     ref = O.oracle_sw((q.buf, q.off), (t.buf, t.off), prm["match"], prm["mismatch"], prm["gap_open"], prm["gap_extend"], csr=True)
     assert np.array_equal(res.fixed, ref.fixed) and np.array_equal(res.cigar, ref.cigar) and np.array_equal(res.cigar_off, ref.cigar_off)
-    monkeypatch.setenv("DB200_SW_FINE_MIN_PAIRS", "0")
     qs, ts = pairgen.sw_pairs(515, 3000, 600)
     res = batch.sw_align_batch(qs, ts, 5, -4, 8, 2)
     ref = O.oracle_sw(qs, ts, 5, -4, 8, 2)
