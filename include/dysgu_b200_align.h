@@ -190,7 +190,9 @@ int db200_sw_batch_host_packed(int device, const db200_sw_params *params,
                                db200_sw_result *results, uint32_t *cigar_buf, int64_t cigar_cap,
                                int64_t *cigar_off, int32_t *status);
 /* The pre-packed form with everything resident in device memory: d_units = [all queries][all targets], dense; q_bases /
- * t_bases the sums of the lengths; otherwise as db200_sw_batch_device. */
+ * t_bases the sums of the lengths; otherwise as db200_sw_batch_device.  A 16-byte aligned d_units is read in place by every
+ * kernel of the call (scoring, reverse preparation, traceback) and never written: it must stay unchanged until the work
+ * enqueued on `stream` has finished, like the other device inputs.  An unaligned one is copied into the workspace first. */
 int db200_sw_batch_device_packed(int device, const db200_sw_params *params, const uint32_t *d_units, int64_t n_units,
                                  const int32_t *d_qlen, const int32_t *d_tlen, int64_t q_bases, int64_t t_bases, int64_t npairs,
                                  int32_t max_query_len, int32_t max_target_len, const int32_t *d_mask_len,
