@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
 #define SW_UNR 4
 #endif
             constexpr int UNR = SW_UNR;
+            static_assert(UNR == 4, "the query decode below takes the codes of four rows from two 8-bit windows");
             const int trips = (steps + 7) >> 3;
             for (int t8 = 0; t8 < trips; ++t8) {
               {
@@ -346,13 +347,21 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
 #pragma unroll 1
               for (int hb = 0; hb < 8 / UNR; ++hb) {
               uint32_t m2r[UNR];
+              // The running maximum of a virtual lane is one chain through all its cells: a row group starts from the best
+              // value so far (no zero per row, no fold at the end) and m2r[] keeps what it was after each row.
+              uint32_t m2 = best2;
+              // codes of this group's rows: one variable shift per group, then a constant mask and an IMAD per row (the
+              // mask keeps the code in place, the multiply scales it to the profile row: (x & 0xF0) * (row / 16) ...)
+              const uint32_t curh = cur >> (4 * UNR * hb);
+              const uint32_t curh2 = curh >> 8;
 #pragma unroll
               for (int bb = 0; bb < UNR; ++bb) {
                 const int b = hb * UNR + bb;
                 const int t = t8 * 8 + b;
-                // the pool only holds codes 0..5; shift left (an IMAD on the FMA pipe) then right instead of shift + mask
-                const int c_lo = (int)((cur << (28 - 4 * b)) >> 28);
-                const uint16_t *row_lo = prof + c_lo * ROW16 + lane * 2;
+                // the pool only holds codes 0..5
+                const uint32_t cw = (bb & 2) ? curh2 : curh;
+                const uint16_t *row_lo = (bb & 1) ? prof + ((cw & 0xF0u) * (uint32_t)(ROW16 / 16)) + lane * 2
+                                                  : prof + ((cw & 0x0Fu) * (uint32_t)ROW16) + lane * 2;
 
                 // ---- inputs from the preceding virtual lane ---------------------------------------
                 uint32_t sh = OH, sv = OV;
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
                 uint32_t Vv = inV;
                 uint32_t diag = prevIn;
                 prevIn = inH;
-                uint32_t m2 = 0;
+                if (!LAZY) m2 = best2;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     {
@@ -401,11 +410,10 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
                 row_hi = row_lo + 1;
                 if (LAZY) m2r[bb] = m2;   // running maximum of each virtual lane: examined once per UNR rows, below
                 else {
-                    const uint32_t nb = __vmaxs2(best2, m2);
-                    const uint32_t chg = nb ^ best2;
+                    const uint32_t chg = m2 ^ best2;
                     if (chg & 0x0000FFFFu) bstep_lo = t;
                     if (chg & 0xFFFF0000u) bstep_hi = t;
-                    best2 = nb;
+                    best2 = m2;
                 }
 
                 if (WATCH) {
@@ -447,25 +455,20 @@ __global__ void __launch_bounds__(SW_PASS_THREADS, (K <= SW_FINE_KMAX && !MULTI)
                 }
               }
               // ---- running maximum of each virtual lane (strict improvement -> step) ------------
-              // One three-way maximum per two rows finds out whether any of the UNR rows improved a lane's maximum; only
-              // then (a warp-uniform branch) the rows are examined one by one for the first step of strict improvement.
+              // The chain's value after the group tells whether any of the UNR rows improved a lane's maximum; only then
+              // (a warp-uniform branch) the rows' snapshots are examined one by one for the first step of strict improvement.
               // With 32 pairs in a warp (G = 1) some pair improves in most row groups and the per-row test is cheaper
               // (B200, 32-column targets: 110 issue slots per row against 121).
               // (__vibmax_s16x2's predicate outputs would do it per row in one instruction, but the variant built with
               //  it produced wrong rows on B200 with CUDA 12.9.)
               if (LAZY) {
-                uint32_t nb = best2;
-#pragma unroll
-                for (int bb = 0; bb + 1 < UNR; bb += 2) nb = __vimax3_s16x2(nb, m2r[bb], m2r[bb + 1]);
-                if (UNR & 1) nb = __vmaxs2(nb, m2r[UNR - 1]);
-                if (__any_sync(FULL, nb != best2)) {
+                if (__any_sync(FULL, m2 != best2)) {
 #pragma unroll
                     for (int bb = 0; bb < UNR; ++bb) {
-                        const uint32_t x = __vmaxs2(best2, m2r[bb]);
-                        const uint32_t chg = x ^ best2;
+                        const uint32_t chg = m2r[bb] ^ best2;   // m2r[] never decreases: a changed half is an improved half
                         if (chg & 0x0000FFFFu) bstep_lo = t8 * 8 + hb * UNR + bb;
                         if (chg & 0xFFFF0000u) bstep_hi = t8 * 8 + hb * UNR + bb;
-                        best2 = x;
+                        best2 = m2r[bb];
                     }
                 }
               }
