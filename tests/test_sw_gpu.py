@@ -248,3 +248,46 @@ def test_fine_configurations_headline_shape_and_large_match_scores(monkeypatch):
     res = batch.sw_align_batch(qs, ts, 5, -4, 8, 2)
     ref = O.oracle_sw(qs, ts, 5, -4, 8, 2)
     compare(qs, ts, res, ref, "fine match=5")
+
+
+# ---- second half of round 2: perfect-diagonal shortcut, word-level reversal, anti-diagonal traceback storage ----------
+
+def test_exact_and_nearly_exact_clips_at_every_offset():
+    # Exact clips skip the reverse pass (sw_mid_kernel's perfect-diagonal shortcut); clips with one substitution, one N, a
+    # lower-case base or an indel must not.  Offsets 0..40 and lengths 1..70 put the alignment's ends on every position of
+    # the packed words (the reversed prefixes are written eight codes at a time, the first seven positions one by one).
+    import random
+    rng = random.Random(77)
+    qs, ts = [], []
+    for length in list(range(1, 41)) + [47, 48, 49, 56, 63, 64, 65, 70]:
+        for off in (0, 1, 2, 3, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 40):
+            w = pairgen.rand_dna(rng, off + length + rng.randint(0, 50))
+            clip = w[off:off + length]
+            variants = [clip, clip.lower()]
+            if length >= 3:
+                mid = length // 2
+                variants.append(clip[:mid] + ("A" if clip[mid] != "A" else "C") + clip[mid + 1:])      # one substitution
+                variants.append(clip[:mid] + "N" + clip[mid + 1:])                                      # an N pair scores 0
+                variants.append(clip[:mid] + clip[mid + 1:])                                            # deletion
+                variants.append(clip[:mid] + "G" + clip[mid:])                                          # insertion
+            for v in variants:
+                qs.append(w.encode()); ts.append(v.encode())
+                qs.append(v.encode()); ts.append(w.encode())          # roles swapped: long target, short query
+    # tandem repeats: several perfect diagonals end in the same column / row
+    for unit_len in (3, 5, 8, 13):
+        u = pairgen.rand_dna(rng, unit_len)
+        for qrep, trep in ((6, 2), (2, 6), (4, 4), (7, 3)):
+            qs.append((pairgen.rand_dna(rng, 5) + u * qrep).encode()); ts.append((u * trep + pairgen.rand_dna(rng, 4)).encode())
+    for scoring in ((2, -8, 6, 1), (2, -3, 10, 1), (5, -4, 8, 2), (1, -1, 1, 1)):
+        m, x, go, ge = scoring
+        res = batch.sw_align_batch(qs, ts, m, x, go, ge)
+        ref = O.oracle_sw(qs, ts, m, x, go, ge)
+        compare(qs, ts, res, ref, "exact clips " + str(scoring))
+
+
+def test_diagonal_shortcut_equals_the_reverse_pass(monkeypatch):
+    q, t, prm = workloads.remap_windows(6000, seed=41)
+    a = batch.sw_align_batch(q, t, **prm)
+    monkeypatch.setenv("DB200_SW_NO_DIAG_SHORTCUT", "1")
+    b = batch.sw_align_batch(q, t, **prm)
+    assert np.array_equal(a.fixed, b.fixed) and np.array_equal(a.cigar, b.cigar) and np.array_equal(a.cigar_off, b.cigar_off)
